@@ -1,0 +1,279 @@
+/*
+ * b200pt.h -- C ABI of the B200-native wavefront path tracer (libb200pt.so)
+ *
+ * This is the drop-in boundary for ONE hot path of Mitsuba 3: the `path`
+ * integrator loop and its PRB adjoint together with everything they call
+ * down to the ray/triangle tests. Each entry point
+ * names the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *   - plain C, opaque handles, POD descriptors, no C++/torch types;
+ *   - every function returns a b200pt_status (0 = ok); the message of the
+ *     last failure on the calling thread is b200pt_last_error();
+ *   - the caller owns every host buffer it passes; the library copies what
+ *     it needs during the call and owns all device memory;
+ *   - "host" pointers are ordinary (ideally pinned) CPU memory, "device"
+ *     pointers are CUDA device pointers on the scene's device;
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with B200PT_ERR_CUDA.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_ABI_VERSION 1
+
+typedef enum b200pt_status {
+    B200PT_OK              = 0,
+    B200PT_ERR_INVALID     = 1, /* bad argument / inconsistent descriptor   */
+    B200PT_ERR_CUDA        = 2, /* CUDA runtime failure or no device        */
+    B200PT_ERR_UNSUPPORTED = 3, /* feature outside the hot-path scope       */
+    B200PT_ERR_NOMEM       = 4
+} b200pt_status;
+
+/* ------------------------------------------------------------------------
+ * Scene description (host side, POD). Mirrors what the plugin extracts from
+ * the live Mitsuba objects: packed meshes (mesh_utils.h:19-46), BSDF /
+ * emitter parameters as seen by mi.traverse(), sensor + film + rfilter.
+ * ---------------------------------------------------------------------- */
+
+/* Texture: constant `rgb`/float value or a raw float32 `bitmap`
+ * (src/textures/bitmap.cpp:496-519, drjit/texture_impl.h:87-205). */
+enum { B200PT_TEX_CONST = 0, B200PT_TEX_BITMAP = 1 };
+enum { B200PT_WRAP_REPEAT = 0, B200PT_WRAP_MIRROR = 1, B200PT_WRAP_CLAMP = 2 };
+enum { B200PT_FILTER_BILINEAR = 0, B200PT_FILTER_NEAREST = 1 };
+
+typedef struct b200pt_texture {
+    int32_t kind;           /* B200PT_TEX_*                                 */
+    int32_t channels;       /* 1 or 3                                       */
+    float   value[3];       /* B200PT_TEX_CONST (channels==1: value[0])     */
+    int32_t width, height;  /* B200PT_TEX_BITMAP                            */
+    const float *data;      /* host, height*width*channels, row-major       */
+    int32_t wrap;           /* B200PT_WRAP_*                                */
+    int32_t filter;         /* B200PT_FILTER_*                              */
+    float   to_uv[9];       /* row-major 3x3 uv transform (identity default)*/
+    int32_t differentiable; /* !=0: PRB accumulates a gradient buffer       */
+} b200pt_texture;
+
+/* BSDF models on the hot path. */
+enum {
+    B200PT_BSDF_DIFFUSE    = 0, /* src/bsdfs/diffuse.cpp    */
+    B200PT_BSDF_CONDUCTOR  = 1, /* src/bsdfs/conductor.cpp  */
+    B200PT_BSDF_DIELECTRIC = 2, /* src/bsdfs/dielectric.cpp */
+    B200PT_BSDF_PRINCIPLED = 3  /* src/bsdfs/principled.cpp */
+};
+
+/* Texture slots (indices into b200pt_bsdf::tex). */
+enum {
+    /* diffuse */
+    B200PT_SLOT_REFLECTANCE = 0,
+    /* conductor */
+    B200PT_SLOT_ETA = 0, B200PT_SLOT_K = 1, B200PT_SLOT_SPEC_REFL = 2,
+    /* dielectric */
+    B200PT_SLOT_D_SPEC_REFL = 0, B200PT_SLOT_D_SPEC_TRANS = 1,
+    /* principled (principled.cpp:190-330) */
+    B200PT_SLOT_P_BASE_COLOR = 0, B200PT_SLOT_P_ROUGHNESS = 1,
+    B200PT_SLOT_P_ANISOTROPIC = 2, B200PT_SLOT_P_METALLIC = 3,
+    B200PT_SLOT_P_SPEC_TRANS = 4, B200PT_SLOT_P_SPECULAR = 5,
+    B200PT_SLOT_P_SPEC_TINT = 6, B200PT_SLOT_P_SHEEN = 7,
+    B200PT_SLOT_P_SHEEN_TINT = 8, B200PT_SLOT_P_FLATNESS = 9,
+    B200PT_SLOT_P_CLEARCOAT = 10, B200PT_SLOT_P_CLEARCOAT_GLOSS = 11,
+    B200PT_MAX_SLOTS = 12
+};
+
+/* Principled feature mask == the m_has_* booleans (principledhelpers.h). */
+enum {
+    B200PT_P_HAS_CLEARCOAT = 1u << 0, B200PT_P_HAS_SHEEN = 1u << 1,
+    B200PT_P_HAS_SPEC_TRANS = 1u << 2, B200PT_P_HAS_METALLIC = 1u << 3,
+    B200PT_P_HAS_SPEC_TINT = 1u << 4, B200PT_P_HAS_SHEEN_TINT = 1u << 5,
+    B200PT_P_HAS_ANISOTROPIC = 1u << 6, B200PT_P_HAS_FLATNESS = 1u << 7,
+    B200PT_P_ETA_SPECULAR = 1u << 8  /* eta given explicitly, not `specular` */
+};
+
+typedef struct b200pt_bsdf {
+    int32_t  type;                  /* B200PT_BSDF_*                        */
+    int32_t  twosided;              /* wrapped in `twosided` (twosided.cpp) */
+    int32_t  tex[B200PT_MAX_SLOTS]; /* texture index per slot, -1 = unset   */
+    float    eta;                   /* dielectric/principled: int_ior/ext_ior*/
+    float    spec_srate;            /* principled: main_specular_sampling_rate */
+    float    clearcoat_srate;       /* principled: clearcoat_sampling_rate  */
+    float    diff_refl_srate;       /* principled: diffuse_reflectance_sampling_rate */
+    uint32_t flags;                 /* B200PT_P_*                           */
+} b200pt_bsdf;
+
+/* How an emitter's shape is sampled by position
+ * (rectangle.cpp:159-179, mesh.cpp:1662-1712). */
+enum { B200PT_SAMPLING_NONE = 0, B200PT_SAMPLING_RECTANGLE = 1, B200PT_SAMPLING_MESH = 2 };
+
+/* Layout bits of the packed records (mesh_utils.h:40-46). */
+enum { B200PT_LAYOUT_NORMALS = 1, B200PT_LAYOUT_TANGENTS = 2, B200PT_LAYOUT_TEXCOORDS = 4 };
+
+typedef struct b200pt_shape {
+    uint32_t n_vertices, n_faces;
+    const float    *vertices; /* n_vertices*8: pos3, normal3, uv2            */
+    const uint32_t *faces;    /* n_faces*4: v0, v1, v2, flags                */
+    uint32_t layout;          /* B200PT_LAYOUT_*                             */
+    int32_t  bsdf;            /* index into b200pt_scene_desc::bsdfs         */
+    int32_t  emitter;         /* index into ::emitters, -1 = not emissive    */
+    int32_t  sampling;        /* B200PT_SAMPLING_*                           */
+    float    to_world[16];    /* row-major; B200PT_SAMPLING_RECTANGLE only   */
+    float    frame_n[3];      /* rectangle m_frame.n                         */
+    float    inv_area;        /* rectangle m_inv_surface_area                */
+} b200pt_shape;
+
+/* Area light (src/emitters/area.cpp). */
+typedef struct b200pt_emitter {
+    int32_t shape;        /* index into ::shapes                            */
+    int32_t radiance_tex; /* texture index (constant rgb on the hot path)   */
+    float   sampling_weight;
+} b200pt_emitter;
+
+/* Reconstruction filter of the film (imageblock.cpp:192-574). */
+enum {
+    B200PT_RFILTER_BOX = 0,
+    B200PT_RFILTER_GAUSSIAN = 1,      /* analytic, polynomial form (gaussian.cpp:57-96; llvm/scalar) */
+    B200PT_RFILTER_GAUSSIAN_EXP2 = 2, /* analytic, exp2 form (gaussian.cpp:98-101; cuda)             */
+    B200PT_RFILTER_GAUSSIAN_TABLE = 3 /* 31-bin table (rfilter.h:70-79; scalar variants only)        */
+};
+
+/* Perspective sensor + hdrfilm (perspective.cpp:239-279, sensor.h:234-269). */
+typedef struct b200pt_sensor {
+    float    sample_to_camera[16]; /* row-major, inverse perspective_projection */
+    float    to_world[16];         /* row-major camera-to-world                 */
+    float    near_clip, far_clip;
+    uint32_t film_size[2];         /* width, height                             */
+    uint32_t crop_size[2];
+    uint32_t crop_offset[2];
+    int32_t  rfilter;              /* B200PT_RFILTER_*                          */
+    float    rfilter_stddev;       /* gaussian (default 0.5; radius = 4 stddev) */
+    uint32_t base_seed;            /* sampler `seed` property (sampler.cpp:133) */
+} b200pt_sensor;
+
+typedef struct b200pt_scene_desc {
+    uint32_t abi_version; /* B200PT_ABI_VERSION */
+    uint32_t n_shapes;   const b200pt_shape   *shapes;
+    uint32_t n_bsdfs;    const b200pt_bsdf    *bsdfs;
+    uint32_t n_emitters; const b200pt_emitter *emitters;
+    uint32_t n_textures; const b200pt_texture *textures;
+    b200pt_sensor sensor;
+} b200pt_scene_desc;
+
+/* Integrator properties (integrator.cpp:26-29,130-146,539-550) plus the
+ * pixel-tile shard this process renders. */
+typedef struct b200pt_render_params {
+    uint32_t seed;          /* `seed` argument of Integrator::render          */
+    uint32_t spp;           /* samples per pixel                              */
+    int32_t  max_depth;     /* -1 = unbounded                                 */
+    int32_t  rr_depth;      /* default 5                                      */
+    int32_t  hide_emitters;
+    uint32_t shard_rank;    /* this process' rank in [0, shard_count)         */
+    uint32_t shard_count;   /* 1 = whole frame                                */
+    uint32_t tile_size;     /* pixel-tile edge for sharding (default 32)      */
+    uint32_t chunk_lanes;   /* wavefront lanes per pass, 0 = library default  */
+    int32_t  prb;           /* 0 = `path` estimator, 1 = `prb` primal rules   */
+} b200pt_render_params;
+
+/* Counters of the last render call on a scene (measurement). */
+typedef struct b200pt_stats {
+    uint64_t samples;          /* camera samples traced                      */
+    uint64_t bounces;          /* loop iterations over all samples           */
+    uint64_t shadow_rays;      /* any-hit queries issued                     */
+    uint64_t kernel_launches;  /* kernels of this library launched           */
+    double   device_ms;        /* CUDA-event time of the whole call          */
+    double   trace_ms;         /* CUDA-event time inside the closest-hit kernel */
+    uint64_t trace_launches;
+    uint64_t trace_rays;       /* closest-hit rays processed                 */
+} b200pt_stats;
+
+typedef struct b200pt_scene b200pt_scene;
+
+/* ---- library ---------------------------------------------------------- */
+uint32_t    b200pt_abi_version(void);
+const char *b200pt_last_error(void);
+/* Number of visible CUDA devices (0 without a driver/GPU). */
+int         b200pt_device_count(void);
+
+/* ---- scene life cycle: replaces Scene::Scene accel build (scene.cpp:93,
+ *      scene_optix.inl:446) for triangle meshes ------------------------- */
+b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device,
+                                  b200pt_scene **out);
+void          b200pt_scene_destroy(b200pt_scene *scene);
+/* Parameter update after an optimiser step (SceneParameters.update ->
+ * parameters_changed, util.py:272-338): overwrite texture `tex` with `n`
+ * floats (3/1 for constants, h*w*c for bitmaps). */
+b200pt_status b200pt_scene_update_texture(b200pt_scene *scene, uint32_t tex,
+                                          const float *host_data, size_t n);
+
+/* ---- forward render: replaces SamplingIntegrator::render (JIT branch,
+ *      integrator.cpp:275-389) + PathIntegrator::sample (path.cpp:94-346)
+ *      + ImageBlock::put + HDRFilm::develop ------------------------------ */
+/* Host entry point (what the plugin calls): out_host is H*W*3 floats. */
+b200pt_status b200pt_render(b200pt_scene *scene, const b200pt_render_params *p,
+                            float *out_host);
+/* Device entry points for multi-GPU: accumulate this shard's samples into a
+ * raw film block (H*W*4: R,G,B,weight) owned by the caller, then develop
+ * (hdrfilm.cpp:393) after the caller has all-reduced the block. */
+b200pt_status b200pt_render_accumulate(b200pt_scene *scene,
+                                       const b200pt_render_params *p,
+                                       float *film_device /* H*W*4, zeroed by caller */,
+                                       void *cuda_stream);
+b200pt_status b200pt_develop(b200pt_scene *scene, const float *film_device,
+                             float *out_device /* H*W*3 */, void *cuda_stream);
+
+/* ---- adjoint: replaces RBIntegrator.render_backward (common.py:625-783)
+ *      + PRBIntegrator.sample Backward mode (prb.py:68-339) -------------- */
+/* grad_in_host: H*W*3 (dLoss/dImage). Gradients are ACCUMULATED into the
+ * per-texture gradient buffers of the scene (dr.grad accumulation). */
+b200pt_status b200pt_render_backward(b200pt_scene *scene,
+                                     const b200pt_render_params *p,
+                                     const float *grad_in_host);
+b200pt_status b200pt_render_backward_device(b200pt_scene *scene,
+                                            const b200pt_render_params *p,
+                                            const float *grad_in_device,
+                                            void *cuda_stream);
+b200pt_status b200pt_grad_zero(b200pt_scene *scene);
+/* Copy the gradient of differentiable texture `tex` to the host. */
+b200pt_status b200pt_grad_read(b200pt_scene *scene, uint32_t tex,
+                               float *host_out, size_t n);
+/* Device view of all gradient buffers as one flat fp32 array (for one fused
+ * NCCL all-reduce); offsets per texture via b200pt_grad_offset. */
+b200pt_status b200pt_grad_device_view(b200pt_scene *scene, float **ptr, size_t *n);
+b200pt_status b200pt_grad_offset(b200pt_scene *scene, uint32_t tex,
+                                 size_t *offset, size_t *n);
+
+/* ---- operators on the path, exposed for parity tests ------------------ */
+/* Scene::ray_intersect_preliminary (scene.cpp:216): n rays, rays_host =
+ * n*7 floats (o3, d3, maxt). Outputs: t (inf on miss), prim_uv n*2,
+ * prim_index (within shape), shape_index (-1 on miss). */
+b200pt_status b200pt_ray_intersect(b200pt_scene *scene, uint32_t n,
+                                   const float *rays_host, float *t_out,
+                                   float *uv_out, uint32_t *prim_out,
+                                   int32_t *shape_out);
+/* Scene::ray_test (scene.cpp:232): hit_out[i] = 1 if occluded. */
+b200pt_status b200pt_ray_test(b200pt_scene *scene, uint32_t n,
+                              const float *rays_host, uint8_t *hit_out);
+/* BSDF::eval_pdf_sample (bsdf.cpp:21-31) for n queries on BSDF `bsdf`:
+ * in_host = n*10 floats (wi3, wo3, uv2 ... see layout below),
+ *   [0..2] si.wi (local), [3..5] wo (local), [6..7] si.uv,
+ *   [8] sample1, [9..10] sample2  -> stride 11
+ * out_host = n*14 floats:
+ *   [0..2] eval (f*cos), [3] pdf, [4..6] bs.wo, [7] bs.pdf, [8] bs.eta,
+ *   [9] sampled_type (as float bits of uint32), [10..12] weight, [13] sampled_component */
+b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *scene, uint32_t bsdf,
+                                          uint32_t n, const float *in_host,
+                                          float *out_host);
+
+/* ---- measurement ------------------------------------------------------ */
+b200pt_status b200pt_get_stats(b200pt_scene *scene, b200pt_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

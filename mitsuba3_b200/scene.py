@@ -1,0 +1,567 @@
+"""Host-side scene description: the subset of ``mi.load_dict`` that the hot
+path needs (what the plugin extracts from live Mitsuba
+objects), and its conversion to the POD ``b200pt_scene_desc``.
+
+Supported plugin types (same property names as the reference):
+  scene; integrators ``path`` / ``prb`` (max_depth, rr_depth, hide_emitters);
+  sensor ``perspective`` (to_world, fov, fov_axis, near_clip, far_clip) with
+  ``hdrfilm`` (width, height, crop_*, rfilter ``gaussian``/``box``) and
+  ``independent`` sampler (sample_count, seed); shapes ``rectangle`` / ``cube``
+  (src/shapes/rectangle.cpp, cube.cpp) and ``mesh`` (packed arrays, as produced
+  by the host's loaders); BSDFs ``diffuse`` / ``conductor`` / ``dielectric`` /
+  ``principled`` / ``twosided``; emitter ``area``; textures ``rgb`` / float /
+  ``bitmap`` (raw float32 data); ``ref``.
+
+Everything else (XML, OBJ/PLY loaders, spectra, other plugins) stays in the
+host Mitsuba -- see INTEGRATION.md for the extraction from live objects.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from . import abi
+from .transform import Transform4f, f32, fma, parse_fov, perspective_sample_to_camera, _cross, _normalize, _sqnorm
+
+# include/mitsuba/render/ior.h:24-48
+IOR_TABLE = {
+    "vacuum": 1.0, "helium": 1.000036, "hydrogen": 1.000132, "air": 1.000277,
+    "carbon dioxide": 1.00045, "water": 1.3330, "acetone": 1.36, "ethanol": 1.361,
+    "carbon tetrachloride": 1.461, "glycerol": 1.4729, "benzene": 1.501,
+    "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458,
+    "pyrex": 1.470, "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046,
+    "sodium chloride": 1.544, "amber": 1.55, "pet": 1.5750, "diamond": 2.419,
+}
+
+
+def lookup_ior(v, default):
+    v = default if v is None else v
+    if isinstance(v, str):
+        return float(f32(IOR_TABLE[v.lower()]))
+    return float(v)
+
+
+@dataclass
+class TextureData:
+    name: str
+    kind: int = abi.TEX_CONST
+    channels: int = 3
+    value: np.ndarray = field(default_factory=lambda: np.zeros(3, f32))
+    data: np.ndarray | None = None           # (H, W, C) float32
+    wrap: int = abi.WRAP_REPEAT
+    filter: int = abi.FILTER_BILINEAR
+    to_uv: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=f32))
+    differentiable: bool = True
+
+    @property
+    def size(self) -> int:
+        return int(self.data.size) if self.kind == abi.TEX_BITMAP else self.channels
+
+    def array(self) -> np.ndarray:
+        return self.data if self.kind == abi.TEX_BITMAP else self.value[: self.channels]
+
+
+@dataclass
+class BsdfData:
+    id: str
+    type: int
+    twosided: bool = False
+    tex: list = field(default_factory=lambda: [-1] * abi.MAX_SLOTS)
+    eta: float = 1.0
+    spec_srate: float = 1.0
+    clearcoat_srate: float = 1.0
+    diff_refl_srate: float = 1.0
+    flags: int = 0
+
+
+@dataclass
+class ShapeData:
+    id: str
+    vertices: np.ndarray      # (V, 8) float32: pos3, normal3, uv2
+    faces: np.ndarray         # (F, 4) uint32: v0 v1 v2 flags
+    layout: int
+    bsdf: int
+    emitter: int = -1
+    sampling: int = abi.SAMPLING_NONE
+    to_world: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=f32))
+    frame_n: np.ndarray = field(default_factory=lambda: np.zeros(3, f32))
+    inv_area: float = 0.0
+
+
+@dataclass
+class EmitterData:
+    shape: int
+    radiance_tex: int
+    sampling_weight: float = 1.0
+
+
+@dataclass
+class SensorData:
+    sample_to_camera: np.ndarray
+    to_world: np.ndarray
+    near_clip: float
+    far_clip: float
+    film_size: tuple
+    crop_size: tuple
+    crop_offset: tuple
+    rfilter: int
+    rfilter_stddev: float
+    base_seed: int
+    sample_count: int
+    x_fov: float
+
+
+class Scene:
+    """Parsed scene + the parameter map that plays the role of ``mi.traverse``."""
+
+    def __init__(self):
+        self.shapes: list[ShapeData] = []
+        self.bsdfs: list[BsdfData] = []
+        self.textures: list[TextureData] = []
+        self.emitters: list[EmitterData] = []
+        self.sensor: SensorData | None = None
+        self.integrator: dict[str, Any] = {"type": "path", "max_depth": -1, "rr_depth": 5, "hide_emitters": False}
+        self._handle = None      # lazily created device scene (mitsuba3_b200.integrators)
+
+    # ---- parameters (mi.traverse analogue) ----------------------------------
+    def parameters(self) -> dict[str, int]:
+        return {t.name: i for i, t in enumerate(self.textures)}
+
+    @property
+    def film_shape(self):
+        return (self.sensor.crop_size[1], self.sensor.crop_size[0], 3)
+
+    @property
+    def n_triangles(self) -> int:
+        return int(sum(s.faces.shape[0] for s in self.shapes))
+
+    # ---- POD descriptor -----------------------------------------------------
+    def build_desc(self):
+        """Returns (SceneDesc, keepalive) -- keepalive owns every buffer the
+        descriptor points to and must outlive the C call."""
+        keep = []
+        texs = (abi.Texture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            ct = texs[i]
+            ct.kind, ct.channels = t.kind, t.channels
+            v = np.zeros(3, f32); v[: t.channels] = np.asarray(t.value, f32)[: t.channels]
+            ct.value = (C.c_float * 3)(*v.tolist())
+            if t.kind == abi.TEX_BITMAP:
+                d = np.ascontiguousarray(t.data, dtype=f32)
+                keep.append(d)
+                ct.height, ct.width = d.shape[0], d.shape[1]
+                ct.data = d.ctypes.data_as(C.POINTER(C.c_float))
+            ct.wrap, ct.filter = t.wrap, t.filter
+            ct.to_uv = (C.c_float * 9)(*np.asarray(t.to_uv, f32).reshape(9).tolist())
+            ct.differentiable = int(t.differentiable)
+        bsdfs = (abi.Bsdf * max(1, len(self.bsdfs)))()
+        for i, b in enumerate(self.bsdfs):
+            cb = bsdfs[i]
+            cb.type, cb.twosided = b.type, int(b.twosided)
+            cb.tex = (C.c_int32 * abi.MAX_SLOTS)(*b.tex)
+            cb.eta, cb.spec_srate, cb.clearcoat_srate, cb.diff_refl_srate = b.eta, b.spec_srate, b.clearcoat_srate, b.diff_refl_srate
+            cb.flags = b.flags
+        shapes = (abi.Shape * max(1, len(self.shapes)))()
+        for i, s in enumerate(self.shapes):
+            cs = shapes[i]
+            v = np.ascontiguousarray(s.vertices, dtype=f32); f = np.ascontiguousarray(s.faces, dtype=np.uint32)
+            keep += [v, f]
+            cs.n_vertices, cs.n_faces = v.shape[0], f.shape[0]
+            cs.vertices = v.ctypes.data_as(C.POINTER(C.c_float))
+            cs.faces = f.ctypes.data_as(C.POINTER(C.c_uint32))
+            cs.layout, cs.bsdf, cs.emitter, cs.sampling = s.layout, s.bsdf, s.emitter, s.sampling
+            cs.to_world = (C.c_float * 16)(*np.asarray(s.to_world, f32).reshape(16).tolist())
+            cs.frame_n = (C.c_float * 3)(*np.asarray(s.frame_n, f32).tolist())
+            cs.inv_area = float(s.inv_area)
+        ems = (abi.Emitter * max(1, len(self.emitters)))()
+        for i, e in enumerate(self.emitters):
+            ems[i].shape, ems[i].radiance_tex, ems[i].sampling_weight = e.shape, e.radiance_tex, e.sampling_weight
+        d = abi.SceneDesc()
+        d.abi_version = abi.ABI_VERSION
+        d.n_shapes, d.shapes = len(self.shapes), shapes
+        d.n_bsdfs, d.bsdfs = len(self.bsdfs), bsdfs
+        d.n_emitters, d.emitters = len(self.emitters), ems
+        d.n_textures, d.textures = len(self.textures), texs
+        se = self.sensor
+        d.sensor.sample_to_camera = (C.c_float * 16)(*np.asarray(se.sample_to_camera, f32).reshape(16).tolist())
+        d.sensor.to_world = (C.c_float * 16)(*np.asarray(se.to_world, f32).reshape(16).tolist())
+        d.sensor.near_clip, d.sensor.far_clip = se.near_clip, se.far_clip
+        d.sensor.film_size = (C.c_uint32 * 2)(*se.film_size)
+        d.sensor.crop_size = (C.c_uint32 * 2)(*se.crop_size)
+        d.sensor.crop_offset = (C.c_uint32 * 2)(*se.crop_offset)
+        d.sensor.rfilter, d.sensor.rfilter_stddev, d.sensor.base_seed = se.rfilter, se.rfilter_stddev, se.base_seed
+        keep += [texs, bsdfs, shapes, ems]
+        return d, keep
+
+
+# ---------------------------------------------------------------------------
+# dict parser
+# ---------------------------------------------------------------------------
+_WRAP = {"repeat": abi.WRAP_REPEAT, "mirror": abi.WRAP_MIRROR, "clamp": abi.WRAP_CLAMP}
+_FILT = {"bilinear": abi.FILTER_BILINEAR, "nearest": abi.FILTER_NEAREST}
+
+
+def _as_transform(t) -> Transform4f:
+    if t is None:
+        return Transform4f()
+    if isinstance(t, Transform4f):
+        return t
+    return Transform4f(np.asarray(t, f32).reshape(4, 4))
+
+
+class _Parser:
+    def __init__(self):
+        self.scene = Scene()
+        self.named_bsdfs: dict[str, int] = {}
+
+    # -- textures ------------------------------------------------------------
+    def texture(self, name: str, spec, channels: int, default=None) -> int:
+        if spec is None:
+            if default is None:
+                return -1
+            spec = default
+        t = TextureData(name=name, channels=channels)
+        if isinstance(spec, (int, float)):
+            t.value = np.full(3, spec, f32); t.name = name + ".value"
+        elif isinstance(spec, (list, tuple, np.ndarray)):
+            v = np.asarray(spec, f32).reshape(-1)
+            t.value = np.full(3, v[0], f32) if v.size == 1 else v[:3].astype(f32)
+            t.name = name + ".value"
+        elif isinstance(spec, dict):
+            ty = spec.get("type")
+            if ty == "rgb":
+                v = np.asarray(spec["value"], f32).reshape(-1)
+                t.value = np.full(3, v[0], f32) if v.size == 1 else v[:3].astype(f32)
+                t.name = name + ".value"
+            elif ty == "bitmap":
+                data = np.asarray(spec["data"], f32)
+                if data.ndim == 2:
+                    data = data[:, :, None]
+                if not spec.get("raw", True):
+                    raise NotImplementedError("bitmap textures must be raw float data (sRGB decoding stays in the host)")
+                if channels == 3 and data.shape[2] == 1:
+                    pass  # luminance broadcast happens at lookup
+                t.kind, t.data, t.channels = abi.TEX_BITMAP, np.ascontiguousarray(data), data.shape[2]
+                t.wrap = _WRAP[spec.get("wrap_mode", "repeat")]
+                t.filter = _FILT[spec.get("filter_type", "bilinear")]
+                if "to_uv" in spec:
+                    t.to_uv = np.asarray(spec["to_uv"], f32).reshape(3, 3)
+                t.name = name + ".data"
+            else:
+                raise NotImplementedError(f"texture type {ty!r} is outside the hot-path scope")
+        else:
+            raise TypeError(f"cannot interpret texture {spec!r}")
+        self.scene.textures.append(t)
+        return len(self.scene.textures) - 1
+
+    # -- bsdfs ---------------------------------------------------------------
+    def bsdf(self, bid: str, d: dict, twosided=False) -> int:
+        ty = d["type"]
+        if ty == "ref":
+            return self.named_bsdfs[d["id"]]
+        if ty == "twosided":
+            inner = d.get("bsdf") or next(v for k, v in d.items() if isinstance(v, dict) and k != "type")
+            return self.bsdf(bid, inner, twosided=True)
+        b = BsdfData(id=bid, type=-1, twosided=twosided)
+        if ty == "diffuse":
+            b.type = abi.BSDF_DIFFUSE
+            b.tex[abi.SLOT_REFLECTANCE] = self.texture(f"{bid}.reflectance", d.get("reflectance"), 3, 0.5)
+        elif ty == "conductor":
+            b.type = abi.BSDF_CONDUCTOR
+            mat = d.get("material")
+            if mat not in (None, "none") and ("eta" not in d):
+                raise NotImplementedError("conductor `material` presets need the host's spectral data; pass rgb eta/k")
+            eta, k = (d.get("eta", 0.0), d.get("k", 1.0))
+            b.tex[abi.SLOT_ETA] = self.texture(f"{bid}.eta", eta, 3)
+            b.tex[abi.SLOT_K] = self.texture(f"{bid}.k", k, 3)
+            b.tex[abi.SLOT_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3, 1.0)
+        elif ty == "dielectric":
+            b.type = abi.BSDF_DIELECTRIC
+            b.eta = float(f32(f32(lookup_ior(d.get("int_ior"), "bk7")) / f32(lookup_ior(d.get("ext_ior"), "air"))))
+            b.tex[abi.SLOT_D_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3)
+            b.tex[abi.SLOT_D_SPEC_TRANS] = self.texture(f"{bid}.specular_transmittance", d.get("specular_transmittance"), 3)
+        elif ty == "principled":
+            self._principled(b, bid, d)
+        else:
+            raise NotImplementedError(f"BSDF {ty!r} is outside the hot-path scope (SURVEY.md 8(a))")
+        self.scene.bsdfs.append(b)
+        return len(self.scene.bsdfs) - 1
+
+    def _principled(self, b: BsdfData, bid: str, d: dict):
+        # principled.cpp:190-330 constructor
+        b.type = abi.BSDF_PRINCIPLED
+        def has(k): return k in d
+        def active(k, dflt):
+            # principledhelpers.h:122-132 get_flag: absent -> False; constant 0 -> False
+            if k not in d:
+                return False
+            v = d[k]
+            if isinstance(v, (int, float)):
+                return float(v) != 0.0
+            return True
+        b.tex[abi.SLOT_P_BASE_COLOR] = self.texture(f"{bid}.base_color", d.get("base_color"), 3, 0.5)
+        b.tex[abi.SLOT_P_ROUGHNESS] = self.texture(f"{bid}.roughness", d.get("roughness"), 1, 0.5)
+        flags = 0
+        if active("anisotropic", 0.0): flags |= abi.P_HAS_ANISOTROPIC
+        if active("spec_trans", 0.0): flags |= abi.P_HAS_SPEC_TRANS
+        if active("sheen", 0.0): flags |= abi.P_HAS_SHEEN
+        if active("sheen_tint", 0.0): flags |= abi.P_HAS_SHEEN_TINT
+        if active("flatness", 0.0): flags |= abi.P_HAS_FLATNESS
+        if active("spec_tint", 0.0): flags |= abi.P_HAS_SPEC_TINT
+        if active("metallic", 0.0): flags |= abi.P_HAS_METALLIC
+        if active("clearcoat", 0.0): flags |= abi.P_HAS_CLEARCOAT
+        b.tex[abi.SLOT_P_ANISOTROPIC] = self.texture(f"{bid}.anisotropic", d.get("anisotropic"), 1, 0.0)
+        b.tex[abi.SLOT_P_SPEC_TRANS] = self.texture(f"{bid}.spec_trans", d.get("spec_trans"), 1, 0.0)
+        b.tex[abi.SLOT_P_SHEEN] = self.texture(f"{bid}.sheen", d.get("sheen"), 1, 0.0)
+        b.tex[abi.SLOT_P_SHEEN_TINT] = self.texture(f"{bid}.sheen_tint", d.get("sheen_tint"), 1, 0.0)
+        b.tex[abi.SLOT_P_FLATNESS] = self.texture(f"{bid}.flatness", d.get("flatness"), 1, 0.0)
+        b.tex[abi.SLOT_P_SPEC_TINT] = self.texture(f"{bid}.spec_tint", d.get("spec_tint"), 1, 0.0)
+        b.tex[abi.SLOT_P_METALLIC] = self.texture(f"{bid}.metallic", d.get("metallic"), 1, 0.0)
+        b.tex[abi.SLOT_P_CLEARCOAT] = self.texture(f"{bid}.clearcoat", d.get("clearcoat"), 1, 0.0)
+        b.tex[abi.SLOT_P_CLEARCOAT_GLOSS] = self.texture(f"{bid}.clearcoat_gloss", d.get("clearcoat_gloss"), 1, 0.0)
+        if has("eta") and has("specular"):
+            raise ValueError("Specified an invalid index of refraction property \"eta\" and \"specular\"")
+        if has("eta"):
+            flags |= abi.P_ETA_SPECULAR
+            eta = float(d["eta"])
+            # principled.cpp: eta == 1 is not plausible -> 1.001
+            if eta == 1.0:
+                eta = 1.001
+            b.eta = eta
+            b.tex[abi.SLOT_P_SPECULAR] = -1
+        else:
+            spec = float(d.get("specular", 0.5))
+            # eta = 2 / (1 - sqrt(0.08 * specular)) - 1
+            b.eta = float(f32(2.0) * f32(1.0 / (1.0 - np.sqrt(0.08 * spec))) - f32(1.0))
+            b.tex[abi.SLOT_P_SPECULAR] = self.texture(f"{bid}.specular", spec, 1)
+        b.spec_srate = float(d.get("main_specular_sampling_rate", 1.0))
+        b.clearcoat_srate = float(d.get("clearcoat_sampling_rate", 1.0))
+        b.diff_refl_srate = float(d.get("diffuse_reflectance_sampling_rate", 1.0))
+        b.flags = flags
+
+    # -- shapes --------------------------------------------------------------
+    def shape(self, sid: str, d: dict):
+        ty = d["type"]
+        bs = d.get("bsdf")
+        if bs is None:
+            for k, v in d.items():
+                if isinstance(v, dict) and v.get("type") in ("diffuse", "conductor", "dielectric", "principled", "twosided", "ref") and k != "emitter":
+                    bs = v
+                    break
+        if bs is None:
+            bs = {"type": "diffuse"}     # Shape default BSDF (shape.cpp: diffuse 0.5)
+        bidx = self.bsdf(f"{sid}.bsdf", bs)
+        to_world = _as_transform(d.get("to_world"))
+        flip = bool(d.get("flip_normals", False))
+        if ty == "rectangle":
+            sh = make_rectangle(sid, to_world, flip, bidx)
+        elif ty == "cube":
+            sh = make_cube(sid, to_world, flip, bidx)
+        elif ty == "mesh":
+            sh = make_mesh(sid, d, to_world, bidx)
+        else:
+            raise NotImplementedError(f"shape {ty!r}: only triangle meshes are on the hot path; "
+                                      "load it with the host Mitsuba and pass the packed records as type 'mesh'")
+        em = d.get("emitter")
+        if em is not None:
+            if em["type"] != "area":
+                raise NotImplementedError("only `area` emitters are on the hot path")
+            rad = self.texture(f"{sid}.emitter.radiance", em.get("radiance"), 3, 1.0)
+            if self.scene.textures[rad].kind != abi.TEX_CONST:
+                raise NotImplementedError("spatially varying area-light radiance is outside the hot path")
+            self.scene.emitters.append(EmitterData(shape=len(self.scene.shapes), radiance_tex=rad,
+                                                   sampling_weight=float(em.get("sampling_weight", 1.0))))
+            sh.emitter = len(self.scene.emitters) - 1
+            if sh.sampling == abi.SAMPLING_NONE:
+                sh.sampling = abi.SAMPLING_MESH
+        elif sh.sampling == abi.SAMPLING_RECTANGLE:
+            pass
+        self.scene.shapes.append(sh)
+
+    # -- sensor --------------------------------------------------------------
+    def sensor(self, d: dict):
+        if d["type"] != "perspective":
+            raise NotImplementedError("only the `perspective` sensor is on the hot path")
+        film = d.get("film", {"type": "hdrfilm"})
+        w, h = int(film.get("width", 768)), int(film.get("height", 576))
+        cw, ch = int(film.get("crop_width", w)), int(film.get("crop_height", h))
+        cx, cy = int(film.get("crop_offset_x", 0)), int(film.get("crop_offset_y", 0))
+        if film.get("sample_border", False):
+            raise NotImplementedError("sample_border is outside the hot-path scope")
+        rf = film.get("rfilter", {"type": "gaussian"})
+        if rf["type"] == "box":
+            rfilter, stddev = abi.RFILTER_BOX, 0.0
+        elif rf["type"] == "gaussian":
+            rfilter, stddev = abi.RFILTER_GAUSSIAN, float(rf.get("stddev", 0.5))
+        else:
+            raise NotImplementedError(f"rfilter {rf['type']!r} is outside the hot-path scope")
+        sampler = d.get("sampler", {"type": "independent"})
+        if sampler.get("type", "independent") != "independent":
+            raise NotImplementedError("only the `independent` sampler is on the hot path")
+        to_world = _as_transform(d.get("to_world"))
+        near, far = float(d.get("near_clip", 1e-2)), float(d.get("far_clip", 1e4))
+        fov = float(d.get("fov", 0.0)) if "fov" in d else None
+        if fov is None:
+            raise NotImplementedError("specify `fov` (focal_length parsing stays in the host)")
+        x_fov = float(f32(parse_fov(fov, d.get("fov_axis", "x"), w / h)))
+        s2c = perspective_sample_to_camera((w, h), (cw, ch), (cx, cy), x_fov, f32(near), f32(far))
+        self.scene.sensor = SensorData(
+            sample_to_camera=s2c, to_world=to_world.matrix.copy(), near_clip=float(f32(near)), far_clip=float(f32(far)),
+            film_size=(w, h), crop_size=(cw, ch), crop_offset=(cx, cy), rfilter=rfilter, rfilter_stddev=stddev,
+            base_seed=int(sampler.get("seed", 0)), sample_count=int(sampler.get("sample_count", 4)), x_fov=x_fov)
+
+    def parse(self, d: dict) -> Scene:
+        if d.get("type") != "scene":
+            raise ValueError("top-level dictionary must have type 'scene'")
+        # first pass: named BSDFs (so that refs resolve irrespective of order)
+        for k, v in d.items():
+            if isinstance(v, dict) and v.get("type") in ("diffuse", "conductor", "dielectric", "principled", "twosided"):
+                self.named_bsdfs[k] = self.bsdf(k, v)
+        for k, v in d.items():
+            if not isinstance(v, dict):
+                continue
+            ty = v.get("type")
+            if ty in ("path", "prb", "b200_path", "b200_prb"):
+                self.scene.integrator = {"type": "prb" if "prb" in ty else "path",
+                                         "max_depth": int(v.get("max_depth", 6 if "prb" in ty else -1)),
+                                         "rr_depth": int(v.get("rr_depth", 5)),
+                                         "hide_emitters": bool(v.get("hide_emitters", False))}
+            elif ty == "perspective":
+                self.sensor(v)
+            elif ty in ("rectangle", "cube", "mesh"):
+                self.shape(k, v)
+            elif ty in ("diffuse", "conductor", "dielectric", "principled", "twosided"):
+                pass
+            else:
+                raise NotImplementedError(f"plugin type {ty!r} is outside the hot-path scope (SURVEY.md 8)")
+        if self.scene.sensor is None:
+            raise ValueError("scene has no sensor")
+        return self.scene
+
+
+def load_dict(d: dict) -> Scene:
+    """Counterpart of ``mi.load_dict`` for the hot-path subset."""
+    return _Parser().parse(d)
+
+
+# ---------------------------------------------------------------------------
+# shape construction (mirrors rectangle.cpp:110-153, cube.cpp:61-113,
+# mesh_utils.cpp:103-133, mesh.cpp:1160-1200)
+# ---------------------------------------------------------------------------
+def _pack(positions, normals, uvs, to_world: Transform4f):
+    n = len(positions)
+    v = np.zeros((n, 8), f32)
+    for i in range(n):
+        v[i, 0:3] = to_world.point(positions[i])
+        nn = to_world.normal(normals[i])
+        il = f32(1) / np.sqrt(_sqnorm(nn), dtype=f32)
+        v[i, 3:6] = nn * (il if np.isfinite(il) else f32(1))
+        v[i, 6:8] = uvs[i]
+    return v
+
+
+def make_rectangle(sid, to_world: Transform4f, flip: bool, bsdf: int) -> ShapeData:
+    tw = to_world
+    if flip:
+        tw = tw @ Transform4f().scale([1, 1, -1])
+    pos = [[-1, -1, 0], [1, -1, 0], [-1, 1, 0], [1, 1, 0]]
+    nrm = [[0, 0, 1]] * 4
+    uv = [[0, 0], [1, 0], [0, 1], [1, 1]]
+    faces = np.array([[1, 2, 0, 0], [1, 3, 2, 0]], np.uint32)
+    verts = _pack(pos, nrm, uv, tw)
+    if tw.det3() < 0:
+        faces = faces[:, [2, 1, 0, 3]].copy()
+    n = _normalize(tw.normal([0, 0, 1]))
+    dp_du, dp_dv = tw.vector([2, 0, 0]), tw.vector([0, 2, 0])
+    area = np.sqrt(_sqnorm(_cross(dp_du, dp_dv)), dtype=f32)
+    # NOTE rectangle.cpp:159-166 samples with m_to_world (the un-flipped transform)
+    return ShapeData(id=sid, vertices=verts, faces=faces, layout=abi.LAYOUT_NORMALS | abi.LAYOUT_TEXCOORDS,
+                     bsdf=bsdf, sampling=abi.SAMPLING_RECTANGLE, to_world=to_world.matrix.copy(),
+                     frame_n=n.astype(f32), inv_area=float(f32(1) / area))
+
+
+def make_cube(sid, to_world: Transform4f, flip: bool, bsdf: int) -> ShapeData:
+    side_normals = [[0, -1, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [-1, 0, 0], [0, 0, -1]]
+    side_uv = [[0, 1], [1, 1], [1, 0], [0, 0]]
+    position_index = [1, 5, 4, 0, 3, 2, 6, 7, 1, 3, 7, 5, 5, 7, 6, 4, 4, 6, 2, 0, 3, 1, 0, 2]
+    corners = [[1.0 if c & 1 else -1.0, 1.0 if c & 2 else -1.0, 1.0 if c & 4 else -1.0] for c in range(8)]
+    pos, nrm, uv, faces = [], [], [], []
+    for s in range(6):
+        v = 4 * s
+        for k in range(4):
+            pos.append(corners[position_index[v + k]]); nrm.append(side_normals[s]); uv.append(side_uv[k])
+        faces += [[v, v + 1, v + 2, 0], [v + 3, v, v + 2, 0]]
+    verts = _pack(pos, nrm, uv, to_world)
+    faces = np.array(faces, np.uint32)
+    mirrored = to_world.det3() < 0
+    if flip:
+        verts[:, 3:6] = -verts[:, 3:6]
+    if mirrored != flip:
+        faces = faces[:, [2, 1, 0, 3]].copy()
+    return ShapeData(id=sid, vertices=verts, faces=faces, layout=abi.LAYOUT_NORMALS | abi.LAYOUT_TEXCOORDS, bsdf=bsdf)
+
+
+def make_mesh(sid, d: dict, to_world: Transform4f, bsdf: int) -> ShapeData:
+    """Triangle mesh from arrays. Either ``packed_vertices`` (V,8) + ``faces``
+    (F,3|4) in world space (what the host's loaders hold, mesh_utils.h:19-46),
+    or ``positions`` (+ optional ``normals``, ``texcoords``) + ``faces``."""
+    faces = np.asarray(d["faces"], np.uint32)
+    if faces.shape[1] == 3:
+        faces = np.concatenate([faces, np.zeros((faces.shape[0], 1), np.uint32)], axis=1)
+    if "packed_vertices" in d:
+        verts = np.asarray(d["packed_vertices"], f32).reshape(-1, 8)
+        layout = int(d.get("layout", abi.LAYOUT_NORMALS | abi.LAYOUT_TEXCOORDS))
+    else:
+        pos = np.asarray(d["positions"], f32).reshape(-1, 3)
+        verts = np.zeros((pos.shape[0], 8), f32)
+        layout = 0
+        m = to_world.matrix.astype(np.float64)
+        verts[:, 0:3] = (pos.astype(np.float64) @ m[:3, :3].T + m[:3, 3]).astype(f32)
+        if d.get("normals") is not None:
+            nr = np.asarray(d["normals"], f32).reshape(-1, 3).astype(np.float64) @ to_world.inverse_transpose[:3, :3].astype(np.float64).T
+            nr /= np.maximum(np.linalg.norm(nr, axis=1, keepdims=True), 1e-30)
+            verts[:, 3:6] = nr.astype(f32); layout |= abi.LAYOUT_NORMALS
+        if d.get("texcoords") is not None:
+            verts[:, 6:8] = np.asarray(d["texcoords"], f32).reshape(-1, 2); layout |= abi.LAYOUT_TEXCOORDS
+        if to_world.det3() < 0:
+            faces = faces[:, [2, 1, 0, 3]].copy()
+    return ShapeData(id=sid, vertices=verts, faces=faces, layout=layout, bsdf=bsdf)
+
+
+# ---------------------------------------------------------------------------
+# mi.cornell_box() (src/python/python/util.py:569-703)
+# ---------------------------------------------------------------------------
+def cornell_box() -> dict:
+    T = Transform4f
+    white = {"type": "ref", "id": "white"}
+    return {
+        "type": "scene",
+        "integrator": {"type": "path", "max_depth": 8},
+        "sensor": {
+            "type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0,
+            "focus_distance": 1000, "fov": 39.3077,
+            "to_world": T().look_at(origin=[0, 0, 3.90], target=[0, 0, 0], up=[0, 1, 0]),
+            "sampler": {"type": "independent", "sample_count": 64},
+            "film": {"type": "hdrfilm", "width": 256, "height": 256, "rfilter": {"type": "gaussian"},
+                     "pixel_format": "rgb", "component_format": "float32"},
+        },
+        "white": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.885809, 0.698859, 0.666422]}},
+        "green": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.105421, 0.37798, 0.076425]}},
+        "red": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.570068, 0.0430135, 0.0443706]}},
+        "light": {"type": "rectangle",
+                  "to_world": T().translate([0.0, 0.99, 0.01]).rotate([1, 0, 0], 90).scale([0.23, 0.19, 0.19]),
+                  "bsdf": white,
+                  "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [18.387, 13.9873, 6.75357]}}},
+        "floor": {"type": "rectangle", "to_world": T().translate([0.0, -1.0, 0.0]).rotate([1, 0, 0], -90), "bsdf": white},
+        "ceiling": {"type": "rectangle", "to_world": T().translate([0.0, 1.0, 0.0]).rotate([1, 0, 0], 90), "bsdf": white},
+        "back": {"type": "rectangle", "to_world": T().translate([0.0, 0.0, -1.0]), "bsdf": white},
+        "green-wall": {"type": "rectangle", "to_world": T().translate([1.0, 0.0, 0.0]).rotate([0, 1, 0], -90),
+                       "bsdf": {"type": "ref", "id": "green"}},
+        "red-wall": {"type": "rectangle", "to_world": T().translate([-1.0, 0.0, 0.0]).rotate([0, 1, 0], 90),
+                     "bsdf": {"type": "ref", "id": "red"}},
+        "small-box": {"type": "cube", "to_world": T().translate([0.335, -0.7, 0.38]).rotate([0, 1, 0], -17).scale(0.3), "bsdf": white},
+        "large-box": {"type": "cube", "to_world": T().translate([-0.33, -0.4, -0.28]).rotate([0, 1, 0], 18.25).scale([0.3, 0.61, 0.3]), "bsdf": white},
+    }

@@ -1,0 +1,284 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container, with the reference's Python package importable
+(variant scalar_rgb; e.g. `source <reference build>/setpath.sh`):
+
+    python tests/golden/gen_golden.py
+
+The reference cannot travel to the GPU box, so the (small) outputs are
+committed: tests/golden/*.npz. Nothing in tests/, smoke() or bench.py imports
+mitsuba at run time.
+
+What is recorded (all from mitsuba scalar_rgb, reference v3.9.1):
+  rng.npz          sample_tea_32 / PCG32 known answers
+  cbox_scene.npz   mi.cornell_box(): packed meshes, BSDF/emitter values, sensor matrices
+  cbox_rays.npz    camera rays, Scene.ray_intersect SI records, ray_test, emitter sampling
+  bsdf_tables.npz  BSDF eval/pdf/sample tables (diffuse, conductor, dielectric, principled)
+  cbox_renders.npz scalar_rgb renders (single 32x32 / 64x64 block; box + gaussian), several seeds
+  materials_renders.npz  same for a Cornell box with conductor / dielectric / principled boxes
+"""
+import os
+import sys
+
+import numpy as np
+
+import mitsuba as mi
+import drjit as dr
+
+mi.set_variant("scalar_rgb")
+OUT = os.path.dirname(os.path.abspath(__file__))
+rng = np.random.default_rng(1234)
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print("wrote", path, {k: np.asarray(v).shape for k, v in arrs.items()})
+
+
+# --------------------------------------------------------------------------- rng
+def gen_rng():
+    pairs = np.array([[0, 0], [0, 5], [1, 1], [123456, 7], [0xffffffff, 0xdeadbeef], [42, 2 ** 31]], np.uint64)
+    tea = np.array([mi.sample_tea_32(int(a), int(b)) for a, b in pairs], np.uint64)
+    tea_f = np.array([mi.sample_tea_float32(1, 1, 4), mi.sample_tea_float32(1, 2, 4), mi.sample_tea_float32(7, 9, 4)], np.float32)
+    seqs = []
+    inits = [(mi.PCG32().state, 0)]  # placeholder to document defaults
+    cases = [(0x853c49e6748fea9b, 0xda3e39cb94b95bdb), (42, 54), (1822236360, 2351406596), (5, 0xda3e39cb94b95bdb)]
+    for st, sq in cases:
+        r = mi.PCG32(initstate=st, initseq=sq)
+        u = [int(r.next_uint32()) for _ in range(8)]
+        r = mi.PCG32(initstate=st, initseq=sq)
+        f = [float(r.next_float32()) for _ in range(8)]
+        seqs.append((u, f))
+    # independent sampler, scalar seeding (test_independent.py:22-34)
+    sampler = mi.load_dict({"type": "independent"})
+    sampler.seed(7)
+    samp = [float(sampler.next_1d()) for _ in range(6)]
+    save("rng.npz", tea_in=pairs, tea_out=tea, tea_float=tea_f,
+         pcg_cases=np.array(cases, np.uint64), pcg_u32=np.array([s[0] for s in seqs], np.uint64),
+         pcg_f32=np.array([s[1] for s in seqs], np.float32), sampler_seed7=np.array(samp, np.float32))
+
+
+# --------------------------------------------------------------------------- scene dump
+def cbox_dict(res=32, rfilter="box", spp=16, max_depth=8, block=True, extra=None):
+    d = mi.cornell_box()
+    d["sensor"]["film"]["width"] = res
+    d["sensor"]["film"]["height"] = res
+    d["sensor"]["film"]["rfilter"] = {"type": rfilter}
+    d["sensor"]["sampler"]["sample_count"] = spp
+    d["integrator"] = {"type": "path", "max_depth": max_depth}
+    if block:
+        d["integrator"]["block_size"] = res   # one spiral block -> block_id 0 (integrator.cpp:203-215)
+    if extra:
+        extra(d)
+    return d
+
+
+def dump_shapes(scene):
+    out = {}
+    for i, s in enumerate(scene.shapes()):
+        # unmerged load (optimize=False) keeps one mesh per shape
+        v = np.array(s.packed_vertices(), np.float32).reshape(-1, 8)
+        f = np.array(s.faces(), np.uint32).reshape(-1, 3)
+        out[f"shape{i}_id"] = np.array(s.id())
+        out[f"shape{i}_vertices"] = v
+        out[f"shape{i}_faces"] = f
+        out[f"shape{i}_is_emitter"] = np.array(s.is_emitter())
+        out[f"shape{i}_bsdf"] = np.array(s.bsdf().id())
+        out[f"shape{i}_area"] = np.array(s.surface_area(), np.float32)
+    out["n_shapes"] = np.array(len(scene.shapes()))
+    return out
+
+
+def gen_scene():
+    d = cbox_dict(res=256, rfilter="gaussian", spp=64, block=False)
+    scene = mi.load_dict(d, optimize=False)
+    sensor = scene.sensors()[0]
+    film = sensor.film()
+    params = mi.traverse(scene)
+    proj = mi.perspective_projection(film.size(), film.crop_size(), film.crop_offset(),
+                                     params["sensor.x_fov"], params["sensor.near_clip"], params["sensor.far_clip"])
+    s2c = np.array(proj.inverse().matrix, np.float32)
+    out = dump_shapes(scene)
+    out.update(sample_to_camera=s2c, to_world=np.array(params["sensor.to_world"].matrix, np.float32),
+               x_fov=np.array(params["sensor.x_fov"], np.float32),
+               near_clip=np.array(params["sensor.near_clip"], np.float32),
+               far_clip=np.array(params["sensor.far_clip"], np.float32))
+    for k in ("white", "green", "red"):
+        out[f"{k}_reflectance"] = np.array(params[f"{k}.reflectance.value"], np.float32)
+    out["light_radiance"] = np.array(params["light.emitter.radiance.value"], np.float32)
+    out["light_to_world"] = np.array(params["light.to_world"].matrix, np.float32)
+    # 32x32 sensor matrix as used by the render fixtures
+    for res in (32, 64):
+        sc = mi.load_dict(cbox_dict(res=res), optimize=False)
+        f2 = sc.sensors()[0].film()
+        p2 = mi.traverse(sc)
+        pr = mi.perspective_projection(f2.size(), f2.crop_size(), f2.crop_offset(), p2["sensor.x_fov"], p2["sensor.near_clip"], p2["sensor.far_clip"])
+        out[f"sample_to_camera_{res}"] = np.array(pr.inverse().matrix, np.float32)
+    save("cbox_scene.npz", **out)
+    return scene
+
+
+# --------------------------------------------------------------------------- rays / SI
+def gen_rays(scene):
+    sensor = scene.sensors()[0]
+    n = 256
+    pos = rng.random((n, 2)).astype(np.float32)
+    cam = np.zeros((n, 7), np.float32)
+    for i in range(n):
+        ray, w = sensor.sample_ray_differential(0.0, 0.5, mi.Point2f(float(pos[i, 0]), float(pos[i, 1])), mi.Point2f(0.5, 0.5))
+        cam[i] = [*ray.o, *ray.d, ray.maxt]
+    # random rays inside the box (origins in [-0.9,0.9]^3, random directions), plus camera rays
+    m = 768
+    o = (rng.random((m, 3)) * 1.8 - 0.9).astype(np.float32)
+    dd = rng.normal(size=(m, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    rays = np.concatenate([cam, np.concatenate([o, dd.astype(np.float32), np.full((m, 1), np.float32(3.4028235e38))], axis=1)], axis=0).astype(np.float32)
+    rays[-64:, 6] = (rng.random(64) * 1.5).astype(np.float32)     # finite maxt -> some misses
+    si_rec = np.zeros((rays.shape[0], 24), np.float32)
+    shape_ids = [s.id() for s in scene.shapes()]
+    occl = np.zeros(rays.shape[0], np.uint8)
+    for i, r in enumerate(rays):
+        ray = mi.Ray3f(mi.Point3f(*map(float, r[0:3])), mi.Vector3f(*map(float, r[3:6])), float(r[6]), 0.0, [])
+        si = scene.ray_intersect(ray)
+        occl[i] = bool(scene.ray_test(ray))
+        if si.is_valid():
+            sidx = shape_ids.index(si.shape.id())
+            si_rec[i] = [si.t, *si.p, *si.n, *si.sh_frame.n, *si.sh_frame.s, *si.sh_frame.t, *si.uv, *si.wi, sidx, si.prim_index, 0]
+        else:
+            si_rec[i, 0] = np.inf; si_rec[i, 21] = -1
+            si_rec[i, 18:21] = -r[3:6]
+    # emitter sampling from reference points (Scene.sample_emitter_direction, test_visibility off/on)
+    k = 256
+    refp = (rng.random((k, 3)) * 1.8 - 0.9).astype(np.float32)
+    smp = rng.random((k, 2)).astype(np.float32)
+    em = np.zeros((k, 16), np.float32)
+    for i in range(k):
+        it = dr.zeros(mi.Interaction3f)
+        it.p = mi.Point3f(*map(float, refp[i])); it.n = mi.Normal3f(0, 0, 0); it.t = 1.0
+        ds, w = scene.sample_emitter_direction(it, mi.Point2f(float(smp[i, 0]), float(smp[i, 1])), False)
+        ds_v, w_v = scene.sample_emitter_direction(it, mi.Point2f(float(smp[i, 0]), float(smp[i, 1])), True)
+        pdf = scene.pdf_emitter_direction(it, ds)
+        em[i] = [*ds.p, *ds.n, ds.pdf, *ds.d, ds.dist, *w, float(np.any(np.array(w_v) != 0) or ds.pdf == 0), pdf]
+    save("cbox_rays.npz", cam_pos=pos, cam_rays=cam, rays=rays, si=si_rec, occluded=occl,
+         em_ref=refp, em_sample=smp, em_out=em, shape_ids=np.array(shape_ids))
+
+
+# --------------------------------------------------------------------------- BSDF tables
+def bsdf_table(bsdf_dict, n=64, seed=7, transmissive=False):
+    r = np.random.default_rng(seed)
+    bsdf = mi.load_dict(bsdf_dict)
+    q = np.zeros((n, 11), np.float32)
+    out = np.zeros((n, 14), np.float32)
+    ctx = mi.BSDFContext()
+    for i in range(n):
+        def hemi(flip):
+            v = r.normal(size=3); v /= np.linalg.norm(v)
+            v[2] = abs(v[2]) * (-1 if flip else 1)
+            return v
+        wi = hemi(transmissive and r.random() < 0.3)
+        wo = hemi(transmissive and r.random() < 0.5)
+        uv = r.random(2); s1 = r.random(); s2 = r.random(2)
+        q[i] = [*wi, *wo, *uv, s1, *s2]
+        q32 = q[i]
+        si = dr.zeros(mi.SurfaceInteraction3f)
+        si.wi = mi.Vector3f(*map(float, q32[0:3])); si.uv = mi.Point2f(float(q32[6]), float(q32[7]))
+        si.sh_frame = mi.Frame3f(mi.Vector3f(0, 0, 1)); si.n = mi.Normal3f(0, 0, 1); si.t = 1.0
+        si.p = mi.Point3f(0, 0, 0)
+        wo_v = mi.Vector3f(*map(float, q32[3:6]))
+        val, pdf, bs, weight = bsdf.eval_pdf_sample(ctx, si, wo_v, float(q32[8]), mi.Point2f(float(q32[9]), float(q32[10])))
+        st = np.array([int(bs.sampled_type)], np.uint32).view(np.float32)[0]
+        out[i] = [*val, pdf, *bs.wo, bs.pdf, bs.eta, st, *weight, bs.sampled_component]
+    return q, out
+
+
+def gen_bsdfs():
+    specs = {
+        "diffuse": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.2, 0.5, 0.8]}},
+        "conductor_none": {"type": "conductor", "material": "none"},
+        "conductor_rgb": {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]},
+                          "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
+                          "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+        "dielectric_bk7": {"type": "dielectric"},
+        "dielectric_water_tinted": {"type": "dielectric", "int_ior": "water", "ext_ior": "air",
+                                    "specular_reflectance": {"type": "rgb", "value": [0.9, 0.95, 1.0]},
+                                    "specular_transmittance": {"type": "rgb", "value": [0.8, 0.9, 0.7]}},
+        "twosided_diffuse": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.3, 0.6, 0.1]}}},
+        "principled_default": {"type": "principled"},
+        "principled_rough_metal": {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.6, 0.2]},
+                                   "metallic": 0.8, "roughness": 0.35, "specular": 0.5},
+        "principled_full": {"type": "principled", "base_color": {"type": "rgb", "value": [0.7, 0.1, 0.1]},
+                            "roughness": 0.15, "anisotropic": 0.5, "metallic": 0.1, "spec_trans": 0.8, "eta": 1.33,
+                            "spec_tint": 0.4, "sheen": 0.9, "sheen_tint": 0.2, "flatness": 0.23,
+                            "clearcoat": 0.9, "clearcoat_gloss": 0.5},
+        "principled_matpreview": {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]},
+                                  "roughness": 0.3, "metallic": 0.0, "specular": 0.5},
+        "principled_coat_sheen": {"type": "principled", "base_color": {"type": "rgb", "value": [0.2, 0.4, 0.9]},
+                                  "roughness": 0.6, "clearcoat": 1.0, "clearcoat_gloss": 0.8, "sheen": 0.5, "sheen_tint": 0.7,
+                                  "spec_tint": 0.3, "flatness": 0.5},
+    }
+    out = {}
+    for name, spec in specs.items():
+        trans = name.startswith("dielectric") or name in ("principled_full", "twosided_diffuse")
+        q, o = bsdf_table(spec, transmissive=trans)
+        out[name + "_in"] = q; out[name + "_out"] = o
+    save("bsdf_tables.npz", **out)
+
+
+# --------------------------------------------------------------------------- renders
+def render(d, seed, spp):
+    scene = mi.load_dict(d, optimize=False)
+    img = mi.render(scene, seed=seed, spp=spp)
+    return np.array(img, np.float32)
+
+
+def gen_renders():
+    out = {}
+    for (res, rf, spp, md, seed) in [(32, "box", 16, 8, 0), (32, "box", 8, 8, 3), (32, "box", 32, 3, 1),
+                                      (32, "gaussian", 8, 8, 0), (64, "box", 4, 8, 2), (32, "box", 64, 1, 0),
+                                      (32, "box", 8, -1, 5)]:
+        key = f"cbox_{res}_{rf}_spp{spp}_d{md}_seed{seed}"
+        out[key] = render(cbox_dict(res=res, rfilter=rf, spp=spp, max_depth=md), seed, spp)
+    # statistics anchors: high-spp mean image (multi-block, default seeds) for z-tests
+    d = cbox_dict(res=64, rfilter="box", spp=2048, max_depth=8, block=False)
+    out["cbox_64_box_ref2048"] = render(d, 0, 2048)
+    d = cbox_dict(res=64, rfilter="gaussian", spp=1024, max_depth=8, block=False)
+    out["cbox_64_gaussian_ref1024"] = render(d, 0, 1024)
+    save("cbox_renders.npz", **out)
+
+
+def materials(d):
+    d["mirror"] = {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}
+    d["glass"] = {"type": "dielectric", "int_ior": "bk7", "ext_ior": "air"}
+    d["pr"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]}, "roughness": 0.3,
+               "metallic": 0.2, "specular": 0.5, "clearcoat": 0.5, "clearcoat_gloss": 0.6, "sheen": 0.3}
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "glass"}
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "mirror"}
+    d["back"]["bsdf"] = {"type": "ref", "id": "pr"}
+    d["floor"]["bsdf"] = {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}}}
+
+
+def gen_material_renders():
+    out = {}
+    for (res, rf, spp, md, seed) in [(32, "box", 16, 8, 0), (32, "box", 8, 12, 4)]:
+        out[f"mat_{res}_{rf}_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter=rf, spp=spp, max_depth=md, extra=materials), seed, spp)
+    d = cbox_dict(res=64, rfilter="box", spp=2048, max_depth=8, block=False, extra=materials)
+    out["mat_64_box_ref2048"] = render(d, 0, 2048)
+    save("materials_renders.npz", **out)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials"]
+    if "rng" in what:
+        gen_rng()
+    scene = None
+    if "scene" in what or "rays" in what:
+        scene = gen_scene()
+    if "rays" in what:
+        gen_rays(scene)
+    if "bsdfs" in what:
+        gen_bsdfs()
+    if "renders" in what:
+        gen_renders()
+    if "materials" in what:
+        gen_material_renders()
