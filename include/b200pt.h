@@ -30,6 +30,12 @@ extern "C" {
 
 #define B200PT_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define B200PT_API __attribute__((visibility("default")))
+#else
+#define B200PT_API
+#endif
+
 typedef enum b200pt_status {
     B200PT_OK              = 0,
     B200PT_ERR_INVALID     = 1, /* bad argument / inconsistent descriptor   */
@@ -195,69 +201,69 @@ typedef struct b200pt_stats {
 typedef struct b200pt_scene b200pt_scene;
 
 /* ---- library ---------------------------------------------------------- */
-uint32_t    b200pt_abi_version(void);
-const char *b200pt_last_error(void);
+B200PT_API uint32_t    b200pt_abi_version(void);
+B200PT_API const char *b200pt_last_error(void);
 /* Number of visible CUDA devices (0 without a driver/GPU). */
-int         b200pt_device_count(void);
+B200PT_API int         b200pt_device_count(void);
 
 /* ---- scene life cycle: replaces Scene::Scene accel build (scene.cpp:93,
  *      scene_optix.inl:446) for triangle meshes ------------------------- */
-b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device,
+B200PT_API b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device,
                                   b200pt_scene **out);
-void          b200pt_scene_destroy(b200pt_scene *scene);
+B200PT_API void          b200pt_scene_destroy(b200pt_scene *scene);
 /* Parameter update after an optimiser step (SceneParameters.update ->
  * parameters_changed, util.py:272-338): overwrite texture `tex` with `n`
  * floats (3/1 for constants, h*w*c for bitmaps). */
-b200pt_status b200pt_scene_update_texture(b200pt_scene *scene, uint32_t tex,
+B200PT_API b200pt_status b200pt_scene_update_texture(b200pt_scene *scene, uint32_t tex,
                                           const float *host_data, size_t n);
 
 /* ---- forward render: replaces SamplingIntegrator::render (JIT branch,
  *      integrator.cpp:275-389) + PathIntegrator::sample (path.cpp:94-346)
  *      + ImageBlock::put + HDRFilm::develop ------------------------------ */
 /* Host entry point (what the plugin calls): out_host is H*W*3 floats. */
-b200pt_status b200pt_render(b200pt_scene *scene, const b200pt_render_params *p,
+B200PT_API b200pt_status b200pt_render(b200pt_scene *scene, const b200pt_render_params *p,
                             float *out_host);
 /* Device entry points for multi-GPU: accumulate this shard's samples into a
  * raw film block (H*W*4: R,G,B,weight) owned by the caller, then develop
  * (hdrfilm.cpp:393) after the caller has all-reduced the block. */
-b200pt_status b200pt_render_accumulate(b200pt_scene *scene,
+B200PT_API b200pt_status b200pt_render_accumulate(b200pt_scene *scene,
                                        const b200pt_render_params *p,
                                        float *film_device /* H*W*4, zeroed by caller */,
                                        void *cuda_stream);
-b200pt_status b200pt_develop(b200pt_scene *scene, const float *film_device,
+B200PT_API b200pt_status b200pt_develop(b200pt_scene *scene, const float *film_device,
                              float *out_device /* H*W*3 */, void *cuda_stream);
 
 /* ---- adjoint: replaces RBIntegrator.render_backward (common.py:625-783)
  *      + PRBIntegrator.sample Backward mode (prb.py:68-339) -------------- */
 /* grad_in_host: H*W*3 (dLoss/dImage). Gradients are ACCUMULATED into the
  * per-texture gradient buffers of the scene (dr.grad accumulation). */
-b200pt_status b200pt_render_backward(b200pt_scene *scene,
+B200PT_API b200pt_status b200pt_render_backward(b200pt_scene *scene,
                                      const b200pt_render_params *p,
                                      const float *grad_in_host);
-b200pt_status b200pt_render_backward_device(b200pt_scene *scene,
+B200PT_API b200pt_status b200pt_render_backward_device(b200pt_scene *scene,
                                             const b200pt_render_params *p,
                                             const float *grad_in_device,
                                             void *cuda_stream);
-b200pt_status b200pt_grad_zero(b200pt_scene *scene);
+B200PT_API b200pt_status b200pt_grad_zero(b200pt_scene *scene);
 /* Copy the gradient of differentiable texture `tex` to the host. */
-b200pt_status b200pt_grad_read(b200pt_scene *scene, uint32_t tex,
+B200PT_API b200pt_status b200pt_grad_read(b200pt_scene *scene, uint32_t tex,
                                float *host_out, size_t n);
 /* Device view of all gradient buffers as one flat fp32 array (for one fused
  * NCCL all-reduce); offsets per texture via b200pt_grad_offset. */
-b200pt_status b200pt_grad_device_view(b200pt_scene *scene, float **ptr, size_t *n);
-b200pt_status b200pt_grad_offset(b200pt_scene *scene, uint32_t tex,
+B200PT_API b200pt_status b200pt_grad_device_view(b200pt_scene *scene, float **ptr, size_t *n);
+B200PT_API b200pt_status b200pt_grad_offset(b200pt_scene *scene, uint32_t tex,
                                  size_t *offset, size_t *n);
 
 /* ---- operators on the path, exposed for parity tests ------------------ */
 /* Scene::ray_intersect_preliminary (scene.cpp:216): n rays, rays_host =
  * n*7 floats (o3, d3, maxt). Outputs: t (inf on miss), prim_uv n*2,
  * prim_index (within shape), shape_index (-1 on miss). */
-b200pt_status b200pt_ray_intersect(b200pt_scene *scene, uint32_t n,
+B200PT_API b200pt_status b200pt_ray_intersect(b200pt_scene *scene, uint32_t n,
                                    const float *rays_host, float *t_out,
                                    float *uv_out, uint32_t *prim_out,
                                    int32_t *shape_out);
 /* Scene::ray_test (scene.cpp:232): hit_out[i] = 1 if occluded. */
-b200pt_status b200pt_ray_test(b200pt_scene *scene, uint32_t n,
+B200PT_API b200pt_status b200pt_ray_test(b200pt_scene *scene, uint32_t n,
                               const float *rays_host, uint8_t *hit_out);
 /* BSDF::eval_pdf_sample (bsdf.cpp:21-31) for n queries on BSDF `bsdf`:
  * in_host = n*10 floats (wi3, wo3, uv2 ... see layout below),
@@ -266,12 +272,15 @@ b200pt_status b200pt_ray_test(b200pt_scene *scene, uint32_t n,
  * out_host = n*14 floats:
  *   [0..2] eval (f*cos), [3] pdf, [4..6] bs.wo, [7] bs.pdf, [8] bs.eta,
  *   [9] sampled_type (as float bits of uint32), [10..12] weight, [13] sampled_component */
-b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *scene, uint32_t bsdf,
+B200PT_API b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *scene, uint32_t bsdf,
                                           uint32_t n, const float *in_host,
                                           float *out_host);
 
 /* ---- measurement ------------------------------------------------------ */
-b200pt_status b200pt_get_stats(b200pt_scene *scene, b200pt_stats *out);
+B200PT_API b200pt_status b200pt_get_stats(b200pt_scene *scene, b200pt_stats *out);
+/* sizeof() of the ABI structs as compiled: 0 texture, 1 bsdf, 2 shape, 3 emitter,
+ * 4 sensor, 5 scene_desc, 6 render_params, 7 stats (binding self-check). */
+B200PT_API size_t b200pt_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }

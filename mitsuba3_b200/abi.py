@@ -104,7 +104,7 @@ SYMBOLS = [
     "b200pt_render_backward", "b200pt_render_backward_device", "b200pt_grad_zero",
     "b200pt_grad_read", "b200pt_grad_device_view", "b200pt_grad_offset",
     "b200pt_ray_intersect", "b200pt_ray_test", "b200pt_bsdf_eval_pdf_sample",
-    "b200pt_get_stats",
+    "b200pt_get_stats", "b200pt_abi_sizeof",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200pt.so")
@@ -147,6 +147,8 @@ def load() -> C.CDLL:
     lib.b200pt_ray_test.argtypes = [vp, u32, f32p, C.POINTER(C.c_uint8)]
     lib.b200pt_bsdf_eval_pdf_sample.argtypes = [vp, u32, u32, f32p, f32p]
     lib.b200pt_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.b200pt_abi_sizeof.argtypes = [C.c_int]
+    lib.b200pt_abi_sizeof.restype = C.c_size_t
     if lib.b200pt_abi_version() != ABI_VERSION:
         raise RuntimeError("libb200pt.so ABI version mismatch")
     _lib = lib

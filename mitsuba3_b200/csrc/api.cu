@@ -1,0 +1,662 @@
+// api.cu -- C ABI of libb200pt.so (include/b200pt.h) and the host-side wavefront
+// scheduler: scene upload + BVH build, per-chunk kernel sequence on a CUDA stream
+// (no host synchronisation inside a chunk: queue sizes stay on the device and the
+// kernels are persistent grid-stride loops), film / gradient management.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200pt.h"
+#include "bvh.h"
+#include "kernels.cuh"
+
+using namespace pt;
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local std::string g_error;
+static b200pt_status fail(b200pt_status st, const std::string &msg) { g_error = msg; return st; }
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(B200PT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// scene object
+// ---------------------------------------------------------------------------
+struct TexMeta { int32_t kind, channels; size_t n; uint32_t grad_offset; bool differentiable; float *dev_data; };
+
+struct Wavefront {
+    size_t cap = 0;
+    PathBuf buf[2];
+    float4 *hit = nullptr, *lane_result = nullptr, *lane_dL = nullptr;
+    Queues q;
+    uint32_t *counts = nullptr; size_t n_counts = 0;
+    std::vector<void *> allocs;
+};
+
+struct b200pt_scene {
+    int device = 0;
+    DevScene dev;
+    std::vector<void *> allocs;
+    std::vector<TexMeta> tex;
+    bool type_present[N_BSDF_TYPES] = { false, false, false, false };
+    size_t grad_floats = 0;
+    uint32_t n_sm = 148;
+    Launch launch;
+    Wavefront wf;
+    // shard pixel list cache
+    uint32_t *pix_ids = nullptr; uint32_t n_pix_ids = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
+    uint32_t *all_pix_ids = nullptr;   // identity list (weights pre-pass)
+    unsigned long long *stats_dev = nullptr;
+    float *film_own = nullptr, *out_dev = nullptr, *grad_in_dev = nullptr, *film_w = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> trace_events; size_t trace_ev_used = 0;
+    bool profile = false;
+    b200pt_stats stats;
+};
+
+template <typename T>
+static cudaError_t dev_upload(b200pt_scene *s, const T *host, size_t n, T **out) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    s->allocs.push_back(p);
+    if (n) e = cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (T *) p;
+    return e;
+}
+
+extern "C" {
+
+uint32_t b200pt_abi_version(void) { return B200PT_ABI_VERSION; }
+const char *b200pt_last_error(void) { return g_error.c_str(); }
+
+int b200pt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void b200pt_scene_destroy(b200pt_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    for (void *p : s->wf.allocs) cudaFree(p);
+    if (s->pix_ids) cudaFree(s->pix_ids);
+    if (s->all_pix_ids) cudaFree(s->all_pix_ids);
+    for (cudaEvent_t e : s->trace_events) cudaEventDestroy(e);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static void init_gaussian(DevScene &d, float stddev) {
+    // gaussian.cpp:48-91: Remez fit to exp(-x/2), rescaled by stddev, zero at the radius
+    d.gauss_radius = 4.f * stddev;
+    static const double coeff[10] = { 9.992604880e-1, -4.977025247e-1, 1.222248550e-1, -1.932406282e-2, 2.136713061e-3,
+                                      -1.679873860e-4, 9.202145248e-6, -3.329417433e-7, 7.128382794e-9, -6.821193280e-11 };
+    float cs[10]; double scale = 1;
+    for (int i = 0; i < 10; ++i) { cs[i] = (float) (coeff[i] * scale); scale /= (double) stddev * (double) stddev; }
+    auto estrin = [&](float x) {
+        float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+        float p01 = fmaf(cs[1], x, cs[0]), p23 = fmaf(cs[3], x, cs[2]), p45 = fmaf(cs[5], x, cs[4]), p67 = fmaf(cs[7], x, cs[6]), p89 = fmaf(cs[9], x, cs[8]);
+        return fmaf(p89, x8, fmaf(fmaf(p67, x2, p45), x4, fmaf(p23, x2, p01)));
+    };
+    cs[0] -= estrin(d.gauss_radius * d.gauss_radius);
+    memcpy(d.gauss_coeff, cs, sizeof(cs));
+    d.gauss_alpha = -1.f / (2.f * stddev * stddev);
+    d.gauss_bias = expf(d.gauss_alpha * d.gauss_radius * d.gauss_radius);
+}
+
+b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b200pt_scene **out) {
+    if (!desc || !out) return fail(B200PT_ERR_INVALID, "null argument");
+    if (desc->abi_version != B200PT_ABI_VERSION) return fail(B200PT_ERR_INVALID, "ABI version mismatch");
+    if (b200pt_device_count() <= device || device < 0) return fail(B200PT_ERR_CUDA, "no such CUDA device (mitsuba3_b200 has no CPU fallback)");
+    if (desc->sensor.rfilter == B200PT_RFILTER_GAUSSIAN_TABLE)
+        return fail(B200PT_ERR_UNSUPPORTED, "the tabulated filter belongs to the scalar variants; JIT variants evaluate the filter analytically");
+    CU_TRY(cudaSetDevice(device));
+    b200pt_scene *s = new b200pt_scene();
+    s->device = device;
+    memset(&s->dev, 0, sizeof(s->dev));
+    memset(&s->stats, 0, sizeof(s->stats));
+    DevScene &d = s->dev;
+#define S_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); b200pt_scene_destroy(s); return fail(B200PT_ERR_CUDA, m); } } while (0)
+#define S_FAIL(st, msg) do { b200pt_scene_destroy(s); return fail(st, msg); } while (0)
+    cudaDeviceProp prop; S_TRY(cudaGetDeviceProperties(&prop, device));
+    s->n_sm = (uint32_t) prop.multiProcessorCount;
+    S_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    S_TRY(cudaEventCreate(&s->ev0)); S_TRY(cudaEventCreate(&s->ev1));
+    s->profile = getenv("B200PT_PROFILE") != nullptr;
+
+    // ---- textures ----------------------------------------------------------
+    std::vector<DevTexture> htex(desc->n_textures);
+    size_t grad_off = 0;
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const b200pt_texture &t = desc->textures[i];
+        DevTexture &o = htex[i]; memset(&o, 0, sizeof(o));
+        if (t.channels != 1 && t.channels != 3) S_FAIL(B200PT_ERR_INVALID, "texture channels must be 1 or 3");
+        o.kind = t.kind; o.channels = t.channels; o.width = t.width; o.height = t.height; o.wrap = t.wrap; o.filter = t.filter;
+        o.differentiable = t.differentiable;
+        memcpy(o.value, t.value, sizeof(o.value)); memcpy(o.to_uv, t.to_uv, sizeof(o.to_uv));
+        TexMeta m; m.kind = t.kind; m.channels = t.channels; m.differentiable = t.differentiable != 0; m.dev_data = nullptr;
+        if (t.kind == B200PT_TEX_BITMAP) {
+            if (!t.data || t.width <= 0 || t.height <= 0) S_FAIL(B200PT_ERR_INVALID, "bitmap texture without data");
+            m.n = (size_t) t.width * t.height * t.channels;
+            float *dd = nullptr; S_TRY(dev_upload(s, t.data, m.n, &dd));
+            o.data = dd; m.dev_data = dd;
+        } else m.n = (size_t) t.channels;
+        m.grad_offset = (uint32_t) grad_off; o.grad_offset = (uint32_t) grad_off;
+        if (m.differentiable) grad_off += m.n;
+        s->tex.push_back(m);
+    }
+    s->grad_floats = grad_off;
+    { DevTexture *p; S_TRY(dev_upload(s, htex.data(), htex.size(), &p)); d.textures = p; d.n_textures = desc->n_textures; }
+    { float *g = nullptr; S_TRY(cudaMalloc(&g, std::max<size_t>(grad_off, 1) * sizeof(float))); s->allocs.push_back(g); S_TRY(cudaMemset(g, 0, std::max<size_t>(grad_off, 1) * sizeof(float))); d.grad = g; }
+
+    // ---- bsdfs / emitters ----------------------------------------------------
+    std::vector<DevBsdf> hb(desc->n_bsdfs);
+    for (uint32_t i = 0; i < desc->n_bsdfs; ++i) {
+        const b200pt_bsdf &b = desc->bsdfs[i];
+        if (b.type < 0 || b.type >= N_BSDF_TYPES) S_FAIL(B200PT_ERR_UNSUPPORTED, "BSDF model outside the hot-path scope");
+        hb[i].type = b.type; hb[i].twosided = b.twosided; memcpy(hb[i].tex, b.tex, sizeof(b.tex));
+        for (int k = 0; k < B200PT_MAX_SLOTS; ++k) if (b.tex[k] >= (int32_t) desc->n_textures) S_FAIL(B200PT_ERR_INVALID, "BSDF references a missing texture");
+        hb[i].eta = b.eta; hb[i].spec_srate = b.spec_srate; hb[i].clearcoat_srate = b.clearcoat_srate; hb[i].diff_refl_srate = b.diff_refl_srate; hb[i].flags = b.flags;
+    }
+    { DevBsdf *p; S_TRY(dev_upload(s, hb.data(), hb.size(), &p)); d.bsdfs = p; d.n_bsdfs = desc->n_bsdfs; }
+    std::vector<DevEmitter> he(desc->n_emitters);
+    for (uint32_t i = 0; i < desc->n_emitters; ++i) {
+        const b200pt_emitter &e = desc->emitters[i];
+        if (e.shape < 0 || e.shape >= (int32_t) desc->n_shapes || e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures)
+            S_FAIL(B200PT_ERR_INVALID, "emitter references a missing shape/texture");
+        if (desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST) S_FAIL(B200PT_ERR_UNSUPPORTED, "textured area lights are outside the hot-path scope");
+        he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].pad = 0.f;
+    }
+    { DevEmitter *p; S_TRY(dev_upload(s, he.data(), he.size(), &p)); d.emitters = p; d.n_emitters = desc->n_emitters; }
+
+    // ---- shapes: flatten to one vertex / primitive array ---------------------
+    size_t n_verts = 0, n_prims = 0;
+    for (uint32_t i = 0; i < desc->n_shapes; ++i) { n_verts += desc->shapes[i].n_vertices; n_prims += desc->shapes[i].n_faces; }
+    if (n_prims >= (1u << 28)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles");
+    std::vector<float> verts(n_verts * 8); std::vector<uint32_t> pv(n_prims * 4); std::vector<float> tri9(n_prims * 9);
+    std::vector<DevShape> hs(desc->n_shapes);
+    size_t vo = 0, po = 0;
+    for (uint32_t i = 0; i < desc->n_shapes; ++i) {
+        const b200pt_shape &sh = desc->shapes[i];
+        if (sh.layout & B200PT_LAYOUT_TANGENTS) S_FAIL(B200PT_ERR_UNSUPPORTED, "packed tangent frames are outside the hot-path scope");
+        if (sh.bsdf < 0 || sh.bsdf >= (int32_t) desc->n_bsdfs) S_FAIL(B200PT_ERR_INVALID, "shape references a missing BSDF");
+        if (sh.emitter >= (int32_t) desc->n_emitters) S_FAIL(B200PT_ERR_INVALID, "shape references a missing emitter");
+        DevShape &o = hs[i]; memset(&o, 0, sizeof(o));
+        o.layout = sh.layout; o.bsdf = sh.bsdf; o.emitter = sh.emitter; o.sampling = sh.sampling;
+        o.first_prim = (uint32_t) po; o.n_prims = sh.n_faces; o.first_vertex = (uint32_t) vo;
+        memcpy(o.to_world, sh.to_world, sizeof(o.to_world)); memcpy(o.frame_n, sh.frame_n, sizeof(o.frame_n)); o.inv_area = sh.inv_area;
+        s->type_present[desc->bsdfs[sh.bsdf].type] = true;
+        memcpy(&verts[vo * 8], sh.vertices, (size_t) sh.n_vertices * 8 * sizeof(float));
+        std::vector<float> cdf;
+        double acc = 0;
+        for (uint32_t f = 0; f < sh.n_faces; ++f) {
+            const uint32_t *fr = sh.faces + 4 * (size_t) f;
+            for (int k = 0; k < 3; ++k) {
+                if (fr[k] >= sh.n_vertices) S_FAIL(B200PT_ERR_INVALID, "face index out of range");
+                pv[(po + f) * 4 + k] = (uint32_t) (vo + fr[k]);
+                memcpy(&tri9[(po + f) * 9 + 3 * k], sh.vertices + 8 * (size_t) fr[k], 3 * sizeof(float));
+            }
+            pv[(po + f) * 4 + 3] = i;
+            if (sh.sampling == B200PT_SAMPLING_MESH) {
+                // Mesh::build_pmf: face areas, cdf accumulated in double (core/distr_1d.h)
+                const float *p0 = &tri9[(po + f) * 9], *p1 = p0 + 3, *p2 = p0 + 6;
+                float e0[3] = { p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2] }, e1[3] = { p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2] };
+                float c[3] = { fmaf(e0[1], e1[2], -(e0[2] * e1[1])), fmaf(e0[2], e1[0], -(e0[0] * e1[2])), fmaf(e0[0], e1[1], -(e0[1] * e1[0])) };
+                float area = .5f * sqrtf(fmaf(c[2], c[2], fmaf(c[1], c[1], c[0] * c[0])));
+                acc += (double) area; cdf.push_back((float) acc);
+            }
+        }
+        if (sh.sampling == B200PT_SAMPLING_MESH) {
+            float *dc = nullptr; S_TRY(dev_upload(s, cdf.data(), cdf.size(), &dc));
+            o.area_cdf = dc; o.area_sum = (float) acc; o.area_norm = (float) (1.0 / acc);
+        }
+        vo += sh.n_vertices; po += sh.n_faces;
+    }
+    { float *p; S_TRY(dev_upload(s, verts.data(), verts.size(), &p)); d.vertices = (const float4 *) p; }
+    { uint32_t *p; S_TRY(dev_upload(s, pv.data(), pv.size(), &p)); d.prim_verts = (const uint4 *) p; }
+    { DevShape *p; S_TRY(dev_upload(s, hs.data(), hs.size(), &p)); d.shapes = p; d.n_shapes = desc->n_shapes; }
+
+    // ---- BVH ----------------------------------------------------------------
+    Bvh bvh = build_bvh(tri9.data(), (uint32_t) n_prims);
+    std::vector<float> tris(n_prims * 12);
+    for (size_t i = 0; i < n_prims; ++i) {
+        uint32_t src = bvh.order[i];
+        const float *p0 = &tri9[(size_t) src * 9], *p1 = p0 + 3, *p2 = p0 + 6;
+        float *o = &tris[i * 12];
+        o[0] = p0[0]; o[1] = p0[1]; o[2] = p0[2]; memcpy(&o[3], &src, 4);
+        o[4] = p1[0] - p0[0]; o[5] = p1[1] - p0[1]; o[6] = p1[2] - p0[2]; o[7] = 0.f;
+        o[8] = p2[0] - p0[0]; o[9] = p2[1] - p0[1]; o[10] = p2[2] - p0[2]; o[11] = 0.f;
+    }
+    { BvhNode *p; S_TRY(dev_upload(s, bvh.nodes.data(), bvh.nodes.size(), &p)); d.nodes = (const float4 *) p; d.n_nodes = (uint32_t) bvh.nodes.size(); }
+    { float *p; S_TRY(dev_upload(s, tris.data(), tris.size(), &p)); d.tris = (const float4 *) p; d.n_tris = (uint32_t) n_prims; }
+    if (bvh.depth > 60) S_FAIL(B200PT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+
+    // ---- sensor / film -------------------------------------------------------
+    const b200pt_sensor &se = desc->sensor;
+    memcpy(d.s2c, se.sample_to_camera, sizeof(d.s2c)); memcpy(d.cam_to_world, se.to_world, sizeof(d.cam_to_world));
+    d.near_clip = se.near_clip; d.far_clip = se.far_clip;
+    d.film_w = se.film_size[0]; d.film_h = se.film_size[1]; d.crop_w = se.crop_size[0]; d.crop_h = se.crop_size[1];
+    d.crop_x = se.crop_offset[0]; d.crop_y = se.crop_offset[1];
+    if (d.crop_w == 0 || d.crop_h == 0) S_FAIL(B200PT_ERR_INVALID, "empty film");
+    d.rfilter = se.rfilter; d.base_seed = se.base_seed;
+    if (se.rfilter != B200PT_RFILTER_BOX) {
+        if (!(se.rfilter_stddev > 0.f) || 4.f * se.rfilter_stddev > 7.5f) S_FAIL(B200PT_ERR_INVALID, "gaussian stddev out of range");
+        init_gaussian(d, se.rfilter_stddev);
+    }
+
+    // ---- launch geometry: persistent grids, top of the BVH staged in shared memory
+    s->launch.n_smem_nodes = std::min<uint32_t>(d.n_nodes, 512);         // 32 KiB of nodes
+    s->launch.n_smem_tris = d.n_tris <= 512 ? d.n_tris : 0;              // <= 24 KiB of triangles
+    s->launch.smem_trace = (size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48;
+    s->launch.grid = (int) s->n_sm * 4;
+    set_trace_smem_attr(s->launch.smem_trace);
+    S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
+    size_t npix = (size_t) d.crop_w * d.crop_h;
+    S_TRY(cudaMalloc(&s->film_own, npix * 4 * sizeof(float))); s->allocs.push_back(s->film_own);
+    S_TRY(cudaMalloc(&s->film_w, npix * 4 * sizeof(float))); s->allocs.push_back(s->film_w);
+    S_TRY(cudaMalloc(&s->out_dev, npix * 3 * sizeof(float))); s->allocs.push_back(s->out_dev);
+    S_TRY(cudaMalloc(&s->grad_in_dev, npix * 3 * sizeof(float))); s->allocs.push_back(s->grad_in_dev);
+    S_TRY(cudaDeviceSynchronize());
+    *out = s;
+    return B200PT_OK;
+#undef S_TRY
+#undef S_FAIL
+}
+
+b200pt_status b200pt_scene_update_texture(b200pt_scene *s, uint32_t tex, const float *host_data, size_t n) {
+    if (!s || !host_data) return fail(B200PT_ERR_INVALID, "null argument");
+    if (tex >= s->tex.size() || n != s->tex[tex].n) return fail(B200PT_ERR_INVALID, "texture index/size mismatch");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (s->tex[tex].kind == B200PT_TEX_BITMAP) CU_TRY(cudaMemcpy(s->tex[tex].dev_data, host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+    else {
+        const DevTexture *dt = s->dev.textures + tex;
+        CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value), host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return B200PT_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// wavefront buffers
+// ---------------------------------------------------------------------------
+constexpr uint32_t MAX_BOUNCE_SLOTS = 1024;   // counters for this many bounces per chunk
+
+static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint) {
+    Wavefront &w = s->wf;
+    bool need_adj = adjoint && (w.cap == 0 || w.buf[0].adj_L == nullptr);
+    if (w.cap >= cap && !need_adj) return B200PT_OK;
+    for (void *p : w.allocs) cudaFree(p);
+    w.allocs.clear(); w.cap = 0;
+    auto A = [&](size_t bytes, void **out) -> cudaError_t { cudaError_t e = cudaMalloc(out, bytes); if (e == cudaSuccess) w.allocs.push_back(*out); return e; };
+    size_t slack = cap + 64;
+    for (int b = 0; b < 2; ++b) {
+        PathBuf &pb = w.buf[b]; memset(&pb, 0, sizeof(pb));
+        CU_TRY(A(slack * 16, (void **) &pb.ray_o)); CU_TRY(A(slack * 16, (void **) &pb.ray_d)); CU_TRY(A(slack * 16, (void **) &pb.thr));
+        CU_TRY(A(slack * 16, (void **) &pb.prev)); CU_TRY(A(slack * 16, (void **) &pb.rng)); CU_TRY(A(slack * 16, (void **) &pb.result));
+        CU_TRY(A(slack * 16, (void **) &pb.sh_o)); CU_TRY(A(slack * 16, (void **) &pb.sh_d)); CU_TRY(A(slack * 8, (void **) &pb.sh_c));
+        if (adjoint) { CU_TRY(A(slack * 16, (void **) &pb.adj_L)); CU_TRY(A(slack * 16, (void **) &pb.adj_dL)); }
+    }
+    CU_TRY(A(slack * 16, (void **) &w.hit)); CU_TRY(A(slack * 16, (void **) &w.lane_result)); CU_TRY(A(slack * 16, (void **) &w.lane_dL));
+    for (int t = 0; t < N_BSDF_TYPES; ++t) {
+        if (s->type_present[t]) CU_TRY(A(slack * 4, (void **) &w.q.slots[t])); else w.q.slots[t] = nullptr;
+    }
+    w.n_counts = (size_t) (MAX_BOUNCE_SLOTS + 2) * 8;
+    CU_TRY(A(w.n_counts * 4, (void **) &w.counts));
+    w.q.counts = w.counts;
+    w.cap = cap;
+    return B200PT_OK;
+}
+
+static b200pt_status ensure_pix_ids(b200pt_scene *s, const b200pt_render_params *p) {
+    uint32_t count = std::max(1u, p->shard_count), rank = p->shard_rank, ts = p->tile_size ? p->tile_size : 32;
+    if (rank >= count) return fail(B200PT_ERR_INVALID, "shard_rank >= shard_count");
+    if (s->pix_ids && s->pix_key[0] == rank && s->pix_key[1] == count && s->pix_key[2] == ts) return B200PT_OK;
+    uint32_t W = s->dev.crop_w, H = s->dev.crop_h;
+    std::vector<uint32_t> ids; ids.reserve((size_t) W * H / count + 1024);
+    uint32_t tiles_x = (W + ts - 1) / ts, tiles_y = (H + ts - 1) / ts;
+    // pixel-tile sharding: tile t belongs to rank t % count; within a rank the
+    // pixels are enumerated tile by tile, row-major inside the tile
+    for (uint32_t t = rank; t < tiles_x * tiles_y; t += count) {
+        uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
+        for (uint32_t y = ty * ts; y < std::min(H, (ty + 1) * ts); ++y)
+            for (uint32_t x = tx * ts; x < std::min(W, (tx + 1) * ts); ++x) ids.push_back(y * W + x);
+    }
+    if (count == 1) { ids.resize((size_t) W * H); for (uint32_t i = 0; i < W * H; ++i) ids[i] = i; }   // whole frame: scanline order
+    if (s->pix_ids) { cudaFree(s->pix_ids); s->pix_ids = nullptr; }
+    CU_TRY(cudaMalloc(&s->pix_ids, std::max<size_t>(ids.size(), 1) * 4));
+    CU_TRY(cudaMemcpy(s->pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+    s->n_pix_ids = (uint32_t) ids.size();
+    s->pix_key[0] = rank; s->pix_key[1] = count; s->pix_key[2] = ts;
+    return B200PT_OK;
+}
+
+static cudaEvent_t next_trace_event(b200pt_scene *s) {
+    if (s->trace_ev_used == s->trace_events.size()) { cudaEvent_t e; cudaEventCreate(&e); s->trace_events.push_back(e); }
+    return s->trace_events[s->trace_ev_used++];
+}
+
+static int grid_for(const b200pt_scene *s, size_t n) {
+    size_t blocks = (n + BLOCK - 1) / BLOCK;
+    return (int) std::max<size_t>(1, std::min<size_t>(blocks, (size_t) s->n_sm * 8));
+}
+
+// One chunk of the wavefront: lanes [pix0*spp, (pix0+npix)*spp) of this shard.
+// mode 0: primal (path / prb) -> lane_result; mode 1: PRB adjoint replay.
+static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStream_t st) {
+    Wavefront &w = s->wf;
+    const DevScene &d = s->dev;
+    uint32_t lanes = cfg.chunk_lanes;
+    cfg.adjoint = mode == 1;
+    CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
+    int g_all = grid_for(s, lanes);
+    launch_generate(d, cfg, s->pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
+    s->stats.kernel_launches++;
+    Launch L = s->launch;
+    L.grid = std::min<int>(s->launch.grid, (int) ((lanes + BLOCK - 1) / BLOCK)); if (L.grid < 1) L.grid = 1;
+    Launch Ls = L; Ls.grid = g_all;
+    auto trace = [&](int bufi, const uint32_t *n_in, uint32_t *qcounts, bool first) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (s->profile) { e0 = next_trace_event(s); e1 = next_trace_event(s); cudaEventRecord(e0, st); }
+        launch_trace(d, cfg, w.buf[bufi], w.hit, n_in, w.q, qcounts, w.lane_result, s->stats_dev, first, L, st);
+        if (s->profile) cudaEventRecord(e1, st);
+        s->stats.kernel_launches++; s->stats.trace_launches++;
+    };
+    int cur = 0;
+    trace(cur, nullptr, w.counts + 0, true);
+    uint32_t max_b = std::min<uint32_t>(cfg.max_depth, MAX_BOUNCE_SLOTS);
+    for (uint32_t b = 0; b < max_b; ++b) {
+        uint32_t *cnt = w.counts + (size_t) b * 8;
+        for (int t = 0; t < N_BSDF_TYPES; ++t) {
+            if (!s->type_present[t]) continue;
+            launch_shade(t, d, cfg, w.buf[cur], w.hit, w.q.slots[t], cnt + t, w.buf[cur ^ 1], cnt + 4, w.lane_result, s->stats_dev, Ls, st);
+            s->stats.kernel_launches++;
+        }
+        cur ^= 1;
+        trace(cur, cnt + 4, w.counts + (size_t) (b + 1) * 8, false);
+        if (b >= 15 && (b & 7) == 7) {
+            // long / unbounded paths: stop as soon as the wavefront is empty
+            uint32_t alive[8];
+            CU_TRY(cudaMemcpyAsync(alive, w.counts + (size_t) (b + 1) * 8, sizeof(alive), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (alive[0] + alive[1] + alive[2] + alive[3] == 0) break;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    return B200PT_OK;
+}
+
+static RenderCfg make_cfg(const b200pt_scene *s, const b200pt_render_params *p) {
+    RenderCfg c; memset(&c, 0, sizeof(c));
+    c.seed_value = s->dev.base_seed + p->seed;
+    c.spp = p->spp;
+    c.max_depth = p->max_depth < 0 ? 0xffffffffu : (uint32_t) p->max_depth;
+    c.rr_depth = (uint32_t) std::max(1, p->rr_depth);
+    c.hide_emitters = p->hide_emitters; c.prb = p->prb;
+    return c;
+}
+
+static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix) {
+    size_t lanes = p->chunk_lanes;
+    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 20); }
+    size_t px = std::max<size_t>(1, lanes / std::max(1u, p->spp));
+    (void) s;
+    return std::min<size_t>(px, std::max(1u, n_pix));
+}
+
+static b200pt_status validate_params(const b200pt_scene *s, const b200pt_render_params *p) {
+    if (!s || !p) return fail(B200PT_ERR_INVALID, "null argument");
+    if (p->spp == 0) return fail(B200PT_ERR_INVALID, "spp must be > 0");
+    if (p->max_depth < -1) return fail(B200PT_ERR_INVALID, "\"max_depth\" must be set to -1 (infinite) or a value >= 0");
+    if (p->rr_depth <= 0) return fail(B200PT_ERR_INVALID, "\"rr_depth\" must be set to a value greater than zero!");
+    if ((uint64_t) s->dev.crop_w * s->dev.crop_h * p->spp > 0xffffffffull)
+        return fail(B200PT_ERR_UNSUPPORTED, "more than 2^32 samples: split the render into passes (integrator.cpp:276-294)");
+    return B200PT_OK;
+}
+
+static void begin_stats(b200pt_scene *s, cudaStream_t st) {
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->trace_ev_used = 0;
+    cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), st);
+    cudaEventRecord(s->ev0, st);
+}
+
+static b200pt_status end_stats(b200pt_scene *s, cudaStream_t st, uint64_t samples) {
+    CU_TRY(cudaEventRecord(s->ev1, st));
+    unsigned long long h[ST_COUNT];
+    CU_TRY(cudaMemcpyAsync(h, s->stats_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f; CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->stats.device_ms = ms; s->stats.samples = samples; s->stats.bounces = h[ST_BOUNCES]; s->stats.shadow_rays = h[ST_SHADOW];
+    s->stats.trace_rays = h[ST_CLOSEST] + h[ST_SHADOW];
+    double tms = 0;
+    for (size_t i = 0; i + 1 < s->trace_ev_used; i += 2) { float m = 0.f; if (cudaEventElapsedTime(&m, s->trace_events[i], s->trace_events[i + 1]) == cudaSuccess) tms += m; }
+    s->stats.trace_ms = tms;
+    return B200PT_OK;
+}
+
+extern "C" {
+
+b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_params *p, float *film_device, void *cuda_stream) {
+    b200pt_status vs = validate_params(s, p); if (vs) return vs;
+    if (!film_device) return fail(B200PT_ERR_INVALID, "null film");
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    b200pt_status e = ensure_pix_ids(s, p); if (e) return e;
+    begin_stats(s, st);
+    if (p->max_depth == 0 || s->n_pix_ids == 0) {
+        // path.cpp:102: nothing to trace; the film still receives the sample weights
+        return end_stats(s, st, 0);
+    }
+    RenderCfg cfg = make_cfg(s, p);
+    size_t cpx = chunk_pixels(s, p, s->n_pix_ids);
+    e = ensure_wavefront(s, cpx * p->spp, false); if (e) return e;
+    for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
+        size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
+        cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p->spp);
+        e = run_chunk(s, cfg, 0, st); if (e) return e;
+        launch_splat(s->dev, cfg, s->pix_ids, s->wf.lane_result, film_device, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+        s->stats.kernel_launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return end_stats(s, st, (uint64_t) s->n_pix_ids * p->spp);
+}
+
+b200pt_status b200pt_develop(b200pt_scene *s, const float *film_device, float *out_device, void *cuda_stream) {
+    if (!s || !film_device || !out_device) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    launch_develop(s->dev, film_device, out_device, st);
+    CU_TRY(cudaGetLastError());
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_render(b200pt_scene *s, const b200pt_render_params *p, float *out_host) {
+    if (!s || !out_host) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    size_t npix = (size_t) s->dev.crop_w * s->dev.crop_h;
+    CU_TRY(cudaMemsetAsync(s->film_own, 0, npix * 4 * sizeof(float), s->stream));
+    b200pt_status e = b200pt_render_accumulate(s, p, s->film_own, s->stream); if (e) return e;
+    e = b200pt_develop(s, s->film_own, s->out_dev, s->stream); if (e) return e;
+    CU_TRY(cudaMemcpyAsync(out_host, s->out_dev, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render_params *p_, const float *grad_in_device, void *cuda_stream) {
+    b200pt_status vs = validate_params(s, p_); if (vs) return vs;
+    if (!grad_in_device) return fail(B200PT_ERR_INVALID, "null grad_in");
+    b200pt_render_params p = *p_; p.prb = 1;
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    begin_stats(s, st);
+    if (p.max_depth == 0) return end_stats(s, st, 0);
+    RenderCfg cfg = make_cfg(s, &p);
+    const DevScene &d = s->dev;
+    size_t npix = (size_t) d.crop_w * d.crop_h;
+    if (d.rfilter != B200PT_RFILTER_BOX) {
+        // accumulated filter weights of THIS sample set over the whole frame (common.py:696-746):
+        // cheap (RNG + splat of the weight channel), so every shard computes the full image itself
+        b200pt_render_params all = p; all.shard_rank = 0; all.shard_count = 1;
+        b200pt_status e = ensure_pix_ids(s, &all); if (e) return e;
+        CU_TRY(cudaMemsetAsync(s->film_w, 0, npix * 4 * sizeof(float), st));
+        RenderCfg wc = cfg; wc.chunk_pix0 = 0;
+        size_t cpx = std::max<size_t>(1, ((size_t) 1 << 24) / p.spp);
+        for (size_t pix0 = 0; pix0 < npix; pix0 += cpx) {
+            size_t npx = std::min(cpx, npix - pix0);
+            wc.chunk_pix0 = (uint32_t) pix0; wc.chunk_lanes = (uint32_t) (npx * p.spp);
+            launch_weights(d, wc, s->pix_ids, s->film_w, grid_for(s, wc.chunk_lanes), st);
+            s->stats.kernel_launches++;
+        }
+    }
+    b200pt_status e = ensure_pix_ids(s, &p); if (e) return e;
+    if (s->n_pix_ids == 0) return end_stats(s, st, 0);
+    size_t cpx = chunk_pixels(s, &p, s->n_pix_ids);
+    e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
+    for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
+        size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
+        cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
+        // pass 1: primal with the same stream (sampler.clone(), common.py:752) -> L per lane
+        e = run_chunk(s, cfg, 0, st); if (e) return e;
+        // dL per lane: adjoint of splat + develop
+        launch_splat_adjoint(d, cfg, s->pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, cfg.chunk_lanes), st);
+        s->stats.kernel_launches++;
+        // pass 2: adjoint replay (common.py:765)
+        e = run_chunk(s, cfg, 1, st); if (e) return e;
+    }
+    CU_TRY(cudaGetLastError());
+    return end_stats(s, st, (uint64_t) s->n_pix_ids * p.spp);
+}
+
+b200pt_status b200pt_render_backward(b200pt_scene *s, const b200pt_render_params *p, const float *grad_in_host) {
+    if (!s || !grad_in_host) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    size_t npix = (size_t) s->dev.crop_w * s->dev.crop_h;
+    CU_TRY(cudaMemcpyAsync(s->grad_in_dev, grad_in_host, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    b200pt_status e = b200pt_render_backward_device(s, p, s->grad_in_dev, s->stream); if (e) return e;
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_grad_zero(b200pt_scene *s) {
+    if (!s) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaMemsetAsync(s->dev.grad, 0, std::max<size_t>(s->grad_floats, 1) * sizeof(float), s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_grad_offset(b200pt_scene *s, uint32_t tex, size_t *offset, size_t *n) {
+    if (!s || tex >= s->tex.size()) return fail(B200PT_ERR_INVALID, "texture index out of range");
+    if (!s->tex[tex].differentiable) return fail(B200PT_ERR_INVALID, "texture is not differentiable");
+    if (offset) *offset = s->tex[tex].grad_offset;
+    if (n) *n = s->tex[tex].n;
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_grad_read(b200pt_scene *s, uint32_t tex, float *host_out, size_t n) {
+    size_t off = 0, cnt = 0;
+    b200pt_status e = b200pt_grad_offset(s, tex, &off, &cnt); if (e) return e;
+    if (n != cnt || !host_out) return fail(B200PT_ERR_INVALID, "gradient size mismatch");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaMemcpy(host_out, s->dev.grad + off, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_grad_device_view(b200pt_scene *s, float **ptr, size_t *n) {
+    if (!s || !ptr || !n) return fail(B200PT_ERR_INVALID, "null argument");
+    *ptr = s->dev.grad; *n = s->grad_floats;
+    return B200PT_OK;
+}
+
+// ---- operators ----------------------------------------------------------------
+b200pt_status b200pt_ray_intersect(b200pt_scene *s, uint32_t n, const float *rays_host, float *t_out, float *uv_out, uint32_t *prim_out, int32_t *shape_out) {
+    if (!s || (n && (!rays_host || !t_out || !uv_out || !prim_out || !shape_out))) return fail(B200PT_ERR_INVALID, "null argument");
+    if (n == 0) return B200PT_OK;   // empty batch
+    CU_TRY(cudaSetDevice(s->device));
+    float *dr, *dt, *duv; uint32_t *dp; int32_t *ds;
+    CU_TRY(cudaMalloc(&dr, (size_t) n * 28)); CU_TRY(cudaMalloc(&dt, (size_t) n * 4)); CU_TRY(cudaMalloc(&duv, (size_t) n * 8));
+    CU_TRY(cudaMalloc(&dp, (size_t) n * 4)); CU_TRY(cudaMalloc(&ds, (size_t) n * 4));
+    CU_TRY(cudaMemcpyAsync(dr, rays_host, (size_t) n * 28, cudaMemcpyHostToDevice, s->stream));
+    Launch L = s->launch; L.grid = grid_for(s, n);
+    launch_ray_intersect(s->dev, n, dr, dt, duv, dp, ds, L, s->stream);
+    CU_TRY(cudaMemcpyAsync(t_out, dt, (size_t) n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaMemcpyAsync(uv_out, duv, (size_t) n * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaMemcpyAsync(prim_out, dp, (size_t) n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaMemcpyAsync(shape_out, ds, (size_t) n * 4, cudaMemcpyDeviceToHost, s->stream));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(dr); cudaFree(dt); cudaFree(duv); cudaFree(dp); cudaFree(ds);
+    CU_TRY(e);
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_ray_test(b200pt_scene *s, uint32_t n, const float *rays_host, uint8_t *hit_out) {
+    if (!s || (n && (!rays_host || !hit_out))) return fail(B200PT_ERR_INVALID, "null argument");
+    if (n == 0) return B200PT_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    float *dr; uint8_t *dh;
+    CU_TRY(cudaMalloc(&dr, (size_t) n * 28)); CU_TRY(cudaMalloc(&dh, n));
+    CU_TRY(cudaMemcpyAsync(dr, rays_host, (size_t) n * 28, cudaMemcpyHostToDevice, s->stream));
+    Launch L = s->launch; L.grid = grid_for(s, n);
+    launch_ray_test(s->dev, n, dr, dh, L, s->stream);
+    CU_TRY(cudaMemcpyAsync(hit_out, dh, n, cudaMemcpyDeviceToHost, s->stream));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(dr); cudaFree(dh);
+    CU_TRY(e);
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *s, uint32_t bsdf, uint32_t n, const float *in_host, float *out_host) {
+    if (!s || (n && (!in_host || !out_host))) return fail(B200PT_ERR_INVALID, "null argument");
+    if (bsdf >= s->dev.n_bsdfs) return fail(B200PT_ERR_INVALID, "BSDF index out of range");
+    if (n == 0) return B200PT_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    float *di, *dout;
+    CU_TRY(cudaMalloc(&di, (size_t) n * 44)); CU_TRY(cudaMalloc(&dout, (size_t) n * 56));
+    CU_TRY(cudaMemcpyAsync(di, in_host, (size_t) n * 44, cudaMemcpyHostToDevice, s->stream));
+    DevBsdf hb; CU_TRY(cudaMemcpy(&hb, s->dev.bsdfs + bsdf, sizeof(hb), cudaMemcpyDeviceToHost));
+    launch_bsdf_eval(s->dev, bsdf, hb.type, n, di, dout, s->stream);
+    CU_TRY(cudaMemcpyAsync(out_host, dout, (size_t) n * 56, cudaMemcpyDeviceToHost, s->stream));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(di); cudaFree(dout);
+    CU_TRY(e);
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_get_stats(b200pt_scene *s, b200pt_stats *out) {
+    if (!s || !out) return fail(B200PT_ERR_INVALID, "null argument");
+    *out = s->stats;
+    return B200PT_OK;
+}
+
+// size of the ABI structs as compiled (checked against the ctypes mirror by tests/test_abi.py)
+size_t b200pt_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(b200pt_texture); case 1: return sizeof(b200pt_bsdf); case 2: return sizeof(b200pt_shape);
+        case 3: return sizeof(b200pt_emitter); case 4: return sizeof(b200pt_sensor); case 5: return sizeof(b200pt_scene_desc);
+        case 6: return sizeof(b200pt_render_params); case 7: return sizeof(b200pt_stats);
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,710 @@
+// kernels.cu -- the wavefront kernels of the B200 path tracer (sm_100a).
+//
+// One wavefront per bounce:
+//
+//   k_generate      lane -> pixel, TEA/PCG32 seeding, primary ray          (integrator.cpp:322-339,448-485)
+//   k_trace         persistent BVH traversal: resolves the pending NEE shadow ray of
+//                   every slot (Scene::ray_test), then the closest hit of its path ray
+//                   (Scene::ray_intersect_preliminary) and bins the slot into the
+//                   queue of the material it hit (warp-ballot bucket pass)
+//   k_shade<TYPE>   one branch-flattened kernel per BSDF model over its material
+//                   queue: surface interaction, emitter hit + MIS, NEE sample, BSDF
+//                   eval/sample, russian roulette; writes the survivors COMPACTED
+//                   into the other state buffer (warp-aggregated slot allocation)
+//   k_splat_*       ImageBlock::put (box / gaussian), k_develop: HDRFilm::develop
+//
+// The path state lives in HBM as structure-of-arrays float4 vectors (kernels.cuh).
+// BVH nodes/triangles of the top of the tree are staged into shared memory with a
+// bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) once per persistent CTA.
+#include "kernels.cuh"
+
+namespace pt {
+
+// ---------------------------------------------------------------------------
+// TMA bulk copy global -> shared, completion on an mbarrier
+// ---------------------------------------------------------------------------
+PT_DEV uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+PT_DEV void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PT_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PT_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+PT_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// Stage `n_nodes` BVH nodes (64 B each) and `n_tris` triangles (48 B each) into
+// shared memory. One elected thread arms the barrier and issues the copies in
+// <= 32 KiB pieces; everybody waits on the barrier's phase 0.
+PT_DEV void stage_bvh(const DevScene &sc, float4 *s_nodes, float4 *s_tris, uint32_t n_nodes, uint32_t n_tris, uint64_t *bar) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t nb = n_nodes * 64u, tb = n_tris * 48u;
+        mbar_expect_tx(bar, nb + tb);
+        const char *src = (const char *) sc.nodes; char *dst = (char *) s_nodes;
+        for (uint32_t off = 0; off < nb; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, nb - off), bar);
+        src = (const char *) sc.tris; dst = (char *) s_tris;
+        for (uint32_t off = 0; off < tb; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, tb - off), bar);
+    }
+    mbar_wait(bar, 0);
+}
+
+// ---------------------------------------------------------------------------
+// BVH traversal (bvh.h layout). The ray/triangle test is the reference's
+// Moeller-Trumbore (mesh.h:1132-1153); boxes only cull.
+// ---------------------------------------------------------------------------
+struct Hit { float t, u, v; uint32_t prim; };
+
+struct TraceCtx {
+    const float4 *s_nodes, *s_tris;   // shared-memory copies (top of the tree / all triangles)
+    const float4 *g_nodes, *g_tris;
+    uint32_t n_smem_nodes, n_smem_tris;
+};
+
+PT_DEV float4 ld_node(const TraceCtx &c, uint32_t node, int k) {
+    return node < c.n_smem_nodes ? c.s_nodes[4 * node + k] : __ldg(&c.g_nodes[4 * (size_t) node + k]);
+}
+PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
+    return tri < c.n_smem_tris ? c.s_tris[3 * tri + k] : __ldg(&c.g_tris[3 * (size_t) tri + k]);
+}
+
+PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
+
+// slab test, subtraction first (no cancellation against o * inv)
+PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, float3 o, float3 inv, float tmax, float &tnear) {
+    float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+    float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+    float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+    float tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+    tnear = tmin;
+    return tmin <= tmx * 1.0000004f;
+}
+
+template <bool ANY>
+PT_DEV bool intersect_leaf(const TraceCtx &c, int32_t leaf, float3 o, float3 d, float &maxt, Hit &hit) {
+    uint32_t enc = (uint32_t) ~leaf, first = enc >> 3, count = (enc & 7u) + 1u;
+    bool found = false;
+    for (uint32_t i = first; i < first + count; ++i) {
+        float4 a = ld_tri(c, i, 0), b = ld_tri(c, i, 1), e = ld_tri(c, i, 2);
+        float t, u, v;
+        if (moeller_trumbore(o, d, maxt, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(e.x, e.y, e.z), t, u, v)) {
+            if (ANY) return true;
+            uint32_t prim = __float_as_uint(a.w);
+            // closest hit; ties keep the smallest (shape, prim) index like a linear scan would
+            if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; maxt = t; found = true; }
+        }
+    }
+    return found;
+}
+
+template <bool ANY>
+PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit) {
+    hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
+    float3 inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    int32_t stack[64]; int sp = 0;
+    int32_t node = 0;
+    bool any = false;
+    while (true) {
+        float4 n0 = ld_node(c, node, 0), n1 = ld_node(c, node, 1), n2 = ld_node(c, node, 2), n3 = ld_node(c, node, 3);
+        int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+        float tl, tr;
+        bool hl = cl != 0x7fffffff && box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl);
+        bool hr = cr != 0x7fffffff && box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr);
+        // leaves are intersected immediately (they may shrink maxt before the sibling is entered)
+        if (hl && cl < 0) { if (intersect_leaf<ANY>(c, cl, o, d, maxt, hit)) { if (ANY) return true; any = true; } hl = false; }
+        if (hr && cr < 0) {
+            if (!(tr > maxt)) { if (intersect_leaf<ANY>(c, cr, o, d, maxt, hit)) { if (ANY) return true; any = true; } }
+            hr = false;
+        }
+        if (hl && tl > maxt) hl = false;
+        if (hr && tr > maxt) hr = false;
+        if (hl && hr) {
+            bool left_first = tl <= tr;
+            stack[sp++] = left_first ? cr : cl;
+            node = left_first ? cl : cr;
+        } else if (hl) node = cl;
+        else if (hr) node = cr;
+        else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return any;
+}
+
+// ---------------------------------------------------------------------------
+// k_generate -- SamplingIntegrator::render JIT branch (integrator.cpp:322-339) +
+// render_sample up to the sensor ray (integrator.cpp:461-485).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids, PathBuf buf,
+                                                    const float4 *__restrict__ adj_dL_lane, const float4 *__restrict__ adj_L_lane) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.chunk_lanes; i += stride) {
+        uint32_t lp = cfg.chunk_pix0 + i / cfg.spp, s = i % cfg.spp;
+        uint32_t pixel = __ldg(&pix_ids[lp]);
+        uint32_t lane = pixel * cfg.spp + s;
+        uint32_t py = pixel / sc.crop_w, px = pixel - py * sc.crop_w;
+        Pcg32 rng; rng.seed_lane(cfg.seed_value, lane);
+        float u1 = rng.next_f32(), u2 = rng.next_f32();
+        float posx = (float) (px + sc.crop_x) + u1, posy = (float) (py + sc.crop_y) + u2;
+        float scx = fdiv(1.f, (float) sc.crop_w), scy = fdiv(1.f, (float) sc.crop_h);
+        float ax = __fmaf_rn(posx, scx, -(float) sc.crop_x * scx), ay = __fmaf_rn(posy, scy, -(float) sc.crop_y * scy);
+        Ray ray = sample_camera_ray(sc, ax, ay);
+        buf.ray_o[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.maxt);
+        buf.ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 1.f);        // prev_bsdf_pdf = 1
+        buf.thr[i] = make_float4(1.f, 1.f, 1.f, 1.f);                      // throughput, eta
+        buf.prev[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PF_PREV_DELTA | PF_ALIVE));
+        buf.rng[i] = make_uint4((uint32_t) rng.state, (uint32_t) (rng.state >> 32), lane, i);
+        buf.result[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cfg.adjoint) { buf.adj_L[i] = adj_L_lane[i]; buf.adj_dL[i] = adj_dL_lane[i]; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_trace -- persistent traversal kernel. Per slot of the current buffer:
+//   1. pending NEE shadow ray (Scene::ray_test, scene.cpp:232/344): unoccluded ->
+//      result += contribution (path.cpp:279-280)
+//   2. if the lane is alive: closest hit (scene.cpp:216) -> hit record, bin the slot
+//      into the queue of the BSDF model it hit; a miss ends the path
+//   3. finished lanes write their radiance to lane_result (consumed by k_splat)
+// ---------------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(BLOCK) k_trace(DevScene sc, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
+                                                 Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
+                                                 unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    float4 *s_nodes = (float4 *) smem_raw;
+    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+
+    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    uint32_t n_shadow = 0, n_closest = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
+        uint32_t i = base + lane_id;
+        bool valid = i < n;
+        int mytype = -1;
+        if (valid) {
+            uint32_t flags = __float_as_uint(cur.prev[i].w);
+            float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool res_loaded = false;
+            if (!FIRST && (flags & PF_HAS_SHADOW)) {
+                float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                Hit h; n_shadow++;
+                bool occluded = traverse<true>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
+                if (!occluded) {
+                    float2 c = cur.sh_c[i];
+                    res = cur.result[i]; res_loaded = true;
+                    res.x += sd.w; res.y += c.x; res.z += c.y;
+                    cur.result[i] = res;
+                }
+            }
+            bool finished = !(flags & PF_ALIVE);
+            if (!finished) {
+                float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                float3 o = V(ro.x, ro.y, ro.z), d = V(rd.x, rd.y, rd.z);
+                float maxt = ro.w;
+                Hit h; n_closest++;
+                bool found = traverse<false>(ctx, o, d, maxt, h);
+                if (FIRST && cfg.hide_emitters) {
+                    // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
+                    while (found && sc.shapes[__ldg(&sc.prim_verts[h.prim]).w].emitter >= 0) {
+                        SurfaceInteraction si = compute_si(sc, h.t, h.u, h.v, h.prim, d);
+                        Ray r = spawn_ray(si.p, si.n, d);
+                        o = r.o; maxt = r.maxt;
+                        cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
+                        found = traverse<false>(ctx, o, d, maxt, h);
+                    }
+                }
+                if (found) {
+                    hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                    const DevShape &sh = sc.shapes[__ldg(&sc.prim_verts[h.prim]).w];
+                    mytype = sc.bsdfs[sh.bsdf].type;
+                } else finished = true;   // path.cpp:225: si invalid, no environment emitter
+            }
+            if (finished) {
+                if (!res_loaded) res = cur.result[i];
+                lane_result[cur.rng[i].w] = res;
+            }
+        }
+        __syncwarp();
+        // bucket pass: bin the slot by material id (one atomic per warp and material)
+#pragma unroll
+        for (int t = 0; t < N_BSDF_TYPES; ++t) {
+            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
+            if (m) {
+                uint32_t leader = __ffs(m) - 1, off = 0;
+                if (lane_id == leader) off = atomicAdd(&qcounts[t], __popc(m));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = i;
+            }
+        }
+    }
+    // statistics: one atomic per warp
+    for (int o = 16; o; o >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, o); }
+    if (lane_id == 0) {
+        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative fp32 gradient scatter (adjoint of tex_eval3). Called by all 32
+// lanes at a converged point; lanes without a request pass tex = -1. Lanes that
+// target the same texel are combined with __match_any_sync + shuffles so that the
+// texture receives ONE atomicAdd per distinct (texel, channel) and warp -- the
+// contention fix for few-texel parameters (constant albedo = 3 floats).
+// ---------------------------------------------------------------------------
+PT_DEV void warp_scatter3(const DevScene &sc, int32_t tex, float2 uv, float3 g) {
+    const uint32_t lane_id = threadIdx.x & 31u;
+    bool has = tex >= 0 && sc.textures[tex >= 0 ? tex : 0].differentiable && (g.x != 0.f || g.y != 0.f || g.z != 0.f);
+    if (!__any_sync(0xffffffffu, has)) return;
+    TexTaps tp; tp.n = 0;
+    int C = 3; float *grad = nullptr; bool is_const = false;
+    if (has) {
+        const DevTexture &t = sc.textures[tex];
+        C = t.channels; grad = sc.grad + t.grad_offset;
+        if (t.kind == B200PT_TEX_CONST) { tp.n = 1; tp.idx[0] = 0; tp.w[0] = 1.f; is_const = true; }
+        else tex_lookup(t, uv, tp);
+    }
+    for (int k = 0; k < 4; ++k) {
+        bool hk = has && k < tp.n;
+        if (!__any_sync(0xffffffffu, hk)) break;
+        unsigned long long key = hk ? (((unsigned long long) (uint32_t) tex << 32) | (uint32_t) tp.idx[k]) : ~0ull;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        float w = hk ? tp.w[k] : 0.f;
+        float v0 = g.x * w, v1 = g.y * w, v2 = g.z * w;
+        uint32_t leader = __ffs(peers) - 1;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (uint32_t m = peers; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            s0 += __shfl_sync(peers, v0, src); s1 += __shfl_sync(peers, v1, src); s2 += __shfl_sync(peers, v2, src);
+        }
+        if (hk && lane_id == leader) {
+            if (C == 1) atomicAdd(grad + (is_const ? 0 : tp.idx[k]), s0 + s1 + s2);
+            else { float *gp = grad + (size_t) tp.idx[k] * 3; atomicAdd(gp, s0); atomicAdd(gp + 1, s1); atomicAdd(gp + 2, s2); }
+        }
+    }
+}
+
+// BSDF parameter adjoint at one vertex (prb.py:263-313 restricted to texture parameters):
+//   d/dtheta [ g_dir . f(wo_em; theta) + g_ind . f(wo_s; theta) / f(wo_s) ]
+// Returns the gradient w.r.t. the (single) differentiable colour texture of the model and its slot.
+template <int TYPE>
+PT_DEV float3 bsdf_backward(const DevScene &sc, const DevBsdf &b, float2 uv, float3 wi, float3 wo_em, float3 wo_s, float3 g_dir, float3 g_ind, int32_t &tex) {
+    tex = -1;
+    if (b.twosided && wi.z < 0.f) { wi.z = -wi.z; wo_em.z = -wo_em.z; wo_s.z = -wo_s.z; }
+    if (TYPE == B200PT_BSDF_DIFFUSE) {
+        tex = b.tex[B200PT_SLOT_REFLECTANCE];
+        float3 rho = tex_eval3(sc, tex, uv);
+        float3 g = V(0.f, 0.f, 0.f);
+        if (wi.z > 0.f && wo_em.z > 0.f) g = g_dir * (PT_INV_PI * wo_em.z);
+        if (wi.z > 0.f && wo_s.z > 0.f)
+            g = g + V(rho.x != 0.f ? fdiv(g_ind.x, rho.x) : 0.f, rho.y != 0.f ? fdiv(g_ind.y, rho.y) : 0.f, rho.z != 0.f ? fdiv(g_ind.z, rho.z) : 0.f);
+        return g;
+    }
+    return V(0.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// k_shade<TYPE> -- loop body of PathIntegrator::sample (path.cpp:193-340) /
+// PRBIntegrator.sample (prb.py:125-333) for the lanes whose hit has BSDF model
+// TYPE. ADJOINT = PRB backward pass: replays the path, resolves the NEE
+// visibility inline and scatters the parameter gradients (prb.py:263-313).
+// ---------------------------------------------------------------------------
+template <int TYPE, bool ADJOINT>
+__global__ void __launch_bounds__(BLOCK) k_shade(DevScene sc, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
+                                                 const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, PathBuf nxt,
+                                                 uint32_t *__restrict__ nxt_count, float4 *__restrict__ lane_result,
+                                                 unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    TraceCtx ctx = { nullptr, nullptr, sc.nodes, sc.tris, 0, 0 };
+    if (ADJOINT) {
+        float4 *s_nodes = (float4 *) smem_raw;
+        float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+        stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+        ctx.s_nodes = s_nodes; ctx.s_tris = s_tris; ctx.n_smem_nodes = n_smem_nodes; ctx.n_smem_tris = n_smem_tris;
+    }
+    const uint32_t n = *qcount;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    const bool prb = cfg.prb != 0;
+    uint32_t n_bounces = 0, n_shadow = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
+        uint32_t qi = base + lane_id;
+        bool valid = qi < n;
+        bool write_next = false;
+        // state of the lane after this vertex
+        float4 o_ro, o_rd, o_thr, o_prev, o_res, o_sho, o_shd, o_L, o_dL; float2 o_shc; uint4 o_rng;
+        // gradient scatter requests of this vertex (adjoint)
+        int32_t gt0 = -1, gt1 = -1, gt2 = -1; float2 guv0 = make_float2(0.f, 0.f), guv1 = guv0, guv2 = guv0;
+        float3 gv0 = V(0.f, 0.f, 0.f), gv1 = gv0, gv2 = gv0;
+        if (valid) {
+            n_bounces++;
+            uint32_t slot = __ldg(&queue[qi]);
+            float4 rd = cur.ray_d[slot], th = cur.thr[slot], pv = cur.prev[slot], hr = hit_in[slot], res = cur.result[slot];
+            uint4 rs = cur.rng[slot];
+            float3 ray_d = V(rd.x, rd.y, rd.z);
+            float prev_bsdf_pdf = rd.w;
+            float3 throughput = V(th.x, th.y, th.z); float eta = th.w;
+            float3 prev_p = V(pv.x, pv.y, pv.z);
+            uint32_t flags = __float_as_uint(pv.w), depth = flags & PF_DEPTH_MASK;
+            bool prev_delta = (flags & PF_PREV_DELTA) != 0;
+            float3 result = V(res.x, res.y, res.z);
+            Pcg32 rng; rng.restore(cfg.seed_value, rs.z, ((uint64_t) rs.y << 32) | rs.x);
+            float3 L = V(0.f, 0.f, 0.f), dL = V(0.f, 0.f, 0.f);
+            if (ADJOINT) { float4 a = cur.adj_L[slot], b = cur.adj_dL[slot]; L = V(a.x, a.y, a.z); dL = V(b.x, b.y, b.z); }
+
+            SurfaceInteraction si = compute_si(sc, hr.x, hr.y, hr.z, __float_as_uint(hr.w), ray_d);
+            const DevShape &sh = sc.shapes[si.shape];
+            const DevBsdf &bsdf = sc.bsdfs[sh.bsdf];
+
+            // ---- direct emission (path.cpp:206-222, prb.py:151-163)
+            float3 Le = V(0.f, 0.f, 0.f);
+            if (sh.emitter >= 0) {
+                float3 rel = si.p - prev_p;
+                float dist = __fsqrt_rn(vsqnorm(rel));
+                float3 d = V(fdiv(rel.x, dist), fdiv(rel.y, dist), fdiv(rel.z, dist));
+                float em_pdf = prev_delta ? 0.f : pdf_emitter_direction(sc, sh.emitter, d, si.sh_n, dist);
+                float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
+                bool em_active = si.wi.z > 0.f && (prb || prev_bsdf_pdf > 0.f);
+                float3 rad = em_active ? tex_eval3(sc, sc.emitters[sh.emitter].radiance_tex, si.uv) : V(0.f, 0.f, 0.f);
+                if (prb) { Le = (throughput * mis_bsdf) * rad; result = result + Le; }
+                else { Le = throughput * (rad * mis_bsdf); result = vfma(throughput, rad * mis_bsdf, result); }
+                if (ADJOINT && em_active) { gt0 = sc.emitters[sh.emitter].radiance_tex; guv0 = si.uv; gv0 = dL * (throughput * mis_bsdf); }
+            }
+            bool active_next = depth + 1 < cfg.max_depth;
+            if (!active_next) {
+                if (!ADJOINT) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
+            } else {
+                // ---- emitter sampling (path.cpp:238-259): the two randoms are always drawn (JIT semantics)
+                const bool smooth = TYPE == B200PT_BSDF_DIFFUSE || TYPE == B200PT_BSDF_PRINCIPLED;
+                float ex = rng.next_f32(), ey = rng.next_f32();
+                DirectionSample ds; ds.pdf = 0.f; ds.emitter = -1; ds.uv = make_float2(0.f, 0.f);
+                float3 em_weight = V(0.f, 0.f, 0.f), wo = V(0.f, 0.f, 0.f);
+                bool active_em = false;
+                Ray sray; sray.o = V(0.f, 0.f, 0.f); sray.d = V(0.f, 0.f, 0.f); sray.maxt = 0.f;
+                if (smooth) {
+                    em_weight = sample_emitter_direction(sc, si.p, ex, ey, ds);
+                    active_em = ds.pdf != 0.f;
+                    wo = si.to_local(ds.d);
+                    if (ADJOINT && active_em) {
+                        // the adjoint needs Lr_dir now (prb.py:227): resolve the visibility inline
+                        sray = spawn_ray_to(si.p, si.n, ds.p);
+                        Hit h; n_shadow++;
+                        if (traverse<true>(ctx, sray.o, sray.d, sray.maxt, h)) { em_weight = V(0.f, 0.f, 0.f); ds.pdf = 0.f; active_em = false; }
+                    }
+                }
+                // ---- BSDF (path.cpp:263-267)
+                float s1 = rng.next_f32(), s2x = rng.next_f32(), s2y = rng.next_f32();
+                BsdfResult br = bsdf_eval_pdf_sample<TYPE>(sc, bsdf, si.uv, si.wi, wo, s1, s2x, s2y);
+                // NEE contribution (path.cpp:271-281); in the primal passes its visibility is resolved by the next k_trace
+                bool has_shadow = false; float3 contrib = V(0.f, 0.f, 0.f); float mis_em = 0.f;
+                if (active_em) {
+                    mis_em = mis_weight(ds.pdf, br.pdf);
+                    contrib = prb ? ((throughput * mis_em) * br.value) * em_weight : throughput * ((br.value * em_weight) * mis_em);
+                    if (!ADJOINT) {
+                        has_shadow = contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f;
+                        if (has_shadow) sray = spawn_ray_to(si.p, si.n, ds.p);
+                    }
+                }
+                // ---- BSDF sampling (path.cpp:285-313)
+                Ray next = spawn_ray(si.p, si.n, si.to_world(br.bs.wo));
+                float3 beta_vertex = throughput;
+                throughput = throughput * br.weight;
+                eta *= br.bs.eta;
+                // ---- russian roulette (path.cpp:317-331 / prb.py:241-252: prb tests the pre-increment depth)
+                float tmax = vmaxc(throughput);
+                float rr_prob = fminf(tmax * sqr(eta), .95f);
+                bool rr_active = prb ? depth >= cfg.rr_depth : depth + 1 >= cfg.rr_depth;
+                bool rr_continue;
+                if (prb) { if (rr_active) throughput = throughput * rcp_(rr_prob); rr_continue = rng.next_f32() < rr_prob; }
+                else { rr_continue = rng.next_f32() < rr_prob; if (rr_active) throughput = throughput * rcp_(rr_prob); }
+                bool active = (!rr_active || rr_continue) && tmax != 0.f;
+                if (ADJOINT) {
+                    float3 Lr_dir = active_em ? contrib : V(0.f, 0.f, 0.f);
+                    L = (L - Le) - Lr_dir;                                            // prb.py:227
+                    float3 g_dir = active_em ? dL * ((beta_vertex * mis_em) * em_weight) : V(0.f, 0.f, 0.f);
+                    float3 g_ind = active ? dL * L : V(0.f, 0.f, 0.f);
+                    gv1 = bsdf_backward<TYPE>(sc, bsdf, si.uv, si.wi, wo, br.bs.wo, g_dir, g_ind, gt1); guv1 = si.uv;
+                    if (active_em) {
+                        // emitter radiance inside em_weight = radiance / pdf (area.cpp:161)
+                        int32_t rt = sc.emitters[ds.emitter].radiance_tex;
+                        float3 rad = tex_eval3(sc, rt, ds.uv);
+                        gt2 = rt; guv2 = ds.uv;
+                        gv2 = dL * V(rad.x != 0.f ? fdiv(Lr_dir.x, rad.x) : 0.f, rad.y != 0.f ? fdiv(Lr_dir.y, rad.y) : 0.f, rad.z != 0.f ? fdiv(Lr_dir.z, rad.z) : 0.f);
+                    }
+                }
+                if (!active && !has_shadow) {
+                    if (!ADJOINT) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
+                } else {
+                    write_next = true;
+                    uint32_t nf = (depth + 1) | ((br.bs.sampled_type & F_DELTA) ? PF_PREV_DELTA : 0u) | (has_shadow ? PF_HAS_SHADOW : 0u) | (active ? PF_ALIVE : 0u);
+                    o_ro = make_float4(next.o.x, next.o.y, next.o.z, next.maxt);
+                    o_rd = make_float4(next.d.x, next.d.y, next.d.z, br.bs.pdf);
+                    o_thr = make_float4(throughput.x, throughput.y, throughput.z, eta);
+                    o_prev = make_float4(si.p.x, si.p.y, si.p.z, __uint_as_float(nf));
+                    o_res = make_float4(result.x, result.y, result.z, 0.f);
+                    o_sho = make_float4(sray.o.x, sray.o.y, sray.o.z, sray.maxt);
+                    o_shd = make_float4(sray.d.x, sray.d.y, sray.d.z, contrib.x);
+                    o_shc = make_float2(contrib.y, contrib.z);
+                    o_rng = make_uint4((uint32_t) rng.state, (uint32_t) (rng.state >> 32), rs.z, rs.w);
+                    if (ADJOINT) { o_L = make_float4(L.x, L.y, L.z, 0.f); o_dL = make_float4(dL.x, dL.y, dL.z, 0.f); }
+                }
+            }
+        }
+        __syncwarp();
+        if (ADJOINT) {
+            // fp32 atomicAdd scatter into the parameter gradients, combined per warp and texel
+            warp_scatter3(sc, gt0, guv0, gv0);
+            warp_scatter3(sc, gt1, guv1, gv1);
+            warp_scatter3(sc, gt2, guv2, gv2);
+        }
+        // compaction: survivors get consecutive slots of the next buffer (one atomic per warp)
+        uint32_t m = __ballot_sync(0xffffffffu, write_next);
+        if (m) {
+            uint32_t leader = __ffs(m) - 1, off = 0;
+            if (lane_id == leader) off = atomicAdd(nxt_count, __popc(m));
+            off = __shfl_sync(0xffffffffu, off, leader);
+            if (write_next) {
+                uint32_t dst = off + __popc(m & ((1u << lane_id) - 1u));
+                nxt.ray_o[dst] = o_ro; nxt.ray_d[dst] = o_rd; nxt.thr[dst] = o_thr; nxt.prev[dst] = o_prev; nxt.result[dst] = o_res;
+                nxt.rng[dst] = o_rng;
+                if (__float_as_uint(o_prev.w) & PF_HAS_SHADOW) { nxt.sh_o[dst] = o_sho; nxt.sh_d[dst] = o_shd; nxt.sh_c[dst] = o_shc; }
+                if (ADJOINT) { nxt.adj_L[dst] = o_L; nxt.adj_dL[dst] = o_dL; }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) { n_bounces += __shfl_xor_sync(0xffffffffu, n_bounces, o); n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); }
+    if (lane_id == 0 && n_bounces) atomicAdd(&stats[ST_BOUNCES], (unsigned long long) n_bounces);
+    if (lane_id == 0 && n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+}
+
+// ---------------------------------------------------------------------------
+// Film: ImageBlock::put (imageblock.cpp:192-574) + HDRFilm::develop (hdrfilm.cpp:393)
+// ---------------------------------------------------------------------------
+// Box filter: the spp samples of a pixel are consecutive lanes -> one warp per
+// pixel sums them in a fixed order and owns the pixel (no atomics, deterministic).
+__global__ void __launch_bounds__(BLOCK) k_splat_box(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
+                                                     const float4 *__restrict__ lane_result, float *__restrict__ film) {
+    uint32_t n_pix = cfg.chunk_lanes / cfg.spp;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane_id = threadIdx.x & 31u, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp; p < n_pix; p += n_warps) {
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (uint32_t s = lane_id; s < cfg.spp; s += 32) {
+            float4 v = lane_result[(size_t) p * cfg.spp + s];
+            r += v.x; g += v.y; b += v.z;
+        }
+        for (int o = 16; o; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane_id == 0) {
+            uint32_t pixel = __ldg(&pix_ids[cfg.chunk_pix0 + p]);
+            float4 *f = (float4 *) film + pixel;
+            float4 a = *f; a.x += r; a.y += g; a.z += b; a.w += (float) cfg.spp; *f = a;
+        }
+    }
+}
+
+PT_DEV void sample_film_pos(const DevScene &sc, const RenderCfg &cfg, uint32_t pixel, uint32_t s, float &pfx, float &pfy) {
+    uint32_t py = pixel / sc.crop_w, px = pixel - py * sc.crop_w;
+    Pcg32 rng; rng.seed_lane(cfg.seed_value, pixel * cfg.spp + s);
+    float u1 = rng.next_f32(), u2 = rng.next_f32();
+    // position relative to the block: pos + (border - offset - .5) (imageblock.cpp:280)
+    pfx = ((float) (px + sc.crop_x) + u1) + (0.f - (float) sc.crop_x - .5f);
+    pfy = ((float) (py + sc.crop_y) + u2) + (0.f - (float) sc.crop_y - .5f);
+}
+
+// Gaussian (any non-box) filter: scatter with fp32 atomics over the <= 5x5 footprint.
+// WEIGHTS_ONLY accumulates only the weight channel (first pass of the adjoint).
+template <bool WEIGHTS_ONLY>
+__global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
+                                                       const float4 *__restrict__ lane_result, float *__restrict__ film) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    int W = (int) sc.crop_w, H = (int) sc.crop_h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.chunk_lanes; i += stride) {
+        uint32_t pixel = __ldg(&pix_ids[cfg.chunk_pix0 + i / cfg.spp]), s = i % cfg.spp;
+        float pfx, pfy; sample_film_pos(sc, cfg, pixel, s, pfx, pfy);
+        float4 v = WEIGHTS_ONLY ? make_float4(0.f, 0.f, 0.f, 0.f) : lane_result[i];
+        int x0 = max((int) ceilf(pfx - sc.gauss_radius), 0), y0 = max((int) ceilf(pfy - sc.gauss_radius), 0);
+        int x1 = min((int) floorf(pfx + sc.gauss_radius), W - 1), y1 = min((int) floorf(pfy + sc.gauss_radius), H - 1);
+        for (int y = y0; y <= y1; ++y) {
+            float wy = rfilter_eval(sc, (float) y - pfy);
+            for (int x = x0; x <= x1; ++x) {
+                float w = rfilter_eval(sc, (float) x - pfx) * wy;
+                float *f = film + 4 * ((size_t) y * W + x);
+                if (!WEIGHTS_ONLY) { atomicAdd(f + 0, v.x * w); atomicAdd(f + 1, v.y * w); atomicAdd(f + 2, v.z * w); }
+                atomicAdd(f + 3, w);
+            }
+        }
+    }
+}
+
+// Adjoint of splat + develop for one sample (common.py:696-746): dL = sum_pix w * grad_in / W
+__global__ void __launch_bounds__(BLOCK) k_splat_adjoint(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
+                                                         const float *__restrict__ grad_in, const float *__restrict__ film_w, float4 *__restrict__ lane_dL) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    int W = (int) sc.crop_w, H = (int) sc.crop_h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.chunk_lanes; i += stride) {
+        uint32_t pixel = __ldg(&pix_ids[cfg.chunk_pix0 + i / cfg.spp]), s = i % cfg.spp;
+        float3 g = V(0.f, 0.f, 0.f);
+        if (sc.rfilter == B200PT_RFILTER_BOX) {
+            float w = (float) cfg.spp;
+            g = V(fdiv(grad_in[3 * (size_t) pixel], w), fdiv(grad_in[3 * (size_t) pixel + 1], w), fdiv(grad_in[3 * (size_t) pixel + 2], w));
+        } else {
+            float pfx, pfy; sample_film_pos(sc, cfg, pixel, s, pfx, pfy);
+            int x0 = max((int) ceilf(pfx - sc.gauss_radius), 0), y0 = max((int) ceilf(pfy - sc.gauss_radius), 0);
+            int x1 = min((int) floorf(pfx + sc.gauss_radius), W - 1), y1 = min((int) floorf(pfy + sc.gauss_radius), H - 1);
+            for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x) {
+                float w = rfilter_eval(sc, (float) x - pfx) * rfilter_eval(sc, (float) y - pfy);
+                size_t pi = (size_t) y * W + x;
+                float ws = film_w[4 * pi + 3]; if (ws == 0.f) ws = 1.f;
+                g.x = __fmaf_rn(w, fdiv(grad_in[3 * pi], ws), g.x); g.y = __fmaf_rn(w, fdiv(grad_in[3 * pi + 1], ws), g.y); g.z = __fmaf_rn(w, fdiv(grad_in[3 * pi + 2], ws), g.z);
+            }
+        }
+        lane_dL[i] = make_float4(g.x, g.y, g.z, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_develop(uint32_t n_pix, const float *__restrict__ film, float *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+        float4 f = ((const float4 *) film)[i];
+        float w = f.w == 0.f ? 1.f : f.w;
+        out[3 * (size_t) i] = fdiv(f.x, w); out[3 * (size_t) i + 1] = fdiv(f.y, w); out[3 * (size_t) i + 2] = fdiv(f.z, w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Operator kernels (parity tests through the C ABI)
+// ---------------------------------------------------------------------------
+template <bool ANY>
+__global__ void __launch_bounds__(BLOCK) k_ray_query(DevScene sc, uint32_t n, const float *__restrict__ rays, float *__restrict__ t_out, float *__restrict__ uv_out,
+                                                     uint32_t *__restrict__ prim_out, int32_t *__restrict__ shape_out, uint8_t *__restrict__ occ_out,
+                                                     uint32_t n_smem_nodes, uint32_t n_smem_tris) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    float4 *s_nodes = (float4 *) smem_raw;
+    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *r = rays + 7 * (size_t) i;
+        Hit h;
+        bool found = traverse<ANY>(ctx, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h);
+        if (ANY) { occ_out[i] = found ? 1 : 0; continue; }
+        t_out[i] = found ? h.t : PT_INF; uv_out[2 * i] = found ? h.u : 0.f; uv_out[2 * i + 1] = found ? h.v : 0.f;
+        if (found) {
+            uint4 pv = sc.prim_verts[h.prim];
+            shape_out[i] = (int32_t) pv.w; prim_out[i] = h.prim - sc.shapes[pv.w].first_prim;
+        } else { shape_out[i] = -1; prim_out[i] = 0; }
+    }
+}
+
+template <int TYPE>
+__global__ void k_bsdf_eval(DevScene sc, uint32_t bsdf, uint32_t n, const float *__restrict__ in, float *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *q = in + 11 * (size_t) i; float *o = out + 14 * (size_t) i;
+        BsdfResult r = bsdf_eval_pdf_sample<TYPE>(sc, sc.bsdfs[bsdf], make_float2(q[6], q[7]), V(q[0], q[1], q[2]), V(q[3], q[4], q[5]), q[8], q[9], q[10]);
+        o[0] = r.value.x; o[1] = r.value.y; o[2] = r.value.z; o[3] = r.pdf;
+        o[4] = r.bs.wo.x; o[5] = r.bs.wo.y; o[6] = r.bs.wo.z; o[7] = r.bs.pdf; o[8] = r.bs.eta;
+        o[9] = __uint_as_float(r.bs.sampled_type);
+        o[10] = r.weight.x; o[11] = r.weight.y; o[12] = r.weight.z; o[13] = (float) r.bs.sampled_component;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, PathBuf buf, const float4 *adj_dL_lane,
+                     const float4 *adj_L_lane, int grid, cudaStream_t st) {
+    k_generate<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, buf, adj_dL_lane, adj_L_lane);
+}
+
+void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
+                  float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
+    if (first) k_trace<true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else k_trace<false><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+}
+
+template <int TYPE>
+static void launch_shade_t(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
+                           PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st) {
+    if (cfg.adjoint) k_shade<TYPE, true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else k_shade<TYPE, false><<<L.grid, BLOCK, 0, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+}
+
+void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
+                  PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &grid, cudaStream_t st) {
+    switch (type) {
+        case B200PT_BSDF_DIFFUSE: launch_shade_t<B200PT_BSDF_DIFFUSE>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
+        case B200PT_BSDF_CONDUCTOR: launch_shade_t<B200PT_BSDF_CONDUCTOR>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
+        case B200PT_BSDF_DIELECTRIC: launch_shade_t<B200PT_BSDF_DIELECTRIC>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
+        default: launch_shade_t<B200PT_BSDF_PRINCIPLED>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
+    }
+}
+
+void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st) {
+    if (sc.rfilter == B200PT_RFILTER_BOX) k_splat_box<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
+    else k_splat_gauss<false><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
+}
+
+void launch_weights(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, float *film, int grid, cudaStream_t st) {
+    k_splat_gauss<true><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, nullptr, film);
+}
+
+void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,
+                          float4 *lane_dL, int grid, cudaStream_t st) {
+    k_splat_adjoint<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, grad_in, film_w, lane_dL);
+}
+
+void launch_develop(const DevScene &sc, const float *film, float *out, cudaStream_t st) {
+    uint32_t n = sc.crop_w * sc.crop_h;
+    k_develop<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, film, out);
+}
+
+void launch_ray_intersect(const DevScene &sc, uint32_t n, const float *rays, float *t, float *uv, uint32_t *prim, int32_t *shape, const Launch &L, cudaStream_t st) {
+    k_ray_query<false><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, t, uv, prim, shape, nullptr, L.n_smem_nodes, L.n_smem_tris);
+}
+void launch_ray_test(const DevScene &sc, uint32_t n, const float *rays, uint8_t *hit, const Launch &L, cudaStream_t st) {
+    k_ray_query<true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, nullptr, nullptr, nullptr, nullptr, hit, L.n_smem_nodes, L.n_smem_tris);
+}
+void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, const float *in, float *out, cudaStream_t st) {
+    int grid = (int) ((n + 127) / 128); if (grid < 1) grid = 1;
+    switch (type) {
+        case B200PT_BSDF_DIFFUSE: k_bsdf_eval<B200PT_BSDF_DIFFUSE><<<grid, 128, 0, st>>>(sc, bsdf, n, in, out); break;
+        case B200PT_BSDF_CONDUCTOR: k_bsdf_eval<B200PT_BSDF_CONDUCTOR><<<grid, 128, 0, st>>>(sc, bsdf, n, in, out); break;
+        case B200PT_BSDF_DIELECTRIC: k_bsdf_eval<B200PT_BSDF_DIELECTRIC><<<grid, 128, 0, st>>>(sc, bsdf, n, in, out); break;
+        default: k_bsdf_eval<B200PT_BSDF_PRINCIPLED><<<grid, 128, 0, st>>>(sc, bsdf, n, in, out); break;
+    }
+}
+
+void set_trace_smem_attr(size_t bytes) {
+    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+
+} // namespace pt

@@ -1,0 +1,71 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Native code is built once per session (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+    g.build()
+    return True
+
+
+def cbox(res=32, rfilter="box", spp=16, max_depth=8, **film):
+    import mitsuba3_b200 as mb
+    d = mb.cornell_box()
+    d["sensor"]["film"].update(width=res, height=res, rfilter={"type": rfilter}, **film)
+    d["sensor"]["sampler"]["sample_count"] = spp
+    d["integrator"]["max_depth"] = max_depth
+    return d
+
+
+def materials_cbox(res=32, rfilter="box", spp=16, max_depth=8):
+    """Cornell box with conductor / dielectric / principled / twosided materials
+    (same scene as gen_golden.py:materials)."""
+    d = cbox(res, rfilter, spp, max_depth)
+    d["mirror"] = {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}
+    d["glass"] = {"type": "dielectric", "int_ior": "bk7", "ext_ior": "air"}
+    d["pr"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]}, "roughness": 0.3,
+               "metallic": 0.2, "specular": 0.5, "clearcoat": 0.5, "clearcoat_gloss": 0.6, "sheen": 0.3}
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "glass"}
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "mirror"}
+    d["back"]["bsdf"] = {"type": "ref", "id": "pr"}
+    d["floor"]["bsdf"] = {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}}}
+    return d
+
+
+def compare_images(img, ref, rtol=1e-3, floor=1e-2, max_bad_frac=0.005, max_mean_rel=1e-3):
+    """Per-pixel comparison at equal sampler seeds.
+
+    fp32 evaluation-order differences (libm sincos vs CUDA sincosf, 1-ulp
+    divisions) perturb a path's value by ~1e-6 relative; very rarely they flip a
+    discrete decision (russian roulette, lobe choice, edge hit/miss) of a single
+    sample. So: all but `max_bad_frac` of the pixels must agree within `rtol`
+    (relative to max(|ref|, floor)), and the whole-image relative L2 error must
+    stay below `max_mean_rel`."""
+    img = np.asarray(img, np.float64); ref = np.asarray(ref, np.float64)
+    assert img.shape == ref.shape
+    assert np.isfinite(img).all()
+    err = np.abs(img - ref) / np.maximum(np.abs(ref), floor)
+    bad = (err.max(axis=-1) > rtol).mean()
+    l2 = np.sqrt(((img - ref) ** 2).sum() / max((ref ** 2).sum(), 1e-30))
+    assert bad <= max_bad_frac, f"{bad:.5f} of the pixels differ by more than {rtol} (allowed {max_bad_frac})"
+    assert l2 <= max_mean_rel, f"relative L2 error {l2:.3e} > {max_mean_rel}"
+    return bad, l2
