@@ -164,7 +164,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         s->tex.push_back(m);
     }
     s->grad_floats = grad_off;
-    { DevTexture *p; S_TRY(dev_upload(s, htex.data(), htex.size(), &p)); d.textures = p; d.n_textures = desc->n_textures; }
+    d.n_textures = desc->n_textures;
     { float *g = nullptr; S_TRY(cudaMalloc(&g, std::max<size_t>(grad_off, 1) * sizeof(float))); s->allocs.push_back(g); S_TRY(cudaMemset(g, 0, std::max<size_t>(grad_off, 1) * sizeof(float))); d.grad = g; }
 
     // ---- bsdfs / emitters ----------------------------------------------------
@@ -176,7 +176,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         for (int k = 0; k < B200PT_MAX_SLOTS; ++k) if (b.tex[k] >= (int32_t) desc->n_textures) S_FAIL(B200PT_ERR_INVALID, "BSDF references a missing texture");
         hb[i].eta = b.eta; hb[i].spec_srate = b.spec_srate; hb[i].clearcoat_srate = b.clearcoat_srate; hb[i].diff_refl_srate = b.diff_refl_srate; hb[i].flags = b.flags;
     }
-    { DevBsdf *p; S_TRY(dev_upload(s, hb.data(), hb.size(), &p)); d.bsdfs = p; d.n_bsdfs = desc->n_bsdfs; }
+    d.n_bsdfs = desc->n_bsdfs;
     std::vector<DevEmitter> he(desc->n_emitters);
     for (uint32_t i = 0; i < desc->n_emitters; ++i) {
         const b200pt_emitter &e = desc->emitters[i];
@@ -185,7 +185,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         if (desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST) S_FAIL(B200PT_ERR_UNSUPPORTED, "textured area lights are outside the hot-path scope");
         he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].pad = 0.f;
     }
-    { DevEmitter *p; S_TRY(dev_upload(s, he.data(), he.size(), &p)); d.emitters = p; d.n_emitters = desc->n_emitters; }
+    d.n_emitters = desc->n_emitters;
 
     // ---- shapes: flatten to one vertex / primitive array ---------------------
     size_t n_verts = 0, n_prims = 0;
@@ -232,7 +232,20 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     }
     { float *p; S_TRY(dev_upload(s, verts.data(), verts.size(), &p)); d.vertices = (const float4 *) p; }
     { uint32_t *p; S_TRY(dev_upload(s, pv.data(), pv.size(), &p)); d.prim_verts = (const uint4 *) p; }
-    { DevShape *p; S_TRY(dev_upload(s, hs.data(), hs.size(), &p)); d.shapes = p; d.n_shapes = desc->n_shapes; }
+    d.n_shapes = desc->n_shapes;
+    {
+        // one contiguous blob: shapes | bsdfs | emitters | textures, every section 16-byte aligned
+        auto al = [](size_t x) { return (x + 15) & ~(size_t) 15; };
+        size_t o_b = al(hs.size() * sizeof(DevShape)), o_e = al(o_b + hb.size() * sizeof(DevBsdf)), o_t = al(o_e + he.size() * sizeof(DevEmitter));
+        size_t total = al(o_t + htex.size() * sizeof(DevTexture));
+        std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
+        memcpy(blob.data(), hs.data(), hs.size() * sizeof(DevShape)); memcpy(blob.data() + o_b, hb.data(), hb.size() * sizeof(DevBsdf));
+        memcpy(blob.data() + o_e, he.data(), he.size() * sizeof(DevEmitter)); memcpy(blob.data() + o_t, htex.data(), htex.size() * sizeof(DevTexture));
+        unsigned char *p; S_TRY(dev_upload(s, blob.data(), blob.size(), &p));
+        d.tables = p; d.tables_bytes = (uint32_t) blob.size(); d.off_bsdfs = (uint32_t) o_b; d.off_emitters = (uint32_t) o_e; d.off_textures = (uint32_t) o_t;
+        d.shapes = (const DevShape *) p; d.bsdfs = (const DevBsdf *) (p + o_b); d.emitters = (const DevEmitter *) (p + o_e); d.textures = (const DevTexture *) (p + o_t);
+        d.geom_bytes = (uint32_t) std::min<size_t>(n_prims * 16 + n_verts * 32, 0x7fffffff); d.n_vertices = (uint32_t) n_verts;
+    }
 
     // ---- BVH ----------------------------------------------------------------
     Bvh bvh = build_bvh(tri9.data(), (uint32_t) n_prims);
@@ -265,9 +278,10 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     // ---- launch geometry: persistent grids, top of the BVH staged in shared memory
     s->launch.n_smem_nodes = std::min<uint32_t>(d.n_nodes, 512);         // 32 KiB of nodes
     s->launch.n_smem_tris = d.n_tris <= 512 ? d.n_tris : 0;              // <= 24 KiB of triangles
-    s->launch.smem_trace = (size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48;
+    s->launch.smem_trace = ((size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
+    s->launch.smem_tables = (d.tables_bytes <= 12288 ? d.tables_bytes : 0) + (d.geom_bytes <= 20480 ? d.geom_bytes : 0);
     s->launch.grid = (int) s->n_sm * 4;
-    set_trace_smem_attr(s->launch.smem_trace);
+    set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
     S_TRY(cudaMalloc(&s->film_own, npix * 4 * sizeof(float))); s->allocs.push_back(s->film_own);
@@ -417,7 +431,7 @@ static RenderCfg make_cfg(const b200pt_scene *s, const b200pt_render_params *p) 
 
 static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix) {
     size_t lanes = p->chunk_lanes;
-    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 20); }
+    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 24); }   // 16 Mi lanes (~6.5 GB of wavefront state): measured optimum, see DESIGN.md
     size_t px = std::max<size_t>(1, lanes / std::max(1u, p->spp));
     (void) s;
     return std::min<size_t>(px, std::max(1u, n_pix));

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <limits>
 #include <queue>
+#include <cstdlib>
 
 namespace pt {
 namespace {
@@ -26,6 +27,7 @@ struct TmpNode { Box box; int32_t left = -1, right = -1; uint32_t first = 0, cou
 
 struct Builder {
     const float *tri; uint32_t n;
+    uint32_t max_leaf = BVH_MAX_LEAF;
     std::vector<Box> tbox; std::vector<float> cent;   // per triangle
     std::vector<uint32_t> order;
     std::vector<TmpNode> tmp;
@@ -38,7 +40,7 @@ struct Builder {
         Box box, cbox;
         for (uint32_t i = first; i < first + count; ++i) { box.grow(tbox[order[i]]); cbox.grow(&cent[3 * order[i]]); }
         tmp[id].box = box; tmp[id].first = first; tmp[id].count = count;
-        if (count <= BVH_MAX_LEAF || depth > 60)
+        if (count <= max_leaf || depth > 60)
             if (count <= 8) return id;
         // binned SAH over the 3 axes
         constexpr int NB = 16;
@@ -65,8 +67,8 @@ struct Builder {
         }
         uint32_t mid;
         float leaf_cost = box.area() * count;
-        if (best_axis < 0 || (count <= BVH_MAX_LEAF && best_cost >= leaf_cost)) {
-            if (count <= BVH_MAX_LEAF) return id;
+        if (best_axis < 0 || (count <= max_leaf && best_cost >= leaf_cost)) {
+            if (count <= max_leaf) return id;
             // degenerate centroids: median split in index order
             mid = first + count / 2;
         } else {
@@ -108,6 +110,7 @@ Bvh build_bvh(const float *tri, uint32_t n) {
         return out;
     }
     Builder b; b.tri = tri; b.n = n;
+    if (const char *e = getenv("B200PT_BVH_LEAF")) b.max_leaf = (uint32_t) std::min(8, std::max(1, atoi(e)));
     b.tbox.resize(n); b.cent.resize(3 * (size_t) n); b.order.resize(n);
     for (uint32_t i = 0; i < n; ++i) {
         b.order[i] = i;

@@ -34,7 +34,7 @@
 namespace pt {
 
 constexpr int32_t BVH_EMPTY = 0x7fffffff;
-constexpr uint32_t BVH_MAX_LEAF = 4;
+constexpr uint32_t BVH_MAX_LEAF = 2;   // measured: 2 beats 1 and 4 on B200 (profiles/r01_tuning.md)
 
 struct BvhNode { float f[12]; int32_t left, right, pad0, pad1; };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");

@@ -51,8 +51,6 @@ PT_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
 // shared memory. One elected thread arms the barrier and issues the copies in
 // <= 32 KiB pieces; everybody waits on the barrier's phase 0.
 PT_DEV void stage_bvh(const DevScene &sc, float4 *s_nodes, float4 *s_tris, uint32_t n_nodes, uint32_t n_tris, uint64_t *bar) {
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t nb = n_nodes * 64u, tb = n_tris * 48u;
         mbar_expect_tx(bar, nb + tb);
@@ -62,6 +60,36 @@ PT_DEV void stage_bvh(const DevScene &sc, float4 *s_nodes, float4 *s_tris, uint3
         for (uint32_t off = 0; off < tb; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, tb - off), bar);
     }
     mbar_wait(bar, 0);
+}
+
+// Scene tables (shapes, BSDFs, emitters, textures) and -- for small scenes -- the shading
+// geometry (prim_verts + packed vertices) are staged into shared memory as well: the
+// shading kernels chase slot -> hit -> primitive -> vertex -> shape -> BSDF -> texture,
+// and every hop that stays on chip removes an L2 round trip from that dependent chain.
+constexpr uint32_t TABLES_SMEM_MAX = 12288, GEOM_SMEM_MAX = 20480;
+PT_DEV uint32_t tables_smem_bytes(const DevScene &sc) {
+    return (sc.tables_bytes <= TABLES_SMEM_MAX ? sc.tables_bytes : 0u) + (sc.geom_bytes <= GEOM_SMEM_MAX ? sc.geom_bytes : 0u);
+}
+// `sc` is the kernel's private copy of the scene descriptor; its pointers are redirected.
+PT_DEV void stage_tables(DevScene &sc, unsigned char *smem, uint64_t *bar, uint32_t phase) {
+    bool st = sc.tables_bytes <= TABLES_SMEM_MAX, sg = sc.geom_bytes <= GEOM_SMEM_MAX;
+    if (!st && !sg) return;
+    uint32_t tb = st ? sc.tables_bytes : 0u, gb = sg ? sc.geom_bytes : 0u;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, tb + gb);
+        if (st) bulk_g2s(smem, sc.tables, tb, bar);
+        if (sg) {
+            uint32_t pvb = sc.n_tris * 16u;
+            bulk_g2s(smem + tb, sc.prim_verts, pvb, bar);
+            bulk_g2s(smem + tb + pvb, sc.vertices, gb - pvb, bar);
+        }
+    }
+    mbar_wait(bar, phase);
+    if (st) {
+        sc.shapes = (const DevShape *) smem; sc.bsdfs = (const DevBsdf *) (smem + sc.off_bsdfs);
+        sc.emitters = (const DevEmitter *) (smem + sc.off_emitters); sc.textures = (const DevTexture *) (smem + sc.off_textures);
+    }
+    if (sg) { sc.prim_verts = (const uint4 *) (smem + tb); sc.vertices = (const float4 *) (smem + tb + sc.n_tris * 16u); }
 }
 
 // ---------------------------------------------------------------------------
@@ -96,53 +124,54 @@ PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float
     return tmin <= tmx * 1.0000004f;
 }
 
-template <bool ANY>
-PT_DEV bool intersect_leaf(const TraceCtx &c, int32_t leaf, float3 o, float3 d, float &maxt, Hit &hit) {
-    uint32_t enc = (uint32_t) ~leaf, first = enc >> 3, count = (enc & 7u) + 1u;
-    bool found = false;
-    for (uint32_t i = first; i < first + count; ++i) {
-        float4 a = ld_tri(c, i, 0), b = ld_tri(c, i, 1), e = ld_tri(c, i, 2);
-        float t, u, v;
-        if (moeller_trumbore(o, d, maxt, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(e.x, e.y, e.z), t, u, v)) {
-            if (ANY) return true;
-            uint32_t prim = __float_as_uint(a.w);
-            // closest hit; ties keep the smallest (shape, prim) index like a linear scan would
-            if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; maxt = t; found = true; }
-        }
-    }
-    return found;
-}
+// Speculative while-while traversal (Aila & Laine, "Understanding the Efficiency of Ray
+// Traversal on GPUs"): every lane walks inner nodes until it has found a leaf, postpones
+// it and keeps walking until ALL lanes of the warp hold a leaf; then the warp tests
+// triangles together. This keeps the two instruction streams (box tests / triangle
+// tests) converged instead of interleaving them per lane.
+constexpr int32_t TRAV_SENTINEL = 0x76543210;
 
 template <bool ANY>
 PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit) {
     hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
     float3 inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
-    int32_t stack[64]; int sp = 0;
-    int32_t node = 0;
+    int32_t stack[64]; stack[0] = TRAV_SENTINEL; int sp = 0;
+    int32_t node = 0, leaf = 0;     // leaf >= 0: none postponed
     bool any = false;
-    while (true) {
-        float4 n0 = ld_node(c, node, 0), n1 = ld_node(c, node, 1), n2 = ld_node(c, node, 2), n3 = ld_node(c, node, 3);
-        int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-        float tl, tr;
-        bool hl = cl != 0x7fffffff && box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl);
-        bool hr = cr != 0x7fffffff && box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr);
-        // leaves are intersected immediately (they may shrink maxt before the sibling is entered)
-        if (hl && cl < 0) { if (intersect_leaf<ANY>(c, cl, o, d, maxt, hit)) { if (ANY) return true; any = true; } hl = false; }
-        if (hr && cr < 0) {
-            if (!(tr > maxt)) { if (intersect_leaf<ANY>(c, cr, o, d, maxt, hit)) { if (ANY) return true; any = true; } }
-            hr = false;
+    while (node != TRAV_SENTINEL) {
+        bool searching = true;
+        while (node >= 0 && node != TRAV_SENTINEL) {
+            float4 n0 = ld_node(c, node, 0), n1 = ld_node(c, node, 1), n2 = ld_node(c, node, 2), n3 = ld_node(c, node, 3);
+            int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+            float tl, tr;
+            bool hl = cl != 0x7fffffff && box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl);
+            bool hr = cr != 0x7fffffff && box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr);
+            if (!hl && !hr) node = stack[sp--];
+            else {
+                node = hl ? cl : cr;
+                if (hl && hr) {
+                    int32_t far = cr;
+                    if (tr < tl) { far = cl; node = cr; }
+                    stack[++sp] = far;
+                }
+            }
+            if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }   // postpone the first leaf
+            if (!__any_sync(__activemask(), searching)) break;
         }
-        if (hl && tl > maxt) hl = false;
-        if (hr && tr > maxt) hr = false;
-        if (hl && hr) {
-            bool left_first = tl <= tr;
-            stack[sp++] = left_first ? cr : cl;
-            node = left_first ? cl : cr;
-        } else if (hl) node = cl;
-        else if (hr) node = cr;
-        else {
-            if (sp == 0) break;
-            node = stack[--sp];
+        while (leaf < 0) {
+            uint32_t enc = (uint32_t) ~leaf, first = enc >> 3, count = (enc & 7u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                float4 a = ld_tri(c, i, 0), b = ld_tri(c, i, 1), e = ld_tri(c, i, 2);
+                float t, u, v;
+                if (moeller_trumbore(o, d, maxt, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(e.x, e.y, e.z), t, u, v)) {
+                    if (ANY) return true;
+                    uint32_t prim = __float_as_uint(a.w);
+                    // closest hit; ties keep the smallest (shape, prim) index like a linear scan would
+                    if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; maxt = t; any = true; }
+                }
+            }
+            leaf = node;
+            if (node < 0) node = stack[sp--];
         }
     }
     return any;
@@ -185,14 +214,18 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
 //   3. finished lanes write their radiance to lane_result (consumed by k_splat)
 // ---------------------------------------------------------------------------
 template <bool FIRST>
-__global__ void __launch_bounds__(BLOCK) k_trace(DevScene sc, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
+__global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
                                                  Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    DevScene sc = sc_in;
     float4 *s_nodes = (float4 *) smem_raw;
     float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
     TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
 
     const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
@@ -227,7 +260,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(DevScene sc, RenderCfg cfg, Pat
                 bool found = traverse<false>(ctx, o, d, maxt, h);
                 if (FIRST && cfg.hide_emitters) {
                     // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
-                    while (found && sc.shapes[__ldg(&sc.prim_verts[h.prim]).w].emitter >= 0) {
+                    while (found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0) {
                         SurfaceInteraction si = compute_si(sc, h.t, h.u, h.v, h.prim, d);
                         Ray r = spawn_ray(si.p, si.n, d);
                         o = r.o; maxt = r.maxt;
@@ -237,7 +270,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(DevScene sc, RenderCfg cfg, Pat
                 }
                 if (found) {
                     hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-                    const DevShape &sh = sc.shapes[__ldg(&sc.prim_verts[h.prim]).w];
+                    const DevShape &sh = sc.shapes[sc.prim_verts[h.prim].w];
                     mytype = sc.bsdfs[sh.bsdf].type;
                 } else finished = true;   // path.cpp:225: si invalid, no environment emitter
             }
@@ -332,19 +365,25 @@ PT_DEV float3 bsdf_backward(const DevScene &sc, const DevBsdf &b, float2 uv, flo
 // visibility inline and scatters the parameter gradients (prb.py:263-313).
 // ---------------------------------------------------------------------------
 template <int TYPE, bool ADJOINT>
-__global__ void __launch_bounds__(BLOCK) k_shade(DevScene sc, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
+__global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : 4) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
                                                  const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, PathBuf nxt,
                                                  uint32_t *__restrict__ nxt_count, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    DevScene sc = sc_in;
     TraceCtx ctx = { nullptr, nullptr, sc.nodes, sc.tris, 0, 0 };
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    uint32_t bvh_bytes = 0;
     if (ADJOINT) {
         float4 *s_nodes = (float4 *) smem_raw;
         float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
         stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
         ctx.s_nodes = s_nodes; ctx.s_tris = s_tris; ctx.n_smem_nodes = n_smem_nodes; ctx.n_smem_tris = n_smem_tris;
+        bvh_bytes = (n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u;
     }
+    stage_tables(sc, smem_raw + bvh_bytes, &bar, ADJOINT ? 1u : 0u);
     const uint32_t n = *qcount;
     const uint32_t lane_id = threadIdx.x & 31u;
     const uint32_t warp_stride = gridDim.x * blockDim.x;
@@ -533,26 +572,76 @@ PT_DEV void sample_film_pos(const DevScene &sc, const RenderCfg &cfg, uint32_t p
     pfy = ((float) (py + sc.crop_y) + u2) + (0.f - (float) sc.crop_y - .5f);
 }
 
-// Gaussian (any non-box) filter: scatter with fp32 atomics over the <= 5x5 footprint.
+// Gaussian (any non-box) filter. The samples of a pixel are consecutive lanes, so a warp
+// usually holds 32 samples of ONE pixel whose footprints lie in the same 5x5 window
+// (floor(pos) +- 2, imageblock.cpp:452-466): the warp reduces the 25 x 4 weighted values
+// with shuffles and issues one fp32 atomicAdd per (tap, channel) instead of 32.
 // WEIGHTS_ONLY accumulates only the weight channel (first pass of the adjoint).
 template <bool WEIGHTS_ONLY>
 __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
                                                        const float4 *__restrict__ lane_result, float *__restrict__ film) {
-    uint32_t stride = gridDim.x * blockDim.x;
-    int W = (int) sc.crop_w, H = (int) sc.crop_h;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.chunk_lanes; i += stride) {
-        uint32_t pixel = __ldg(&pix_ids[cfg.chunk_pix0 + i / cfg.spp]), s = i % cfg.spp;
-        float pfx, pfy; sample_film_pos(sc, cfg, pixel, s, pfx, pfy);
-        float4 v = WEIGHTS_ONLY ? make_float4(0.f, 0.f, 0.f, 0.f) : lane_result[i];
-        int x0 = max((int) ceilf(pfx - sc.gauss_radius), 0), y0 = max((int) ceilf(pfy - sc.gauss_radius), 0);
-        int x1 = min((int) floorf(pfx + sc.gauss_radius), W - 1), y1 = min((int) floorf(pfy + sc.gauss_radius), H - 1);
-        for (int y = y0; y <= y1; ++y) {
-            float wy = rfilter_eval(sc, (float) y - pfy);
-            for (int x = x0; x <= x1; ++x) {
-                float w = rfilter_eval(sc, (float) x - pfx) * wy;
-                float *f = film + 4 * ((size_t) y * W + x);
-                if (!WEIGHTS_ONLY) { atomicAdd(f + 0, v.x * w); atomicAdd(f + 1, v.y * w); atomicAdd(f + 2, v.z * w); }
-                atomicAdd(f + 3, w);
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    const int W = (int) sc.crop_w, H = (int) sc.crop_h;
+    const int n = (int) ceilf(sc.gauss_radius - .5f);          // taps on either side (2 for the default radius)
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < cfg.chunk_lanes; base += warp_stride) {
+        uint32_t i = base + lane_id;
+        bool valid = i < cfg.chunk_lanes;
+        uint32_t pixel = 0xffffffffu; float pfx = 0.f, pfy = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            pixel = __ldg(&pix_ids[cfg.chunk_pix0 + i / cfg.spp]);
+            sample_film_pos(sc, cfg, pixel, i % cfg.spp, pfx, pfy);
+            if (!WEIGHTS_ONLY) v = lane_result[i];
+        }
+        uint32_t pixel0 = __shfl_sync(0xffffffffu, pixel, 0);
+        bool uniform = __all_sync(0xffffffffu, pixel == pixel0) && n <= 2;
+        if (uniform) {
+            int py = (int) (pixel0 / sc.crop_w), px = (int) (pixel0 - (uint32_t) py * sc.crop_w);
+            // per-lane separable weights on the common window px-2..px+2; zero outside the
+            // sample's own footprint [ceil(p - r), floor(p + r)] (imageblock.cpp:283-287)
+            float wx[5], wy[5];
+            int x0 = (int) ceilf(pfx - sc.gauss_radius), x1 = (int) floorf(pfx + sc.gauss_radius);
+            int y0 = (int) ceilf(pfy - sc.gauss_radius), y1 = (int) floorf(pfy + sc.gauss_radius);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int x = px - 2 + k, y = py - 2 + k;
+                wx[k] = (x >= x0 && x <= x1) ? rfilter_eval(sc, (float) x - pfx) : 0.f;
+                wy[k] = (y >= y0 && y <= y1) ? rfilter_eval(sc, (float) y - pfy) : 0.f;
+            }
+            float mine0 = 0.f, mine1 = 0.f, mine2 = 0.f, mine3 = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    float w = wx[kx] * wy[ky];
+                    float a0 = v.x * w, a1 = v.y * w, a2 = v.z * w, a3 = w;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        if (!WEIGHTS_ONLY) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+                        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+                    }
+                    if ((int) lane_id == ky * 5 + kx) { mine0 = a0; mine1 = a1; mine2 = a2; mine3 = a3; }
+                }
+            if (lane_id < 25) {
+                int x = px - 2 + (int) (lane_id % 5), y = py - 2 + (int) (lane_id / 5);
+                if (x >= 0 && y >= 0 && x < W && y < H && mine3 != 0.f) {
+                    float *f = film + 4 * ((size_t) y * W + x);
+                    if (!WEIGHTS_ONLY) { atomicAdd(f + 0, mine0); atomicAdd(f + 1, mine1); atomicAdd(f + 2, mine2); }
+                    atomicAdd(f + 3, mine3);
+                }
+            }
+        } else if (valid) {
+            int x0 = max((int) ceilf(pfx - sc.gauss_radius), 0), y0 = max((int) ceilf(pfy - sc.gauss_radius), 0);
+            int x1 = min((int) floorf(pfx + sc.gauss_radius), W - 1), y1 = min((int) floorf(pfy + sc.gauss_radius), H - 1);
+            for (int y = y0; y <= y1; ++y) {
+                float wy = rfilter_eval(sc, (float) y - pfy);
+                for (int x = x0; x <= x1; ++x) {
+                    float w = rfilter_eval(sc, (float) x - pfx) * wy;
+                    float *f = film + 4 * ((size_t) y * W + x);
+                    if (!WEIGHTS_ONLY) { atomicAdd(f + 0, v.x * w); atomicAdd(f + 1, v.y * w); atomicAdd(f + 2, v.z * w); }
+                    atomicAdd(f + 3, w);
+                }
             }
         }
     }
@@ -603,6 +692,8 @@ __global__ void __launch_bounds__(BLOCK) k_ray_query(DevScene sc, uint32_t n, co
     __shared__ uint64_t bar;
     float4 *s_nodes = (float4 *) smem_raw;
     float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
     TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -640,15 +731,15 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
-    if (first) k_trace<true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-    else k_trace<false><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    if (first) k_trace<true><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else k_trace<false><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
 }
 
 template <int TYPE>
 static void launch_shade_t(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
                            PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st) {
-    if (cfg.adjoint) k_shade<TYPE, true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-    else k_shade<TYPE, false><<<L.grid, BLOCK, 0, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    if (cfg.adjoint) k_shade<TYPE, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else k_shade<TYPE, false><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
 }
 
 void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
@@ -701,6 +792,10 @@ void set_trace_smem_attr(size_t bytes) {
     cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

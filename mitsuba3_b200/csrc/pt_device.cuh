@@ -135,6 +135,10 @@ struct DevScene {
     const DevShape *shapes; const DevBsdf *bsdfs; const DevEmitter *emitters; const DevTexture *textures;
     uint32_t n_shapes, n_bsdfs, n_emitters, n_textures;
     float *grad;               // flat gradient buffer of all differentiable textures
+    // The four tables above live in ONE contiguous blob (shapes | bsdfs | emitters | textures);
+    // kernels stage it into shared memory when it is small (kernels.cu: stage_tables).
+    const unsigned char *tables; uint32_t tables_bytes, off_bsdfs, off_emitters, off_textures;
+    uint32_t geom_bytes, n_vertices;   // bytes of prim_verts + vertices (staged together when small)
     // sensor + film
     float s2c[16]; float cam_to_world[16];
     float near_clip, far_clip;
@@ -176,11 +180,11 @@ PT_DEV bool moeller_trumbore(float3 o, float3 d, float maxt, float3 p0, float3 e
 // interaction.h:804-830 + mesh.cpp:2254-2437 + interaction.h:558-603
 PT_DEV SurfaceInteraction compute_si(const DevScene &sc, float t, float b1, float b2, uint32_t prim, float3 ray_d) {
     SurfaceInteraction si;
-    uint4 pv = __ldg(&sc.prim_verts[prim]);
+    uint4 pv = sc.prim_verts[prim];
     const DevShape &sh = sc.shapes[pv.w];
-    float4 a0 = __ldg(&sc.vertices[2 * pv.x]), a1 = __ldg(&sc.vertices[2 * pv.x + 1]);
-    float4 c0 = __ldg(&sc.vertices[2 * pv.y]), c1 = __ldg(&sc.vertices[2 * pv.y + 1]);
-    float4 g0 = __ldg(&sc.vertices[2 * pv.z]), g1 = __ldg(&sc.vertices[2 * pv.z + 1]);
+    float4 a0 = sc.vertices[2 * pv.x], a1 = sc.vertices[2 * pv.x + 1];
+    float4 c0 = sc.vertices[2 * pv.y], c1 = sc.vertices[2 * pv.y + 1];
+    float4 g0 = sc.vertices[2 * pv.z], g1 = sc.vertices[2 * pv.z + 1];
     float3 p0 = V(a0.x, a0.y, a0.z), p1 = V(c0.x, c0.y, c0.z), p2 = V(g0.x, g0.y, g0.z);
     float b0 = 1.f - b1 - b2;
     float3 e1 = p1 - p0, e2 = p2 - p0;
@@ -467,10 +471,10 @@ PT_DEV void shape_sample_position(const DevScene &sc, const DevShape &sh, float 
     uint32_t face = lo;
     float cdf0 = face ? __ldg(&sh.area_cdf[face - 1]) : 0.f, cdf1 = __ldg(&sh.area_cdf[face]);
     float sy_re = fdiv(value - cdf0, cdf1 - cdf0);
-    uint4 pv = __ldg(&sc.prim_verts[sh.first_prim + face]);
-    float4 a0 = __ldg(&sc.vertices[2 * pv.x]), a1 = __ldg(&sc.vertices[2 * pv.x + 1]);
-    float4 c0 = __ldg(&sc.vertices[2 * pv.y]), c1 = __ldg(&sc.vertices[2 * pv.y + 1]);
-    float4 g0 = __ldg(&sc.vertices[2 * pv.z]), g1 = __ldg(&sc.vertices[2 * pv.z + 1]);
+    uint4 pv = sc.prim_verts[sh.first_prim + face];
+    float4 a0 = sc.vertices[2 * pv.x], a1 = sc.vertices[2 * pv.x + 1];
+    float4 c0 = sc.vertices[2 * pv.y], c1 = sc.vertices[2 * pv.y + 1];
+    float4 g0 = sc.vertices[2 * pv.z], g1 = sc.vertices[2 * pv.z + 1];
     float3 p0 = V(a0.x, a0.y, a0.z), e0 = V(c0.x, c0.y, c0.z) - p0, e1 = V(g0.x, g0.y, g0.z) - p0;
     float2 b = square_to_uniform_triangle(sx, sy_re);
     p = vfmas(e0, b.x, vfmas(e1, b.y, p0));
