@@ -323,20 +323,21 @@ class _Parser:
         b.tex[abi.SLOT_P_CLEARCOAT] = self.texture(f"{bid}.clearcoat", d.get("clearcoat"), 1, 0.0)
         b.tex[abi.SLOT_P_CLEARCOAT_GLOSS] = self.texture(f"{bid}.clearcoat_gloss", d.get("clearcoat_gloss"), 1, 0.0)
         if has("eta") and has("specular"):
-            raise ValueError("Specified an invalid index of refraction property \"eta\" and \"specular\"")
+            raise ValueError("Specified an invalid index of refraction property \"eta\", either use \"eta\" or \"specular\" !")
+        has_st = bool(flags & abi.P_HAS_SPEC_TRANS)
         if has("eta"):
             flags |= abi.P_ETA_SPECULAR
-            eta = float(d["eta"])
-            # principled.cpp: eta == 1 is not plausible -> 1.001
-            if eta == 1.0:
-                eta = 1.001
-            b.eta = eta
-            b.tex[abi.SLOT_P_SPECULAR] = -1
+            eta = f32(d["eta"])
+            if has_st and eta == f32(1):            # principled.cpp:221: eta = 1 is not plausible for transmission
+                eta = f32(1.001)
+            b.eta = float(eta)
         else:
-            spec = float(d.get("specular", 0.5))
-            # eta = 2 / (1 - sqrt(0.08 * specular)) - 1
-            b.eta = float(f32(2.0) * f32(1.0 / (1.0 - np.sqrt(0.08 * spec))) - f32(1.0))
-            b.tex[abi.SLOT_P_SPECULAR] = self.texture(f"{bid}.specular", spec, 1)
+            spec = f32(d.get("specular", 0.5))
+            if has_st and spec == f32(0):           # principled.cpp:226
+                spec = f32(1e-3)
+            # principled.cpp:227: eta = 2 * rcp(1 - sqrt(0.08 * specular)) - 1 (fp32)
+            b.eta = float(f32(2) * (f32(1) / (f32(1) - np.sqrt(f32(0.08) * spec, dtype=f32))) - f32(1))
+        b.tex[abi.SLOT_P_SPECULAR] = -1
         b.spec_srate = float(d.get("main_specular_sampling_rate", 1.0))
         b.clearcoat_srate = float(d.get("clearcoat_sampling_rate", 1.0))
         b.diff_refl_srate = float(d.get("diffuse_reflectance_sampling_rate", 1.0))

@@ -39,12 +39,15 @@ def cbox(res=32, rfilter="box", spp=16, max_depth=8, **film):
 def materials_cbox(res=32, rfilter="box", spp=16, max_depth=8):
     """Cornell box with conductor / dielectric / principled / twosided materials
     (same scene as gen_golden.py:materials)."""
+    import mitsuba3_b200 as mb
     d = cbox(res, rfilter, spp, max_depth)
     d["mirror"] = {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}
     d["glass"] = {"type": "dielectric", "int_ior": "bk7", "ext_ior": "air"}
     d["pr"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]}, "roughness": 0.3,
                "metallic": 0.2, "specular": 0.5, "clearcoat": 0.5, "clearcoat_gloss": 0.6, "sheen": 0.3}
     d["small-box"]["bsdf"] = {"type": "ref", "id": "glass"}
+    # lifted off the floor (coincident faces = backend-specific tie in the reference, see gen_golden.py)
+    d["small-box"]["to_world"] = mb.Transform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
     d["large-box"]["bsdf"] = {"type": "ref", "id": "mirror"}
     d["back"]["bsdf"] = {"type": "ref", "id": "pr"}
     d["floor"]["bsdf"] = {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}}}

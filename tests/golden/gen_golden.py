@@ -253,6 +253,10 @@ def materials(d):
     d["pr"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]}, "roughness": 0.3,
                "metallic": 0.2, "specular": 0.5, "clearcoat": 0.5, "clearcoat_gloss": 0.6, "sheen": 0.3}
     d["small-box"]["bsdf"] = {"type": "ref", "id": "glass"}
+    # lifted off the floor: the stock small box has its bottom face exactly IN the floor plane, and which
+    # of two coincident surfaces a ray "hits first" is backend-specific in the reference itself
+    # (kd-tree / Embree / OptiX) -- it only matters once the box is transparent
+    d["small-box"]["to_world"] = mi.ScalarTransform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
     d["large-box"]["bsdf"] = {"type": "ref", "id": "mirror"}
     d["back"]["bsdf"] = {"type": "ref", "id": "pr"}
     d["floor"]["bsdf"] = {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}}}

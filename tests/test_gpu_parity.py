@@ -82,6 +82,14 @@ BSDF_SPECS = {
                                 "specular_reflectance": {"type": "rgb", "value": [0.9, 0.95, 1.0]},
                                 "specular_transmittance": {"type": "rgb", "value": [0.8, 0.9, 0.7]}},
     "twosided_diffuse": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.3, 0.6, 0.1]}}},
+    "principled_default": {"type": "principled"},
+    "principled_rough_metal": {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.6, 0.2]}, "metallic": 0.8, "roughness": 0.35, "specular": 0.5},
+    "principled_full": {"type": "principled", "base_color": {"type": "rgb", "value": [0.7, 0.1, 0.1]}, "roughness": 0.15, "anisotropic": 0.5,
+                        "metallic": 0.1, "spec_trans": 0.8, "eta": 1.33, "spec_tint": 0.4, "sheen": 0.9, "sheen_tint": 0.2, "flatness": 0.23,
+                        "clearcoat": 0.9, "clearcoat_gloss": 0.5},
+    "principled_matpreview": {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]}, "roughness": 0.3, "metallic": 0.0, "specular": 0.5},
+    "principled_coat_sheen": {"type": "principled", "base_color": {"type": "rgb", "value": [0.2, 0.4, 0.9]}, "roughness": 0.6, "clearcoat": 1.0,
+                              "clearcoat_gloss": 0.8, "sheen": 0.5, "sheen_tint": 0.7, "spec_tint": 0.3, "flatness": 0.5},
 }
 
 
@@ -97,8 +105,10 @@ def test_bsdf_tables(name, oracle_mod):
     cols = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12]
     assert np.array_equal(out[:, 9].view(np.uint32), ref[:, 9].view(np.uint32))      # sampled_type
     assert np.array_equal(out[:, 13], ref[:, 13])                                    # sampled_component
-    assert np.allclose(out[:, cols], ref[:, cols], rtol=2e-5, atol=1e-6)
-    assert np.allclose(out[:, cols], orc[:, cols], rtol=2e-5, atol=1e-6)
+    # principled: sharp GGX lobes (alpha ~ 0.02) amplify 1-ulp differences of the half vector -> 2e-4
+    rtol = 2e-4 if name.startswith("principled") else 2e-5
+    assert np.allclose(out[:, cols], ref[:, cols], rtol=rtol, atol=2e-6)
+    assert np.allclose(out[:, cols], orc[:, cols], rtol=rtol, atol=2e-6)
 
 
 RENDER_CASES = [
