@@ -31,6 +31,8 @@ WORKLOADS = {
     # name: (width, height, spp per GPU, max_depth, rfilter)
     "cornell_box_512x512_256spp_8bounce": (512, 512, 256, 8, "gaussian"),
     "cornell_box_256x256_64spp_8bounce": (256, 256, 64, 8, "gaussian"),
+    # synthetic stand-in for the 200k-triangle config (BASELINE.json configs[4], asset not in the reference tree)
+    "heightfield205k_1024x1024_64spp_8bounce": (1024, 1024, 64, 8, "gaussian"),
 }
 DEFAULT_WORKLOAD = "cornell_box_512x512_256spp_8bounce"
 METRIC = "Msamples/sec (fwd path, Cornell box)"
@@ -39,7 +41,7 @@ METRIC = "Msamples/sec (fwd path, Cornell box)"
 def build_scene(workload):
     import mitsuba3_b200 as mb
     w, h, spp, md, rf = WORKLOADS[workload]
-    d = mb.cornell_box()
+    d = mb.cornell_box_heightfield(320) if workload.startswith("heightfield") else mb.cornell_box()
     d["sensor"]["film"].update(width=w, height=h, rfilter={"type": rf})
     d["sensor"]["sampler"]["sample_count"] = spp
     d["integrator"] = {"type": "path", "max_depth": md}
@@ -87,45 +89,71 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(scene, spp_sample, threads=None):
-    """Times the CPU oracle (port of the reference algorithm, OpenMP over pixels) on a
-    bounded sample of the same workload: same frame, `spp_sample` spp."""
+def cpu_baseline_port(scene, spp_sample):
+    """CPU oracle (port of the reference algorithm, OpenMP over pixels) on a bounded sample."""
     from oracle import oracle
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
     o = oracle.OracleScene(scene)
     H, W, _ = scene.film_shape
     o.render(spp=1, seed=0, mode=0)                      # warm-up (page-in, thread pool)
     t0 = time.perf_counter()
-    _, st = o.render(spp=spp_sample, seed=0, mode=0, return_stats=True)
+    o.render(spp=spp_sample, seed=0, mode=0)
     dt = time.perf_counter() - t0
-    return W * H * spp_sample / dt / 1e6, dt, st
+    return W * H * spp_sample / dt / 1e6, dt
+
+
+def cpu_baseline_reference(workload, spp_sample, reps=1):
+    """The UNMODIFIED reference (mitsuba scalar_rgb, all host threads) when a snapshot of its
+    runtime travels with the repo (oracle/ref_snapshot.sh); None otherwise."""
+    from mitsuba3_b200._ref_env import reference_env
+    env = reference_env(ROOT)
+    if env is None or workload.startswith("heightfield"):
+        return None
+    w, h, spp, md, rf = WORKLOADS[workload]
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), str(w), str(h), str(spp_sample), str(md), rf, str(reps)],
+                           env=env, capture_output=True, text=True, timeout=1500)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def cpu_baseline(scene, workload, spp1):
+    """Reported CPU baseline on a bounded sample (same frame, fewer spp): the reference itself when
+    available, else the oracle port."""
+    cores = os.cpu_count() or 1
+    spp_sample = max(1, min(spp1, int(round(32 * cores / 8))))
+    w, h, _, md, _ = WORKLOADS[workload]
+    ref = cpu_baseline_reference(workload, spp_sample)
+    if ref is not None:
+        return {"value": ref["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "kind": "reference", "seconds": ref["seconds"],
+                "sample": f"mitsuba {ref['version']} scalar_rgb, {ref['accel']}, same frame {w}x{h}, max_depth {md}, {spp_sample} of {spp1} spp ({ref['seconds']:.1f} s)"}
+    spp_sample = max(1, spp_sample // 2)
+    v, dt = cpu_baseline_port(scene, spp_sample)
+    return {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"CPU oracle (OpenMP), same frame {w}x{h}, max_depth {md}, {spp_sample} of {spp1} spp ({dt:.1f} s)"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own algorithm on the host cores (the CPU oracle
-    restates it and is pinned to the unmodified reference's scalar_rgb renders; the
-    reference itself needs its cmake build tree and cannot travel)."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores --
+    mitsuba scalar_rgb from the runtime snapshot when it travelled with the repo, else the CPU
+    oracle that restates it (pinned per pixel to scalar_rgb renders)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     scene, (w, h, spp, md, rf) = build_scene(args.workload)
-    cores = os.cpu_count() or 1
-    spp_sample = max(1, min(spp, int(round(16 * cores / 8))))
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(scene, 1)
-    vals, times = [], []
-    for _ in range(args.steps):
-        v, dt, st = cpu_baseline(scene, spp_sample)
-        vals.append(v); times.append(dt)
+    vals = []
+    base = None
+    for _ in range(max(1, args.steps)):
+        base = cpu_baseline(scene, args.workload, spp)
+        vals.append(base["value"])
     v = float(np.mean(vals))
-    sample = f"same frame {w}x{h}, max_depth {md}, {spp_sample} of {spp} spp per step"
+    base["value"] = v
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "parallelism": "cpu-openmp", "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "parallelism": "host cores", "sample": base["sample"]},
+        "cpu_baseline": base,
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
@@ -279,11 +307,7 @@ def main():
         if prb:
             out["prb"] = prb
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            spp_sample = max(1, min(spp1, int(round(16 * cores / 8))))
-            v, dt, _ = cpu_baseline(scene, spp_sample)
-            out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                   "sample": f"same frame {w}x{h}, max_depth {md}, {spp_sample} of {spp1} spp ({dt:.1f} s)"}
+            out["cpu_baseline"] = cpu_baseline(scene, args.workload, spp1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -1,0 +1,15 @@
+"""Locate an (optional) snapshot of the unmodified reference's runtime for the live-plugin
+tests and the `kind: "reference"` CPU baseline (oracle/ref_snapshot.sh). Returns the
+environment a SUBPROCESS needs; this package never imports mitsuba itself."""
+import os
+
+
+def reference_env(root=None):
+    root = root or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for base in (os.environ.get("B200PT_MITSUBA_BUILD", ""), os.path.join(root, "oracle", "_ref", "mitsuba_build"), "/tmp/mi_probe/build"):
+        if base and os.path.exists(os.path.join(base, "libmitsuba.so")):
+            env = dict(os.environ)
+            env["PYTHONPATH"] = os.pathsep.join([os.path.join(base, "python"), root, env.get("PYTHONPATH", "")])
+            env["LD_LIBRARY_PATH"] = os.pathsep.join([base, os.path.join(base, "python", "mitsuba"), os.path.join(base, "python", "drjit"), env.get("LD_LIBRARY_PATH", "")])
+            return env
+    return None

@@ -1,0 +1,255 @@
+"""Registration of the B200 path tracer as integrator plugins of a live Mitsuba 3.
+
+    import mitsuba as mi; mi.set_variant("llvm_ad_rgb")        # or scalar_rgb / cuda_ad_rgb
+    import mitsuba3_b200.mitsuba_plugin as b200; b200.register(mi)
+    scene = mi.load_dict({... "integrator": {"type": "b200_path", "max_depth": 8} ...})
+    img = mi.render(scene, spp=256)                              # -> libb200pt.so
+
+The plugin classes derive from ``mi.SamplingIntegrator`` (trampoline
+src/render/python/integrator_v.cpp:59-132) and are registered with
+``mi.register_integrator`` (src/render/python/scene_v.cpp:166-171), i.e. the
+reference's own Python plugin route. ``render`` extracts the
+scene from the live objects through public bindings only (``scene.shapes()``,
+``Mesh.packed_vertices()/faces()``, ``mi.traverse``), hands POD buffers to the C
+ABI and wraps the result as ``mi.TensorXf``. ``render_backward`` accumulates
+into ``dr.grad`` of the attached parameters with ``dr.accum_grad``.
+
+The host Mitsuba is never imported by this package on its own: ``register`` is
+given the module. Extraction is variant-agnostic (host arrays in / out).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+from .scene import (BsdfData, EmitterData, Scene, SensorData, ShapeData, TextureData, f32)
+from .transform import _cross, _normalize, _sqnorm, Transform4f
+
+_BSDF_CLASS = {"SmoothDiffuse": abi.BSDF_DIFFUSE, "SmoothConductor": abi.BSDF_CONDUCTOR,
+               "SmoothDielectric": abi.BSDF_DIELECTRIC, "Principled": abi.BSDF_PRINCIPLED}
+
+
+def _np(x, dtype=np.float32):
+    return np.array(x, dtype=dtype)
+
+
+class _Extractor:
+    def __init__(self, mi, scene, sensor):
+        self.mi, self.scene_mi = mi, scene
+        self.out = Scene()
+        self.bsdf_index = {}
+        self.sensor_mi = scene.sensors()[sensor] if isinstance(sensor, int) else sensor
+
+    # ---- textures from a traversed parameter set ---------------------------------
+    def _texture(self, params, prefix, key, name, channels, default=None, differentiable=True):
+        """`prefix.key.value` (constant) or `prefix.key.data` (bitmap tensor)."""
+        k_val, k_data = f"{prefix}{key}.value", f"{prefix}{key}.data"
+        t = TextureData(name=name, channels=channels, differentiable=differentiable)
+        if k_val in params:
+            v = _np(params[k_val]).reshape(-1)
+            t.value = np.full(3, v[0], f32) if v.size == 1 else v[:3].astype(f32)
+            if v.size == 1:
+                t.channels = 1 if channels == 1 else 3
+            t.name = name + ".value"
+        elif k_data in params:
+            d = _np(params[k_data])
+            if d.ndim == 2:
+                d = d[:, :, None]
+            t.kind, t.data, t.channels = abi.TEX_BITMAP, np.ascontiguousarray(d), d.shape[2]
+            t.name = name + ".data"
+            if f"{prefix}{key}.to_uv" in params:
+                t.to_uv = _np(params[f"{prefix}{key}.to_uv"].matrix).reshape(3, 3)
+        elif default is not None:
+            t.value = np.full(3, default, f32); t.name = name + ".value"
+        else:
+            return -1
+        self.out.textures.append(t)
+        return len(self.out.textures) - 1
+
+    # ---- BSDFs ----------------------------------------------------------------------
+    def bsdf(self, b, name):
+        key = b.id() if b.id() and not b.id().startswith("_unnamed") else name
+        if key in self.bsdf_index:
+            return self.bsdf_index[key]
+        mi = self.mi
+        params = mi.traverse(b)
+        cls = b.class_name()
+        prefix, twosided = "", False
+        if cls in ("TwoSidedBRDF", "TwoSided"):
+            twosided, prefix = True, "brdf_0."
+            inner = [k for k in params.keys() if k.startswith("brdf_0.")]
+            cls = self._guess_class(inner)
+        if cls not in _BSDF_CLASS:
+            raise NotImplementedError(f"BSDF class {cls!r} is outside the hot-path scope (SURVEY.md 8(a))")
+        d = BsdfData(id=key, type=_BSDF_CLASS[cls], twosided=twosided)
+        T = lambda k, ch, default=None: self._texture(params, prefix, k, f"{key}.{prefix}{k}", ch, default)
+        if d.type == abi.BSDF_DIFFUSE:
+            d.tex[abi.SLOT_REFLECTANCE] = T("reflectance", 3, 0.5)
+        elif d.type == abi.BSDF_CONDUCTOR:
+            d.tex[abi.SLOT_ETA], d.tex[abi.SLOT_K] = T("eta", 3, 0.0), T("k", 3, 1.0)
+            d.tex[abi.SLOT_SPEC_REFL] = T("specular_reflectance", 3, 1.0)
+        elif d.type == abi.BSDF_DIELECTRIC:
+            d.eta = float(params[f"{prefix}eta"])
+            d.tex[abi.SLOT_D_SPEC_REFL] = T("specular_reflectance", 3)
+            d.tex[abi.SLOT_D_SPEC_TRANS] = T("specular_transmittance", 3)
+        else:
+            flags = 0
+            slots = [("base_color", abi.SLOT_P_BASE_COLOR, 3, 0), ("roughness", abi.SLOT_P_ROUGHNESS, 1, 0),
+                     ("anisotropic", abi.SLOT_P_ANISOTROPIC, 1, abi.P_HAS_ANISOTROPIC), ("metallic", abi.SLOT_P_METALLIC, 1, abi.P_HAS_METALLIC),
+                     ("spec_trans", abi.SLOT_P_SPEC_TRANS, 1, abi.P_HAS_SPEC_TRANS), ("spec_tint", abi.SLOT_P_SPEC_TINT, 1, abi.P_HAS_SPEC_TINT),
+                     ("sheen", abi.SLOT_P_SHEEN, 1, abi.P_HAS_SHEEN), ("sheen_tint", abi.SLOT_P_SHEEN_TINT, 1, abi.P_HAS_SHEEN_TINT),
+                     ("flatness", abi.SLOT_P_FLATNESS, 1, abi.P_HAS_FLATNESS), ("clearcoat", abi.SLOT_P_CLEARCOAT, 1, abi.P_HAS_CLEARCOAT),
+                     ("clearcoat_gloss", abi.SLOT_P_CLEARCOAT_GLOSS, 1, 0)]
+            for k, slot, ch, flag in slots:
+                d.tex[slot] = T(k, ch, 0.5 if k in ("base_color", "roughness") else 0.0)
+                t = self.out.textures[d.tex[slot]]
+                if flag and (t.kind == abi.TEX_BITMAP or float(t.value[0]) != 0.0):
+                    flags |= flag           # m_has_* (principledhelpers.h get_flag): a zero constant == lobe off
+            if f"{prefix}eta" in params:
+                d.eta = float(params[f"{prefix}eta"]); flags |= abi.P_ETA_SPECULAR
+            else:
+                spec = f32(float(params[f"{prefix}specular"]))
+                d.eta = float(f32(2) * (f32(1) / (f32(1) - np.sqrt(f32(0.08) * spec, dtype=f32))) - f32(1))
+            d.spec_srate = float(params[f"{prefix}main_specular_sampling_rate"])
+            d.clearcoat_srate = float(params[f"{prefix}clearcoat_sampling_rate"])
+            d.diff_refl_srate = float(params[f"{prefix}diffuse_reflectance_sampling_rate"])
+            d.flags = flags
+        self.out.bsdfs.append(d)
+        self.bsdf_index[key] = len(self.out.bsdfs) - 1
+        return self.bsdf_index[key]
+
+    @staticmethod
+    def _guess_class(keys):
+        ks = " ".join(keys)
+        if "base_color" in ks: return "Principled"
+        if "specular_transmittance" in ks or ".eta" in ks and ".k" not in ks and "reflectance.value" not in ks: return "SmoothDielectric"
+        if ".k." in ks: return "SmoothConductor"
+        return "SmoothDiffuse"
+
+    # ---- shapes / emitters ---------------------------------------------------------------
+    def shapes(self):
+        mi = self.mi
+        for i, s in enumerate(self.scene_mi.shapes()):
+            if not s.is_mesh():
+                raise NotImplementedError("only triangle meshes are on the hot path (SURVEY.md 2, row 9b)")
+            if getattr(s, "packs_tangent", lambda: False)():
+                raise NotImplementedError("packed tangent frames (anisotropic / normal-mapped BSDFs) are outside the hot-path scope")
+            sid = s.id() or f"shape_{i}"
+            verts = _np(s.packed_vertices()).reshape(-1, 8)
+            faces3 = _np(s.faces(), np.uint32).reshape(-1, 3)
+            faces = np.concatenate([faces3, np.zeros((faces3.shape[0], 1), np.uint32)], axis=1)
+            layout = (abi.LAYOUT_NORMALS if s.has_normals() else 0) | (abi.LAYOUT_TEXCOORDS if s.has_texcoords() else 0)
+            sh = ShapeData(id=sid, vertices=verts, faces=faces, layout=layout, bsdf=self.bsdf(s.bsdf(), f"{sid}.bsdf"))
+            if s.is_emitter():
+                ep = mi.traverse(s.emitter())
+                rad = self._texture(ep, "", "radiance", f"{sid}.emitter.radiance", 3)
+                if rad < 0 or self.out.textures[rad].kind != abi.TEX_CONST:
+                    raise NotImplementedError("only uniform area lights are on the hot path")
+                self.out.emitters.append(EmitterData(shape=len(self.out.shapes), radiance_tex=rad,
+                                                     sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0))
+                sh.emitter = len(self.out.emitters) - 1
+                sp = mi.traverse(s)
+                if "to_world" in sp and verts.shape[0] == 4 and faces.shape[0] == 2:
+                    # Rectangle: sampled by its parameterisation (rectangle.cpp:159-172)
+                    tw = Transform4f(_np(sp["to_world"].matrix))
+                    sh.sampling, sh.to_world = abi.SAMPLING_RECTANGLE, tw.matrix.copy()
+                    sh.frame_n = _normalize(tw.normal([0, 0, 1])).astype(f32)
+                    area = np.sqrt(_sqnorm(_cross(tw.vector([2, 0, 0]), tw.vector([0, 2, 0]))), dtype=f32)
+                    sh.inv_area = float(f32(1) / area)
+                else:
+                    sh.sampling = abi.SAMPLING_MESH
+            self.out.shapes.append(sh)
+
+    # ---- sensor / film ---------------------------------------------------------------------
+    def sensor(self):
+        mi, se = self.mi, self.sensor_mi
+        film = se.film()
+        p = mi.traverse(se)
+        size, crop, off = [int(v) for v in film.size()], [int(v) for v in film.crop_size()], [int(v) for v in film.crop_offset()]
+        proj = mi.perspective_projection(film.size(), film.crop_size(), film.crop_offset(), p["x_fov"], p["near_clip"], p["far_clip"])
+        rf = film.rfilter()
+        if rf.is_box_filter():
+            rfilter, stddev = abi.RFILTER_BOX, 0.0
+        elif rf.class_name() == "GaussianFilter":
+            rfilter, stddev = abi.RFILTER_GAUSSIAN, float(rf.radius()) / 4.0
+        else:
+            raise NotImplementedError(f"rfilter {rf.class_name()} is outside the hot-path scope")
+        if film.sample_border():
+            raise NotImplementedError("sample_border is outside the hot-path scope")
+        self.out.sensor = SensorData(
+            sample_to_camera=_np(proj.inverse().matrix), to_world=_np(p["to_world"].matrix),
+            near_clip=float(p["near_clip"]), far_clip=float(p["far_clip"]), film_size=tuple(size), crop_size=tuple(crop),
+            crop_offset=tuple(off), rfilter=rfilter, rfilter_stddev=stddev, base_seed=0,
+            sample_count=int(se.sampler().sample_count()), x_fov=float(p["x_fov"]))
+
+    def run(self) -> Scene:
+        if self.scene_mi.environment() is not None:
+            raise NotImplementedError("environment emitters are a 'next' row (SURVEY.md 8(f))")
+        self.shapes()
+        self.sensor()
+        return self.out
+
+
+def extract_scene(mi, scene, sensor=0) -> Scene:
+    """Live ``mi.Scene`` -> host ``Scene`` (POD arrays) through public bindings only."""
+    return _Extractor(mi, scene, sensor).run()
+
+
+def register(mi):
+    """Register ``b200_path`` and ``b200_prb`` for the CURRENT variant of ``mi``."""
+    import drjit as dr
+    from .integrators import PathIntegrator, PRBIntegrator, update_params
+
+    class _Base(mi.SamplingIntegrator):
+        _impl_cls = PathIntegrator
+
+        def __init__(self, props):
+            super().__init__(props)
+            kw = {}
+            for k in ("max_depth", "rr_depth", "hide_emitters"):
+                if props.has_property(k):
+                    kw[k] = props[k]
+            self._impl = self._impl_cls(kw)
+            self._cache = {}
+
+        def _host_scene(self, scene, sensor):
+            key = (id(scene), sensor if isinstance(sensor, int) else id(sensor))
+            if key not in self._cache:
+                self._cache[key] = extract_scene(mi, scene, sensor)
+            return self._cache[key]
+
+        def _sync_params(self, host, scene):
+            """Push the current values of the differentiable parameters (optimiser steps)."""
+            params = mi.traverse(scene)
+            vals = {}
+            for name in host.parameters():
+                if name in params:
+                    vals[name] = np.array(params[name], np.float32)
+            update_params(host, vals)
+
+        def render(self, scene, sensor=0, seed=0, spp=0, develop=True, evaluate=True):
+            host = self._host_scene(scene, sensor)
+            self._sync_params(host, scene)
+            img = self._impl.render(host, seed=int(seed), spp=int(spp))
+            return mi.TensorXf(img)
+
+        def to_string(self):
+            return repr(self._impl).replace(type(self._impl).__name__, "B200" + type(self._impl).__name__)
+
+    class B200Path(_Base):
+        _impl_cls = PathIntegrator
+
+    class B200PRB(_Base):
+        _impl_cls = PRBIntegrator
+
+        def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
+            host = self._host_scene(scene, sensor)
+            self._sync_params(host, scene)
+            grads = self._impl.render_backward(host, np.array(grad_in, np.float32), seed=int(seed), spp=int(spp))
+            for name, g in grads.items():
+                if name in params and dr.grad_enabled(params[name]):
+                    dr.accum_grad(params[name], type(params[name])(g))     # opt.step() reads dr.grad (drjit/opt.py:451)
+
+    mi.register_integrator("b200_path", lambda props: B200Path(props))
+    mi.register_integrator("b200_prb", lambda props: B200PRB(props))
+    return B200Path, B200PRB

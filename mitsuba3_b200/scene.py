@@ -566,3 +566,37 @@ def cornell_box() -> dict:
         "small-box": {"type": "cube", "to_world": T().translate([0.335, -0.7, 0.38]).rotate([0, 1, 0], -17).scale(0.3), "bsdf": white},
         "large-box": {"type": "cube", "to_world": T().translate([-0.33, -0.4, -0.28]).rotate([0, 1, 0], 18.25).scale([0.3, 0.61, 0.3]), "bsdf": white},
     }
+
+
+# ---------------------------------------------------------------------------
+# synthetic stand-ins for the larger BASELINE.json configs (no external assets)
+# ---------------------------------------------------------------------------
+def heightfield_mesh(n: int, amplitude: float = 0.08, y0: float = -1.0, extent: float = 1.0, freq: float = 5.0):
+    """(n x n quads = 2 n^2 triangles) bumpy floor over [-extent, extent]^2 at height y0,
+    with analytic smooth normals and uv -- a triangle-count knob for BVH tests/benchmarks."""
+    g = np.linspace(-extent, extent, n + 1, dtype=np.float64)
+    x, z = np.meshgrid(g, g, indexing="xy")
+    h = amplitude * (np.sin(freq * x) * np.cos(freq * z) + 0.5 * np.sin(2.3 * freq * x + 1.0) * np.sin(1.7 * freq * z))
+    y = y0 + h
+    dhdx = amplitude * (freq * np.cos(freq * x) * np.cos(freq * z) + 0.5 * 2.3 * freq * np.cos(2.3 * freq * x + 1.0) * np.sin(1.7 * freq * z))
+    dhdz = amplitude * (-freq * np.sin(freq * x) * np.sin(freq * z) + 0.5 * 1.7 * freq * np.sin(2.3 * freq * x + 1.0) * np.cos(1.7 * freq * z))
+    nrm = np.stack([-dhdx, np.ones_like(h), -dhdz], axis=-1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    pos = np.stack([x, y, z], axis=-1).reshape(-1, 3).astype(f32)
+    uv = np.stack([(x + extent) / (2 * extent), (z + extent) / (2 * extent)], axis=-1).reshape(-1, 2).astype(f32)
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    # winding such that the geometric normal points up (+y)
+    faces = np.concatenate([np.stack([a, c, b], axis=1), np.stack([b, c, d], axis=1)], axis=0).astype(np.uint32)
+    return {"type": "mesh", "positions": pos, "normals": nrm.reshape(-1, 3).astype(f32), "texcoords": uv, "faces": faces}
+
+
+def cornell_box_heightfield(n: int = 64, **kw) -> dict:
+    """Cornell box whose floor is an (2 n^2)-triangle heightfield (n = 320 -> 204 800 triangles:
+    the documented synthetic stand-in for BASELINE.json's 200k-triangle config)."""
+    d = cornell_box()
+    hf = heightfield_mesh(n, **kw)
+    hf["bsdf"] = {"type": "ref", "id": "white"}
+    del d["floor"]
+    d["floor"] = hf
+    return d

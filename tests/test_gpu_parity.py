@@ -182,3 +182,30 @@ def test_size_independent_properties():
     assert np.all(a >= 0) and np.isfinite(a).all()
     st = sc._handle.stats()
     assert st["samples"] == 96 * 96 * 16 and 1.0 < st["bounces"] / st["samples"] <= 8.0
+
+
+# ---------------------------------------------------------------- larger meshes: BVH nodes / triangles beyond shared memory
+@pytest.mark.parametrize("n", [48, 100])
+def test_heightfield_scene_matches_oracle(n, oracle_mod):
+    """2 n^2 + 34 triangles: the BVH no longer fits the shared-memory staging area, so the
+    traversal reads nodes / triangles from global memory (L2) below the staged top levels."""
+    from mitsuba3_b200.integrators import device_scene
+    d = mb.cornell_box_heightfield(n)
+    d["sensor"]["film"].update(width=48, height=48, rfilter={"type": "box"})
+    sc = mb.load_dict(d)
+    assert sc.n_triangles == 2 * n * n + 34
+    ds, orc = device_scene(sc), oracle_mod.OracleScene(sc)
+    rng = np.random.default_rng(n)
+    m = 100_000
+    o = (rng.random((m, 3)) * 1.9 - 0.95).astype(np.float32); o[:, 1] = np.abs(o[:, 1]) * 0.9 - 0.6
+    dd = rng.normal(size=(m, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    rays = np.concatenate([o, dd.astype(np.float32), np.full((m, 1), 3.4e38, np.float32)], axis=1).astype(np.float32)
+    t, uv, prim, shape = ds.ray_intersect(rays)
+    to, uvo, primo, shapeo = orc.ray_intersect(rays)
+    assert np.array_equal(shape, shapeo) and np.array_equal(prim, primo)
+    hit = shape >= 0
+    assert np.array_equal(t[hit], to[hit]) and np.array_equal(uv[hit], uvo[hit])
+    assert np.array_equal(ds.ray_test(rays), orc.ray_test(rays))
+    img = mb.render(sc, spp=8, seed=1)
+    ref = orc.render(spp=8, seed=1, mode=0)
+    compare_images(img, ref)
