@@ -225,7 +225,10 @@ B200PT_API b200pt_status b200pt_render(b200pt_scene *scene, const b200pt_render_
                             float *out_host);
 /* Device entry points for multi-GPU: accumulate this shard's samples into a
  * raw film block (H*W*4: R,G,B,weight) owned by the caller, then develop
- * (hdrfilm.cpp:393) after the caller has all-reduced the block. */
+ * (hdrfilm.cpp:393) after the caller has all-reduced the block. All work is
+ * enqueued on `cuda_stream` (a cudaStream_t; NULL = the CUDA default stream) so
+ * that it orders with the caller's collectives; the call returns after the
+ * stream has drained (statistics are read back). */
 B200PT_API b200pt_status b200pt_render_accumulate(b200pt_scene *scene,
                                        const b200pt_render_params *p,
                                        float *film_device /* H*W*4, zeroed by caller */,

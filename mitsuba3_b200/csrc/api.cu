@@ -474,7 +474,7 @@ b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_para
     b200pt_status vs = validate_params(s, p); if (vs) return vs;
     if (!film_device) return fail(B200PT_ERR_INVALID, "null film");
     CU_TRY(cudaSetDevice(s->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    cudaStream_t st = (cudaStream_t) cuda_stream;   // NULL = the CUDA default stream, as everywhere in CUDA
     b200pt_status e = ensure_pix_ids(s, p); if (e) return e;
     begin_stats(s, st);
     if (p->max_depth == 0 || s->n_pix_ids == 0) {
@@ -498,7 +498,7 @@ b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_para
 b200pt_status b200pt_develop(b200pt_scene *s, const float *film_device, float *out_device, void *cuda_stream) {
     if (!s || !film_device || !out_device) return fail(B200PT_ERR_INVALID, "null argument");
     CU_TRY(cudaSetDevice(s->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    cudaStream_t st = (cudaStream_t) cuda_stream;   // NULL = the CUDA default stream, as everywhere in CUDA
     launch_develop(s->dev, film_device, out_device, st);
     CU_TRY(cudaGetLastError());
     return B200PT_OK;
@@ -521,7 +521,7 @@ b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render
     if (!grad_in_device) return fail(B200PT_ERR_INVALID, "null grad_in");
     b200pt_render_params p = *p_; p.prb = 1;
     CU_TRY(cudaSetDevice(s->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : s->stream;
+    cudaStream_t st = (cudaStream_t) cuda_stream;   // NULL = the CUDA default stream, as everywhere in CUDA
     begin_stats(s, st);
     if (p.max_depth == 0) return end_stats(s, st, 0);
     RenderCfg cfg = make_cfg(s, &p);

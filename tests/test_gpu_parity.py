@@ -209,3 +209,15 @@ def test_heightfield_scene_matches_oracle(n, oracle_mod):
     img = mb.render(sc, spp=8, seed=1)
     ref = orc.render(spp=8, seed=1, mode=0)
     compare_images(img, ref)
+
+
+def test_two_rank_nccl_film_and_gradient_reduce(built):
+    """Pixel-tile sharding over 2 GPUs + NCCL all-reduce == single-GPU render (skipped on 1-GPU boxes;
+    the same plumbing runs under gloo in tests/test_host.py)."""
+    import os, subprocess, sys, torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29553", os.path.join(ROOT, "tests", "_nccl_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "NCCL_OK 2" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
