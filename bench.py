@@ -286,6 +286,14 @@ def main():
         trace_bytes = closest * 48.0 + shadow * 64.0
         trace_avg_ms = trace_ms / max(1, trace_launches)
         trace_gbs = trace_bytes / max(trace_ms * 1e-3, 1e-12) / 1e9 if trace_ms > 0 else None
+        # DRAM traffic of the dominant kernel per launch: dram__bytes_{read,write}.sum per lane from the committed
+        # `ncu --set full` capture (profiles/r01_trace_traffic.json) x the lanes one launch of this run processed
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_trace_traffic.json")))
+            traffic = tj["dram_bytes_per_lane"] * (trace_rays / 2.0) / max(1, trace_launches)   # ~2 rays (shadow + closest) per lane
+        except Exception:
+            pass
         step_bytes = (144.0 + 304.0 * b_bar) * (samples_per_step // n_gpus)
         step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
         out = {
@@ -299,7 +307,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "wall_ms_per_step": wall / args.steps * 1e3,
             "roofline": {"kernel": "k_trace (BVH traversal: NEE shadow ray + closest hit)", "bound": "hbm",
                          "achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (trace_gbs / hbm_peak) if trace_gbs else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (trace_gbs / hbm_peak) if trace_gbs else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": trace_bytes / max(1, trace_launches), "peak_source": peak_src,
                          "avg_launch_ms": trace_avg_ms, "launches": int(trace_launches),
                          "share_of_step": trace_ms / max(dev_ms, 1e-9),
                          "step": {"bytes_per_sample": 144.0 + 304.0 * b_bar, "achieved": step_gbs, "frac": step_gbs / hbm_peak}},

@@ -104,10 +104,16 @@ struct TraceCtx {
     uint32_t n_smem_nodes, n_smem_tris;
 };
 
+// SMEM_ALL: the whole BVH and all triangles are staged (small scenes) -> plain LDS, no
+// per-access shared/global selection (it costs ~12 address instructions per node visit).
+template <bool SMEM_ALL>
 PT_DEV float4 ld_node(const TraceCtx &c, uint32_t node, int k) {
+    if (SMEM_ALL) return c.s_nodes[4 * node + k];
     return node < c.n_smem_nodes ? c.s_nodes[4 * node + k] : __ldg(&c.g_nodes[4 * (size_t) node + k]);
 }
+template <bool SMEM_ALL>
 PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
+    if (SMEM_ALL) return c.s_tris[3 * tri + k];
     return tri < c.n_smem_tris ? c.s_tris[3 * tri + k] : __ldg(&c.g_tris[3 * (size_t) tri + k]);
 }
 
@@ -131,7 +137,7 @@ PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float
 // tests) converged instead of interleaving them per lane.
 constexpr int32_t TRAV_SENTINEL = 0x76543210;
 
-template <bool ANY>
+template <bool ANY, bool SMEM_ALL>
 PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit) {
     hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
     float3 inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
@@ -141,11 +147,13 @@ PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit
     while (node != TRAV_SENTINEL) {
         bool searching = true;
         while (node >= 0 && node != TRAV_SENTINEL) {
-            float4 n0 = ld_node(c, node, 0), n1 = ld_node(c, node, 1), n2 = ld_node(c, node, 2), n3 = ld_node(c, node, 3);
+            float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
             int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
             float tl, tr;
-            bool hl = cl != 0x7fffffff && box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl);
-            bool hr = cr != 0x7fffffff && box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr);
+            // both slab tests are evaluated unconditionally (no short-circuit branches); the
+            // "no child" marker only exists in the synthetic root of a <= 2-triangle scene
+            bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
+            bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
             if (!hl && !hr) node = stack[sp--];
             else {
                 node = hl ? cl : cr;
@@ -161,7 +169,7 @@ PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit
         while (leaf < 0) {
             uint32_t enc = (uint32_t) ~leaf, first = enc >> 3, count = (enc & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
-                float4 a = ld_tri(c, i, 0), b = ld_tri(c, i, 1), e = ld_tri(c, i, 2);
+                float4 a = ld_tri<SMEM_ALL>(c, i, 0), b = ld_tri<SMEM_ALL>(c, i, 1), e = ld_tri<SMEM_ALL>(c, i, 2);
                 float t, u, v;
                 if (moeller_trumbore(o, d, maxt, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(e.x, e.y, e.z), t, u, v)) {
                     if (ANY) return true;
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
 //      into the queue of the BSDF model it hit; a miss ends the path
 //   3. finished lanes write their radiance to lane_result (consumed by k_splat)
 // ---------------------------------------------------------------------------
-template <bool FIRST>
+template <bool FIRST, bool SMEM_ALL>
 __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
                                                  Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
             if (!FIRST && (flags & PF_HAS_SHADOW)) {
                 float4 so = cur.sh_o[i], sd = cur.sh_d[i];
                 Hit h; n_shadow++;
-                bool occluded = traverse<true>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
+                bool occluded = traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
                 if (!occluded) {
                     float2 c = cur.sh_c[i];
                     res = cur.result[i]; res_loaded = true;
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                 float3 o = V(ro.x, ro.y, ro.z), d = V(rd.x, rd.y, rd.z);
                 float maxt = ro.w;
                 Hit h; n_closest++;
-                bool found = traverse<false>(ctx, o, d, maxt, h);
+                bool found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
                 if (FIRST && cfg.hide_emitters) {
                     // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
                     while (found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0) {
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                         Ray r = spawn_ray(si.p, si.n, d);
                         o = r.o; maxt = r.maxt;
                         cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
-                        found = traverse<false>(ctx, o, d, maxt, h);
+                        found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
                     }
                 }
                 if (found) {
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : 4) k_shade(const __
                         // the adjoint needs Lr_dir now (prb.py:227): resolve the visibility inline
                         sray = spawn_ray_to(si.p, si.n, ds.p);
                         Hit h; n_shadow++;
-                        if (traverse<true>(ctx, sray.o, sray.d, sray.maxt, h)) { em_weight = V(0.f, 0.f, 0.f); ds.pdf = 0.f; active_em = false; }
+                        if (traverse<true, false>(ctx, sray.o, sray.d, sray.maxt, h)) { em_weight = V(0.f, 0.f, 0.f); ds.pdf = 0.f; active_em = false; }
                     }
                 }
                 // ---- BSDF (path.cpp:263-267)
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(BLOCK) k_ray_query(DevScene sc, uint32_t n, co
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float *r = rays + 7 * (size_t) i;
         Hit h;
-        bool found = traverse<ANY>(ctx, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h);
+        bool found = traverse<ANY, false>(ctx, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h);
         if (ANY) { occ_out[i] = found ? 1 : 0; continue; }
         t_out[i] = found ? h.t : PT_INF; uv_out[2 * i] = found ? h.u : 0.f; uv_out[2 * i + 1] = found ? h.v : 0.f;
         if (found) {
@@ -731,8 +739,11 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
-    if (first) k_trace<true><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-    else k_trace<false><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
+#define LAUNCH_TRACE(F, A) k_trace<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
+    if (first) { if (all) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
+    else { if (all) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
+#undef LAUNCH_TRACE
 }
 
 template <int TYPE>
@@ -788,8 +799,10 @@ void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, c
 }
 
 void set_trace_smem_attr(size_t bytes) {
-    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
