@@ -309,6 +309,176 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 }
 
 // ---------------------------------------------------------------------------
+// k_trace_dyn -- persistent-threads variant with dynamic work fetch (Aila & Laine).
+// A warp keeps a pool of up to 32 "ray jobs" (one per lane). A job is a slot of the
+// current buffer: its NEE shadow ray first (if any), then its path ray. Lanes that
+// finish a job become idle; when enough lanes are idle the warp claims the next slots
+// from a global counter (one atomicAdd per refill) instead of waiting for the slowest
+// ray of the batch. The traversal itself is the same speculative while-while walk,
+// resumable across refills (node / leaf / stack live in registers + local memory).
+// Semantics per slot are identical to k_trace.
+// ---------------------------------------------------------------------------
+
+template <bool FIRST, bool SMEM_ALL>
+__global__ void __launch_bounds__(BLOCK) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
+                                                     const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
+                                                     float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    DevScene sc = sc_in;
+    float4 *s_nodes = (float4 *) smem_raw;
+    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
+    TraceCtx c = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+
+    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    uint32_t n_shadow = 0, n_closest = 0;
+
+    // job state of this lane
+    int kind = 0;                     // 0 idle, 1 shadow ray, 2 path ray
+    uint32_t slot = 0, flags = 0;
+    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
+    float maxt = 0.f;
+    Hit hit; hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
+    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
+    bool occluded = false;
+    bool exhausted = false;           // the global pool is empty
+
+    auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
+        o = ro; d = rd; maxt = rmaxt;
+        inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+        hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
+        stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf = 0; occluded = false;
+    };
+
+    while (true) {
+        // ---- refill idle lanes from the global pool --------------------------------------
+        uint32_t idle_mask = __ballot_sync(0xffffffffu, kind == 0);
+        if (!exhausted && (__popc(idle_mask) >= DYN_REFILL_IDLE)) {
+            uint32_t cnt = __popc(idle_mask), base = 0;
+            if (lane_id == 0) base = atomicAdd(work_counter, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + cnt >= n) exhausted = true;
+            if (kind == 0) {
+                uint32_t i = base + __popc(idle_mask & ((1u << lane_id) - 1u));
+                if (i < n) {
+                    slot = i;
+                    flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w);
+                    if (!FIRST && (flags & PF_HAS_SHADOW)) {
+                        float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                        kind = 1; n_shadow++;
+                        start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
+                    } else {       // every queued slot is alive or has a shadow ray
+                        float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                        kind = 2; n_closest++;
+                        start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, kind != 0)) break;
+
+        // ---- traverse until this lane's ray is done or the warp wants to refill -----------
+        if (kind != 0) {
+            while (node != TRAV_SENTINEL) {
+                bool searching = true;
+                while (node >= 0 && node != TRAV_SENTINEL) {
+                    float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
+                    int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+                    float tl, tr;
+                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
+                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
+                    if (!hl && !hr) node = stack[sp--];
+                    else {
+                        node = hl ? cl : cr;
+                        if (hl && hr) {
+                            int32_t far = cr;
+                            if (tr < tl) { far = cl; node = cr; }
+                            stack[++sp] = far;
+                        }
+                    }
+                    if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }
+                    if (!__any_sync(__activemask(), searching)) break;
+                }
+                while (leaf < 0) {
+                    uint32_t enc = (uint32_t) ~leaf, first = enc >> 3, count = (enc & 7u) + 1u;
+                    for (uint32_t i = first; i < first + count; ++i) {
+                        float4 a = ld_tri<SMEM_ALL>(c, i, 0), b = ld_tri<SMEM_ALL>(c, i, 1), e = ld_tri<SMEM_ALL>(c, i, 2);
+                        float t, u, v;
+                        if (moeller_trumbore(o, d, maxt, V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(e.x, e.y, e.z), t, u, v)) {
+                            uint32_t prim = __float_as_uint(a.w);
+                            if (kind == 1) { occluded = true; }
+                            else if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; maxt = t; }
+                        }
+                    }
+                    leaf = node;
+                    if (node < 0) node = stack[sp--];
+                    if (occluded) { node = TRAV_SENTINEL; leaf = 0; }     // any-hit: stop at the first occluder
+                }
+                // dynamic fetch: leave the loop when too few lanes of the warp are still walking
+                if (!exhausted && __popc(__activemask()) < 32 - DYN_REFILL_IDLE) break;
+            }
+        }
+        __syncwarp();
+
+        // ---- retire finished rays -----------------------------------------------------------
+        int mytype = -1;
+        if (kind != 0 && node == TRAV_SENTINEL) {
+            if (kind == 1) {
+                if (!occluded) {
+                    float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
+                    res.x += sd.w; res.y += cc.x; res.z += cc.y;
+                    cur.result[slot] = res;
+                }
+                if (flags & PF_ALIVE) {
+                    float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
+                    kind = 2; n_closest++;
+                    start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
+                } else {
+                    lane_result[cur.rng[slot].w] = cur.result[slot];
+                    kind = 0;
+                }
+            } else {
+                bool found = hit.prim != 0xffffffffu;
+                if (FIRST && cfg.hide_emitters && found && sc.shapes[sc.prim_verts[hit.prim].w].emitter >= 0) {
+                    // skip_area_emitters (integrator.cpp:96-123)
+                    SurfaceInteraction si = compute_si(sc, hit.t, hit.u, hit.v, hit.prim, d);
+                    Ray r = spawn_ray(si.p, si.n, d);
+                    cur.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt);
+                    start_ray(r.o, d, r.maxt);
+                } else {
+                    if (found) {
+                        hit_out[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+                        mytype = sc.bsdfs[sc.shapes[sc.prim_verts[hit.prim].w].bsdf].type;
+                    } else lane_result[cur.rng[slot].w] = cur.result[slot];
+                    kind = 0;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < N_BSDF_TYPES; ++t) {
+            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
+            if (m) {
+                uint32_t leader = __ffs(m) - 1, off = 0;
+                if (lane_id == leader) off = atomicAdd(&qcounts[t], __popc(m));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = slot;
+            }
+        }
+    }
+    for (int of = 16; of; of >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, of); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, of); }
+    if (lane_id == 0) {
+        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Warp-cooperative fp32 gradient scatter (adjoint of tex_eval3). Called by all 32
 // lanes at a converged point; lanes without a request pass tex = -1. Lanes that
 // target the same texel are combined with __match_any_sync + shuffles so that the
@@ -740,6 +910,13 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
+    if (L.dynamic_fetch) {
+#define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
+        if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
+        else { if (all) LAUNCH_DYN(false, true); else LAUNCH_DYN(false, false); }
+#undef LAUNCH_DYN
+        return;
+    }
 #define LAUNCH_TRACE(F, A) k_trace<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
     if (first) { if (all) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
     else { if (all) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
@@ -799,6 +976,10 @@ void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, c
 }
 
 void set_trace_smem_attr(size_t bytes) {
+    cudaFuncSetAttribute(k_trace_dyn<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
