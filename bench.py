@@ -104,7 +104,7 @@ def cpu_baseline_port(scene, spp_sample):
 def cpu_baseline_reference(workload, spp_sample, reps=1):
     """The UNMODIFIED reference (mitsuba scalar_rgb, all host threads) when a snapshot of its
     runtime travels with the repo (oracle/ref_snapshot.sh); None otherwise."""
-    from mitsuba3_b200._ref_env import reference_env
+    from oracle.ref_env import reference_env
     env = reference_env(ROOT)
     if env is None or workload.startswith("heightfield"):
         return None

@@ -52,14 +52,15 @@ typedef enum b200pt_status {
 
 /* Texture: constant `rgb`/float value or a raw float32 `bitmap`
  * (src/textures/bitmap.cpp:496-519, drjit/texture_impl.h:87-205). */
-enum { B200PT_TEX_CONST = 0, B200PT_TEX_BITMAP = 1 };
+enum { B200PT_TEX_CONST = 0, B200PT_TEX_BITMAP = 1, B200PT_TEX_CHECKERBOARD = 2 /* src/textures/checkerboard.cpp:70-110, constant colours */ };
 enum { B200PT_WRAP_REPEAT = 0, B200PT_WRAP_MIRROR = 1, B200PT_WRAP_CLAMP = 2 };
 enum { B200PT_FILTER_BILINEAR = 0, B200PT_FILTER_NEAREST = 1 };
 
 typedef struct b200pt_texture {
     int32_t kind;           /* B200PT_TEX_*                                 */
     int32_t channels;       /* 1 or 3                                       */
-    float   value[3];       /* B200PT_TEX_CONST (channels==1: value[0])     */
+    float   value[3];       /* B200PT_TEX_CONST (channels==1: value[0]); checkerboard color0 */
+    float   value1[3];      /* B200PT_TEX_CHECKERBOARD color1 (gradient: color0 then color1) */
     int32_t width, height;  /* B200PT_TEX_BITMAP                            */
     const float *data;      /* host, height*width*channels, row-major       */
     int32_t wrap;           /* B200PT_WRAP_*                                */

@@ -16,7 +16,7 @@ ABI_VERSION = 1
 MAX_SLOTS = 12
 
 # enums ---------------------------------------------------------------------
-TEX_CONST, TEX_BITMAP = 0, 1
+TEX_CONST, TEX_BITMAP, TEX_CHECKERBOARD = 0, 1, 2
 WRAP_REPEAT, WRAP_MIRROR, WRAP_CLAMP = 0, 1, 2
 FILTER_BILINEAR, FILTER_NEAREST = 0, 1
 BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PRINCIPLED = 0, 1, 2, 3
@@ -41,7 +41,7 @@ STATUS = {0: "ok", 1: "invalid argument", 2: "CUDA error / no device",
 
 
 class Texture(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("channels", C.c_int32), ("value", C.c_float * 3),
+    _fields_ = [("kind", C.c_int32), ("channels", C.c_int32), ("value", C.c_float * 3), ("value1", C.c_float * 3),
                 ("width", C.c_int32), ("height", C.c_int32), ("data", C.POINTER(C.c_float)),
                 ("wrap", C.c_int32), ("filter", C.c_int32), ("to_uv", C.c_float * 9),
                 ("differentiable", C.c_int32)]

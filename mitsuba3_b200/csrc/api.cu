@@ -151,14 +151,14 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         if (t.channels != 1 && t.channels != 3) S_FAIL(B200PT_ERR_INVALID, "texture channels must be 1 or 3");
         o.kind = t.kind; o.channels = t.channels; o.width = t.width; o.height = t.height; o.wrap = t.wrap; o.filter = t.filter;
         o.differentiable = t.differentiable;
-        memcpy(o.value, t.value, sizeof(o.value)); memcpy(o.to_uv, t.to_uv, sizeof(o.to_uv));
+        memcpy(o.value, t.value, sizeof(o.value)); memcpy(o.value1, t.value1, sizeof(o.value1)); memcpy(o.to_uv, t.to_uv, sizeof(o.to_uv));
         TexMeta m; m.kind = t.kind; m.channels = t.channels; m.differentiable = t.differentiable != 0; m.dev_data = nullptr;
         if (t.kind == B200PT_TEX_BITMAP) {
             if (!t.data || t.width <= 0 || t.height <= 0) S_FAIL(B200PT_ERR_INVALID, "bitmap texture without data");
             m.n = (size_t) t.width * t.height * t.channels;
             float *dd = nullptr; S_TRY(dev_upload(s, t.data, m.n, &dd));
             o.data = dd; m.dev_data = dd;
-        } else m.n = (size_t) t.channels;
+        } else m.n = (size_t) t.channels * (t.kind == B200PT_TEX_CHECKERBOARD ? 2 : 1);
         m.grad_offset = (uint32_t) grad_off; o.grad_offset = (uint32_t) grad_off;
         if (m.differentiable) grad_off += m.n;
         s->tex.push_back(m);
@@ -305,7 +305,10 @@ b200pt_status b200pt_scene_update_texture(b200pt_scene *s, uint32_t tex, const f
     if (s->tex[tex].kind == B200PT_TEX_BITMAP) CU_TRY(cudaMemcpy(s->tex[tex].dev_data, host_data, n * sizeof(float), cudaMemcpyHostToDevice));
     else {
         const DevTexture *dt = s->dev.textures + tex;
-        CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value), host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+        int ch = s->tex[tex].channels;
+        CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value), host_data, ch * sizeof(float), cudaMemcpyHostToDevice));
+        if (s->tex[tex].kind == B200PT_TEX_CHECKERBOARD)   // color0 then color1
+            CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value1), host_data + ch, ch * sizeof(float), cudaMemcpyHostToDevice));
     }
     return B200PT_OK;
 }

@@ -495,6 +495,7 @@ PT_DEV void warp_scatter3(const DevScene &sc, int32_t tex, float2 uv, float3 g) 
         const DevTexture &t = sc.textures[tex];
         C = t.channels; grad = sc.grad + t.grad_offset;
         if (t.kind == B200PT_TEX_CONST) { tp.n = 1; tp.idx[0] = 0; tp.w[0] = 1.f; is_const = true; }
+        else if (t.kind == B200PT_TEX_CHECKERBOARD) { tp.n = 1; tp.idx[0] = checker_masks_equal(t, uv) ? 0 : 1; tp.w[0] = 1.f; }
         else tex_lookup(t, uv, tp);
     }
     for (int k = 0; k < 4; ++k) {

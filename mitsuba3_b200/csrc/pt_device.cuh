@@ -104,6 +104,7 @@ struct DevTexture {
     int32_t kind, channels, width, height, wrap, filter, differentiable;
     uint32_t grad_offset;      // into the flat gradient buffer (floats)
     float value[3];
+    float value1[3];           // checkerboard color1
     float to_uv[9];
     const float *data;
 };
@@ -240,8 +241,8 @@ PT_DEV int32_t tex_wrap(int32_t pos, int32_t shape, int mode) {
 }
 struct TexTaps { int32_t idx[4]; float w[4]; int n; };
 PT_DEV void tex_lookup(const DevTexture &t, float2 uv, TexTaps &tp) {
-    float u = __fmaf_rn(t.to_uv[0], uv.x, __fmaf_rn(t.to_uv[1], uv.y, t.to_uv[2]));
-    float v = __fmaf_rn(t.to_uv[3], uv.x, __fmaf_rn(t.to_uv[4], uv.y, t.to_uv[5]));
+    float u = __fmaf_rn(t.to_uv[1], uv.y, __fmaf_rn(t.to_uv[0], uv.x, t.to_uv[2]));
+    float v = __fmaf_rn(t.to_uv[4], uv.y, __fmaf_rn(t.to_uv[3], uv.x, t.to_uv[5]));
     int32_t W = t.width, H = t.height;
     if (t.filter == B200PT_FILTER_NEAREST) {
         int32_t px = tex_wrap((int32_t) floorf(u * (float) W), W, t.wrap), py = tex_wrap((int32_t) floorf(v * (float) H), H, t.wrap);
@@ -257,10 +258,22 @@ PT_DEV void tex_lookup(const DevTexture &t, float2 uv, TexTaps &tp) {
     tp.idx[0] = y0 * W + x0; tp.w[0] = w0x * w0y; tp.idx[1] = y0 * W + x1; tp.w[1] = w1x * w0y;
     tp.idx[2] = y1 * W + x0; tp.w[2] = w0x * w1y; tp.idx[3] = y1 * W + x1; tp.w[3] = w1x * w1y;
 }
+// checkerboard.cpp:70-110: which of the two colours is seen at uv. eval() picks color0 where the two
+// half-cell masks are EQUAL, eval_1() where they DIFFER (the reference's own asymmetry, kept).
+PT_DEV bool checker_masks_equal(const DevTexture &t, float2 uv) {
+    float u = __fmaf_rn(t.to_uv[1], uv.y, __fmaf_rn(t.to_uv[0], uv.x, t.to_uv[2]));
+    float v = __fmaf_rn(t.to_uv[4], uv.y, __fmaf_rn(t.to_uv[3], uv.x, t.to_uv[5]));
+    bool mx = u - floorf(u) > .5f, my = v - floorf(v) > .5f;
+    return mx == my;
+}
 PT_DEV float3 tex_eval3(const DevScene &sc, int32_t tex, float2 uv) {
     if (tex < 0) return V(0.f, 0.f, 0.f);
     const DevTexture &t = sc.textures[tex];
     if (t.kind == B200PT_TEX_CONST) return t.channels == 1 ? V(t.value[0], t.value[0], t.value[0]) : V(t.value[0], t.value[1], t.value[2]);
+    if (t.kind == B200PT_TEX_CHECKERBOARD) {
+        const float *c = checker_masks_equal(t, uv) ? t.value : t.value1;
+        return t.channels == 1 ? V(c[0], c[0], c[0]) : V(c[0], c[1], c[2]);
+    }
     TexTaps tp; tex_lookup(t, uv, tp);
     float out[3]; int C = t.channels;
 #pragma unroll
@@ -273,7 +286,13 @@ PT_DEV float3 tex_eval3(const DevScene &sc, int32_t tex, float2 uv) {
     }
     return V(out[0], out[1], out[2]);
 }
-PT_DEV float tex_eval1(const DevScene &sc, int32_t tex, float2 uv) { return tex_eval3(sc, tex, uv).x; }
+PT_DEV float tex_eval1(const DevScene &sc, int32_t tex, float2 uv) {
+    if (tex >= 0 && sc.textures[tex].kind == B200PT_TEX_CHECKERBOARD) {
+        const DevTexture &t = sc.textures[tex];
+        return checker_masks_equal(t, uv) ? t.value1[0] : t.value[0];      // eval_1: color0 where the masks differ
+    }
+    return tex_eval3(sc, tex, uv).x;
+}
 
 // fp32 atomicAdd scatter of a texture-parameter gradient (adjoint of tex_eval3)
 PT_DEV void tex_scatter3(const DevScene &sc, int32_t tex, float2 uv, float3 g) {

@@ -215,6 +215,9 @@ def update_params(scene: Scene, values: dict, device: int = 0) -> None:
         v = np.asarray(v, np.float32)
         if t.kind == abi.TEX_BITMAP:
             t.data = np.ascontiguousarray(v.reshape(t.data.shape))
+        elif t.kind == abi.TEX_CHECKERBOARD:
+            v = v.reshape(2, -1)
+            t.value[: t.channels], t.value1[: t.channels] = v[0, : t.channels], v[1, : t.channels]
         else:
             t.value[: t.channels] = v.reshape(-1)[: t.channels]
         if scene._handle is not None and scene._handle.h is not None:

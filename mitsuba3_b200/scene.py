@@ -50,6 +50,7 @@ class TextureData:
     kind: int = abi.TEX_CONST
     channels: int = 3
     value: np.ndarray = field(default_factory=lambda: np.zeros(3, f32))
+    value1: np.ndarray = field(default_factory=lambda: np.zeros(3, f32))   # checkerboard color1
     data: np.ndarray | None = None           # (H, W, C) float32
     wrap: int = abi.WRAP_REPEAT
     filter: int = abi.FILTER_BILINEAR
@@ -58,10 +59,16 @@ class TextureData:
 
     @property
     def size(self) -> int:
-        return int(self.data.size) if self.kind == abi.TEX_BITMAP else self.channels
+        if self.kind == abi.TEX_BITMAP:
+            return int(self.data.size)
+        return self.channels * (2 if self.kind == abi.TEX_CHECKERBOARD else 1)
 
     def array(self) -> np.ndarray:
-        return self.data if self.kind == abi.TEX_BITMAP else self.value[: self.channels]
+        if self.kind == abi.TEX_BITMAP:
+            return self.data
+        if self.kind == abi.TEX_CHECKERBOARD:      # (2, channels): color0, color1
+            return np.stack([self.value[: self.channels], self.value1[: self.channels]])
+        return self.value[: self.channels]
 
 
 @dataclass
@@ -149,6 +156,8 @@ class Scene:
             ct.kind, ct.channels = t.kind, t.channels
             v = np.zeros(3, f32); v[: t.channels] = np.asarray(t.value, f32)[: t.channels]
             ct.value = (C.c_float * 3)(*v.tolist())
+            v1 = np.zeros(3, f32); v1[: t.channels] = np.asarray(t.value1, f32)[: t.channels]
+            ct.value1 = (C.c_float * 3)(*v1.tolist())
             if t.kind == abi.TEX_BITMAP:
                 d = np.ascontiguousarray(t.data, dtype=f32)
                 keep.append(d)
@@ -250,6 +259,20 @@ class _Parser:
                 if "to_uv" in spec:
                     t.to_uv = np.asarray(spec["to_uv"], f32).reshape(3, 3)
                 t.name = name + ".data"
+            elif ty == "checkerboard":
+                def const(c, dflt):
+                    c = dflt if c is None else c
+                    if isinstance(c, dict):
+                        if c.get("type") != "rgb":
+                            raise NotImplementedError("checkerboard colours must be constants")
+                        c = c["value"]
+                    c = np.asarray(c, f32).reshape(-1)
+                    return np.full(3, c[0], f32) if c.size == 1 else c[:3].astype(f32)
+                t.kind = abi.TEX_CHECKERBOARD
+                t.value, t.value1 = const(spec.get("color0"), 0.4), const(spec.get("color1"), 0.2)
+                if "to_uv" in spec:
+                    t.to_uv = np.asarray(getattr(spec["to_uv"], "matrix", spec["to_uv"]), f32).reshape(3, 3)
+                t.name = name + ".colors"       # (2, channels): color0, color1
             else:
                 raise NotImplementedError(f"texture type {ty!r} is outside the hot-path scope")
         else:

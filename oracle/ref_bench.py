@@ -1,5 +1,5 @@
 """Times the UNMODIFIED reference (mitsuba scalar_rgb, all host threads) on a bounded sample of
-a bench workload. Run in a subprocess with the environment of mitsuba3_b200._ref_env; prints one
+a bench workload. Run in a subprocess with the environment of oracle.ref_env; prints one
 JSON line. Used by bench.py (cpu_baseline kind "reference", --impl reference)."""
 import json
 import sys

@@ -1,11 +1,11 @@
 """Locate an (optional) snapshot of the unmodified reference's runtime for the live-plugin
 tests and the `kind: "reference"` CPU baseline (oracle/ref_snapshot.sh). Returns the
-environment a SUBPROCESS needs; this package never imports mitsuba itself."""
+environment a SUBPROCESS needs. Test infrastructure (lives under oracle/, never imported by the product)."""
 import os
 
 
 def reference_env(root=None):
-    root = root or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    root = root or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root
     for base in (os.environ.get("B200PT_MITSUBA_BUILD", ""), os.path.join(root, "oracle", "_ref", "mitsuba_build"), "/tmp/mi_probe/build"):
         if base and os.path.exists(os.path.join(base, "libmitsuba.so")):
             env = dict(os.environ)

@@ -1,5 +1,5 @@
 """Runs inside a subprocess whose environment points at a snapshot of the UNMODIFIED
-reference (mitsuba3_b200._ref_env). `cpu`: extraction parity; `gpu`: mi.render through
+reference (oracle.ref_env). `cpu`: extraction parity; `gpu`: mi.render through
 the registered b200_path plugin on the GPU vs Mitsuba's own `path` on the CPU."""
 import sys
 

@@ -213,6 +213,12 @@ def gen_bsdfs():
                             "clearcoat": 0.9, "clearcoat_gloss": 0.5},
         "principled_matpreview": {"type": "principled", "base_color": {"type": "rgb", "value": [0.94, 0.271, 0.361]},
                                   "roughness": 0.3, "metallic": 0.0, "specular": 0.5},
+        "diffuse_checker": {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                                              "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]},
+                                                              "to_uv": mi.ScalarTransform3f().scale([4, 6])}},
+        "principled_checker_rough": {"type": "principled", "base_color": {"type": "rgb", "value": [0.6, 0.6, 0.6]},
+                                     "roughness": {"type": "checkerboard", "color0": 0.15, "color1": 0.7,
+                                                   "to_uv": mi.ScalarTransform3f().scale([3, 3])}, "metallic": 0.5},
         "principled_coat_sheen": {"type": "principled", "base_color": {"type": "rgb", "value": [0.2, 0.4, 0.9]},
                                   "roughness": 0.6, "clearcoat": 1.0, "clearcoat_gloss": 0.8, "sheen": 0.5, "sheen_tint": 0.7,
                                   "spec_tint": 0.3, "flatness": 0.5},

@@ -82,6 +82,12 @@ BSDF_SPECS = {
                                 "specular_reflectance": {"type": "rgb", "value": [0.9, 0.95, 1.0]},
                                 "specular_transmittance": {"type": "rgb", "value": [0.8, 0.9, 0.7]}},
     "twosided_diffuse": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.3, 0.6, 0.1]}}},
+    "diffuse_checker": {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                                          "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]},
+                                                          "to_uv": [[4, 0, 0], [0, 6, 0], [0, 0, 1]]}},
+    "principled_checker_rough": {"type": "principled", "base_color": {"type": "rgb", "value": [0.6, 0.6, 0.6]},
+                                 "roughness": {"type": "checkerboard", "color0": 0.15, "color1": 0.7, "to_uv": [[3, 0, 0], [0, 3, 0], [0, 0, 1]]},
+                                 "metallic": 0.5},
     "principled_default": {"type": "principled"},
     "principled_rough_metal": {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.6, 0.2]}, "metallic": 0.8, "roughness": 0.35, "specular": 0.5},
     "principled_full": {"type": "principled", "base_color": {"type": "rgb", "value": [0.7, 0.1, 0.1]}, "roughness": 0.15, "anisotropic": 0.5,

@@ -38,6 +38,24 @@ def test_backward_matches_oracle(built, rfilter):
     assert np.abs(g["light.emitter.radiance.value"]).max() > 0
 
 
+def test_backward_checkerboard_colors(built):
+    """Gradients w.r.t. the two colours of a checkerboard reflectance (checkerboard.cpp) vs the oracle."""
+    from oracle import oracle
+    from mitsuba3_b200.integrators import PRBIntegrator
+    d = cbox(res=32, rfilter="box", spp=16, max_depth=4); d["integrator"] = {"type": "prb", "max_depth": 4}
+    d["chk"] = {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.3, 0.2]},
+                                                    "color1": {"type": "rgb", "value": [0.2, 0.4, 0.9]}, "to_uv": [[5, 0, 0], [0, 5, 0], [0, 0, 1]]}}
+    d["floor"]["bsdf"] = {"type": "ref", "id": "chk"}
+    sc = mb.load_dict(d)
+    grad_in = np.random.default_rng(3).random(sc.film_shape).astype(np.float32) * 1e-2
+    g = PRBIntegrator(max_depth=4).render_backward(sc, grad_in, seed=7, spp=16)
+    o = oracle.OracleScene(sc); o.grad_zero(); o.render_backward(grad_in, spp=16, seed=7, max_depth=4)
+    ref = o.grad(sc.parameters()["chk.reflectance.colors"])
+    got = g["chk.reflectance.colors"]
+    assert got.shape == (2, 3) and np.abs(ref).min() > 0
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-3, (got, ref)
+
+
 def test_backward_matches_finite_differences(built):
     """d(mean image)/d(albedo, radiance) vs central differences of the primal renderer."""
     from mitsuba3_b200.integrators import PRBIntegrator, update_params

@@ -7,7 +7,7 @@ import sys
 import pytest
 
 from conftest import ROOT
-from mitsuba3_b200._ref_env import reference_env
+from oracle.ref_env import reference_env
 
 
 def _run(mode):
