@@ -107,7 +107,7 @@ SYMBOLS = [
     "b200pt_get_stats", "b200pt_abi_sizeof",
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200pt.so")
+LIB_PATH = os.environ.get("B200PT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200pt.so")
 _lib = None
 
 

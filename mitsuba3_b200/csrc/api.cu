@@ -205,7 +205,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         memcpy(o.to_world, sh.to_world, sizeof(o.to_world)); memcpy(o.frame_n, sh.frame_n, sizeof(o.frame_n)); o.inv_area = sh.inv_area;
         s->type_present[desc->bsdfs[sh.bsdf].type] = true;
         memcpy(&verts[vo * 8], sh.vertices, (size_t) sh.n_vertices * 8 * sizeof(float));
-        std::vector<float> cdf;
+        std::vector<float> cdf, pmf;
         double acc = 0;
         for (uint32_t f = 0; f < sh.n_faces; ++f) {
             const uint32_t *fr = sh.faces + 4 * (size_t) f;
@@ -221,12 +221,13 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
                 float e0[3] = { p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2] }, e1[3] = { p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2] };
                 float c[3] = { fmaf(e0[1], e1[2], -(e0[2] * e1[1])), fmaf(e0[2], e1[0], -(e0[0] * e1[2])), fmaf(e0[0], e1[1], -(e0[1] * e1[0])) };
                 float area = .5f * sqrtf(fmaf(c[2], c[2], fmaf(c[1], c[1], c[0] * c[0])));
-                acc += (double) area; cdf.push_back((float) acc);
+                acc += (double) area; cdf.push_back((float) acc); pmf.push_back(area);
             }
         }
         if (sh.sampling == B200PT_SAMPLING_MESH) {
-            float *dc = nullptr; S_TRY(dev_upload(s, cdf.data(), cdf.size(), &dc));
-            o.area_cdf = dc; o.area_sum = (float) acc; o.area_norm = (float) (1.0 / acc);
+            // DiscreteDistribution::compute_cdf_scalar (core/distr_1d.h:236-267)
+            float *dc = nullptr, *dp = nullptr; S_TRY(dev_upload(s, cdf.data(), cdf.size(), &dc)); S_TRY(dev_upload(s, pmf.data(), pmf.size(), &dp));
+            o.area_cdf = dc; o.area_pmf = dp; o.area_sum = cdf.empty() ? 0.f : cdf.back(); o.area_norm = 1.0f / o.area_sum;
         }
         vo += sh.n_vertices; po += sh.n_faces;
     }

@@ -543,8 +543,11 @@ PT_DEV float3 bsdf_backward(const DevScene &sc, const DevBsdf &b, float2 uv, flo
 // TYPE. ADJOINT = PRB backward pass: replays the path, resolves the NEE
 // visibility inline and scatters the parameter gradients (prb.py:263-313).
 // ---------------------------------------------------------------------------
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4
+#endif
 template <int TYPE, bool ADJOINT>
-__global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : 4) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
+__global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
                                                  const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, PathBuf nxt,
                                                  uint32_t *__restrict__ nxt_count, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {

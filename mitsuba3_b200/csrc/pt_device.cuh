@@ -121,7 +121,7 @@ struct DevShape {
     uint32_t first_prim, n_prims, first_vertex, pad;
     float to_world[16];
     float frame_n[3]; float inv_area;
-    float area_sum, area_norm; const float *area_cdf; // B200PT_SAMPLING_MESH
+    float area_sum, area_norm; const float *area_cdf, *area_pmf; // B200PT_SAMPLING_MESH (core/distr_1d.h)
 };
 
 struct DevEmitter { int32_t shape, radiance_tex; float sampling_weight; float pad; };
@@ -484,12 +484,16 @@ PT_DEV void shape_sample_position(const DevScene &sc, const DevShape &sh, float 
         n = V(sh.frame_n[0], sh.frame_n[1], sh.frame_n[2]); pdf = sh.inv_area; uv = make_float2(sx, sy);
         return;
     }
+    // DiscreteDistribution::sample_reuse (core/distr_1d.h:137-183)
     float value = sy * sh.area_sum;
     uint32_t lo = 0, hi = sh.n_prims - 1;
-    while (lo < hi) { uint32_t mid = (lo + hi) / 2; float c = __ldg(&sh.area_cdf[mid]); if (c < value || c == 0.f) lo = mid + 1; else hi = mid; }
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) / 2; float c = __ldg(&sh.area_cdf[mid]);
+        if (((c < value) || c == 0.f) && c != sh.area_sum) lo = mid + 1; else hi = mid;
+    }
     uint32_t face = lo;
-    float cdf0 = face ? __ldg(&sh.area_cdf[face - 1]) : 0.f, cdf1 = __ldg(&sh.area_cdf[face]);
-    float sy_re = fdiv(value - cdf0, cdf1 - cdf0);
+    float pmf_n = __ldg(&sh.area_pmf[face]) * sh.area_norm, cdf_n = face ? __ldg(&sh.area_cdf[face - 1]) * sh.area_norm : 0.f;
+    float sy_re = fdiv(sy - cdf_n, pmf_n);
     uint4 pv = sc.prim_verts[sh.first_prim + face];
     float4 a0 = sc.vertices[2 * pv.x], a1 = sc.vertices[2 * pv.x + 1];
     float4 c0 = sc.vertices[2 * pv.y], c1 = sc.vertices[2 * pv.y + 1];

@@ -72,3 +72,17 @@ def compare_images(img, ref, rtol=1e-3, floor=1e-2, max_bad_frac=0.005, max_mean
     assert bad <= max_bad_frac, f"{bad:.5f} of the pixels differ by more than {rtol} (allowed {max_bad_frac})"
     assert l2 <= max_mean_rel, f"relative L2 error {l2:.3e} > {max_mean_rel}"
     return bad, l2
+
+
+def multi_emitter_cbox(res=32, rfilter="box", spp=16, max_depth=6):
+    """Cornell box with three emitters (same scene as gen_golden.py:multi_emitter)."""
+    import mitsuba3_b200 as mb
+    T = mb.Transform4f
+    d = cbox(res, rfilter, spp, max_depth)
+    d["cube-light"] = {"type": "cube", "to_world": T().translate([-0.5, 0.2, 0.3]).rotate([0, 1, 0], 30).scale(0.08),
+                       "bsdf": {"type": "ref", "id": "white"},
+                       "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [2.0, 8.0, 3.0]}}}
+    d["side-light"] = {"type": "rectangle", "to_world": T().translate([0.98, -0.3, 0.2]).rotate([0, 1, 0], -90).scale([0.15, 0.25, 1]),
+                       "bsdf": {"type": "ref", "id": "white"},
+                       "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [6.0, 2.0, 9.0]}}}
+    return d

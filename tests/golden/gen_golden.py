@@ -277,8 +277,28 @@ def gen_material_renders():
     save("materials_renders.npz", **out)
 
 
+def multi_emitter(d):
+    """Second and third light: a small emissive cube (mesh area sampling, mesh.cpp:1662-1712) and a
+    second rectangle -> uniform emitter selection with sample reuse (scene.cpp:248-271)."""
+    T = mi.ScalarTransform4f
+    d["cube-light"] = {"type": "cube", "to_world": T().translate([-0.5, 0.2, 0.3]).rotate([0, 1, 0], 30).scale(0.08),
+                       "bsdf": {"type": "ref", "id": "white"},
+                       "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [2.0, 8.0, 3.0]}}}
+    d["side-light"] = {"type": "rectangle", "to_world": T().translate([0.98, -0.3, 0.2]).rotate([0, 1, 0], -90).scale([0.15, 0.25, 1]),
+                       "bsdf": {"type": "ref", "id": "white"},
+                       "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [6.0, 2.0, 9.0]}}}
+    return d
+
+
+def gen_multi_emitter():
+    out = {}
+    for (res, spp, md, seed) in [(32, 16, 6, 0), (32, 8, 3, 2)]:
+        out[f"multi_{res}_box_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter="box", spp=spp, max_depth=md, extra=multi_emitter), seed, spp)
+    save("multi_emitter_renders.npz", **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials"]
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi"]
     if "rng" in what:
         gen_rng()
     scene = None
@@ -292,3 +312,5 @@ if __name__ == "__main__":
         gen_renders()
     if "materials" in what:
         gen_material_renders()
+    if "multi" in what:
+        gen_multi_emitter()
