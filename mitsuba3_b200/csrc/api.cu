@@ -437,7 +437,7 @@ static RenderCfg make_cfg(const b200pt_scene *s, const b200pt_render_params *p) 
 
 static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix) {
     size_t lanes = p->chunk_lanes;
-    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 24); }   // 16 Mi lanes (~6.5 GB of wavefront state): measured optimum, see DESIGN.md
+    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 26); }   // 64 Mi lanes (~26 GB of wavefront state): fewest launches, measured best (profiles/r01_tuning.md)
     size_t px = std::max<size_t>(1, lanes / std::max(1u, p->spp));
     (void) s;
     return std::min<size_t>(px, std::max(1u, n_pix));
