@@ -183,6 +183,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         if (e.shape < 0 || e.shape >= (int32_t) desc->n_shapes || e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures)
             S_FAIL(B200PT_ERR_INVALID, "emitter references a missing shape/texture");
         if (desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST) S_FAIL(B200PT_ERR_UNSUPPORTED, "textured area lights are outside the hot-path scope");
+        if (e.sampling_weight != 1.f) S_FAIL(B200PT_ERR_UNSUPPORTED, "non-uniform emitter sampling weights (Scene::m_emitter_distr, scene.cpp:259-262) are outside the hot-path scope");
         he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].pad = 0.f;
     }
     d.n_emitters = desc->n_emitters;
@@ -281,7 +282,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     s->launch.n_smem_tris = d.n_tris <= 512 ? d.n_tris : 0;              // <= 24 KiB of triangles
     s->launch.smem_trace = ((size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
     s->launch.smem_tables = (d.tables_bytes <= 12288 ? d.tables_bytes : 0) + (d.geom_bytes <= 20480 ? d.geom_bytes : 0);
-    s->launch.grid = (int) s->n_sm * 4;
+    { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
     set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);

@@ -319,8 +319,11 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 // Semantics per slot are identical to k_trace.
 // ---------------------------------------------------------------------------
 
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 5
+#endif
 template <bool FIRST, bool SMEM_ALL>
-__global__ void __launch_bounds__(BLOCK) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
+__global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -165,7 +165,7 @@ def gen_rays(scene):
 
 
 # --------------------------------------------------------------------------- BSDF tables
-def bsdf_table(bsdf_dict, n=64, seed=7, transmissive=False):
+def bsdf_table(bsdf_dict, n=64, seed=7, transmissive=False, uv_range=(0.0, 1.0)):
     r = np.random.default_rng(seed)
     bsdf = mi.load_dict(bsdf_dict)
     q = np.zeros((n, 11), np.float32)
@@ -178,7 +178,7 @@ def bsdf_table(bsdf_dict, n=64, seed=7, transmissive=False):
             return v
         wi = hemi(transmissive and r.random() < 0.3)
         wo = hemi(transmissive and r.random() < 0.5)
-        uv = r.random(2); s1 = r.random(); s2 = r.random(2)
+        uv = uv_range[0] + (uv_range[1] - uv_range[0]) * r.random(2); s1 = r.random(); s2 = r.random(2)
         q[i] = [*wi, *wo, *uv, s1, *s2]
         q32 = q[i]
         si = dr.zeros(mi.SurfaceInteraction3f)
@@ -223,10 +223,17 @@ def gen_bsdfs():
                                   "roughness": 0.6, "clearcoat": 1.0, "clearcoat_gloss": 0.8, "sheen": 0.5, "sheen_tint": 0.7,
                                   "spec_tint": 0.3, "flatness": 0.5},
     }
-    out = {}
+    # bitmap textures (bitmap.cpp:496-519, texture_impl.h:87-205): raw float data, every wrap / filter mode,
+    # uv outside [0,1] to exercise the wrapping
+    tex = (0.1 + 0.8 * np.random.default_rng(99).random((5, 7, 3))).astype(np.float32)
+    out = {"bitmap_data": tex}
+    for wrap in ("repeat", "mirror", "clamp"):
+        for filt in ("bilinear", "nearest"):
+            specs[f"diffuse_bitmap_{wrap}_{filt}"] = {"type": "diffuse", "reflectance": {
+                "type": "bitmap", "bitmap": mi.Bitmap(tex), "raw": True, "wrap_mode": wrap, "filter_type": filt}}
     for name, spec in specs.items():
         trans = name.startswith("dielectric") or name in ("principled_full", "twosided_diffuse")
-        q, o = bsdf_table(spec, transmissive=trans)
+        q, o = bsdf_table(spec, transmissive=trans, uv_range=(-1.6, 2.6) if "bitmap" in name else (0.0, 1.0))
         out[name + "_in"] = q; out[name + "_out"] = o
     save("bsdf_tables.npz", **out)
 

@@ -99,6 +99,12 @@ BSDF_SPECS = {
 }
 
 
+for _wrap in ("repeat", "mirror", "clamp"):
+    for _filt in ("bilinear", "nearest"):
+        BSDF_SPECS[f"diffuse_bitmap_{_wrap}_{_filt}"] = {"type": "diffuse", "reflectance": {
+            "type": "bitmap", "data": golden("bsdf_tables.npz")["bitmap_data"], "raw": True, "wrap_mode": _wrap, "filter_type": _filt}}
+
+
 @pytest.mark.parametrize("name", sorted(BSDF_SPECS))
 def test_bsdf_tables(name, oracle_mod):
     """BSDF::eval_pdf_sample against the reference's own outputs (bsdf_tables.npz) and the oracle."""
