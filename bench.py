@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prb", action="store_true", help="also time the PRB gradient step (ms/grad-step)")
+    ap.add_argument("--prb", action="store_true", help="(default on) also time the PRB gradient step (ms/grad-step)")
+    ap.add_argument("--no-prb", action="store_true", help="skip the PRB gradient-step timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -256,20 +257,31 @@ def main():
         e2e = {"value": samples_per_step / float(tt.item()) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": img_bytes, "checksum": float(np.asarray(img).mean())}
 
-    # ---- optional PRB gradient step ---------------------------------------------------------
+    # ---- PRB gradient step (BASELINE.json: "ms/grad-step (PRB)"): primal + adjoint, device-timed -------
     prb = None
-    if args.prb:
+    if not args.no_prb:
         pint = PRBIntegrator(max_depth=md)
         gi = torch.full((h, w, 3), 1.0 / (h * w * 3), device=f"cuda:{local}")
-        spp_g = 64
-        mbd.render_backward_distributed(scene, gi, pint, seed=1, spp=spp_g, device=local)
-        sync_all(); t2 = time.perf_counter()
-        for i in range(max(1, args.steps // 2)):
+        spp_g = 64 * n_gpus if args.scaling == "weak" else 64
+        n_grad = max(3, args.steps // 2)
+        for i in range(2):
+            mbd.render_distributed(scene, pint, seed=50 + i, spp=spp_g, device=local)
+            mbd.render_backward_distributed(scene, gi, pint, seed=150 + i, spp=spp_g, device=local)
+        sync_all()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for i in range(n_grad):
             mbd.render_distributed(scene, pint, seed=i, spp=spp_g, device=local)
             mbd.render_backward_distributed(scene, gi, pint, seed=100 + i, spp=spp_g, device=local)
+        pe1.record()
         sync_all()
-        prb = {"ms_per_grad_step": (time.perf_counter() - t2) / max(1, args.steps // 2) * 1e3, "spp": spp_g,
-               "what": "primal render + render_backward (PRB), wall-clock, max_depth %d" % md}
+        tp = torch.tensor([pe0.elapsed_time(pe1)], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        prb = {"ms_per_grad_step": float(tp.item()) / n_grad, "spp": spp_g, "grad_steps": n_grad,
+               "what": "primal render + render_backward (PRB adjoint, atomicAdd gradient scatter%s), CUDA events, "
+                       "max over ranks, max_depth %d" % (" + gradient all-reduce" if world > 1 else "", md),
+               "reference": "unmeasurable here: prb needs an AD variant (llvm_ad_rgb) and the image has no libLLVM"}
 
     if rank == 0:
         peaks = {}
