@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 1
+#define B200PT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define B200PT_API __attribute__((visibility("default")))
@@ -135,11 +135,30 @@ typedef struct b200pt_shape {
     float    inv_area;        /* rectangle m_inv_surface_area                */
 } b200pt_shape;
 
-/* Area light (src/emitters/area.cpp). */
+/* Emitters: area light (src/emitters/area.cpp:83-209) attached to a shape, or ONE
+ * environment emitter per scene (scene.cpp:63-67): `constant`
+ * (src/emitters/constant.cpp:60-160) or `envmap` (src/emitters/envmap.cpp:107-590).
+ * The order of ::emitters is the order of Scene::emitters() (scene.cpp:45-61): it
+ * decides which emitter a sample picks (scene.cpp:248-271). */
+enum { B200PT_EMITTER_AREA = 0, B200PT_EMITTER_CONSTANT = 1, B200PT_EMITTER_ENVMAP = 2 };
+
 typedef struct b200pt_emitter {
-    int32_t shape;        /* index into ::shapes                            */
-    int32_t radiance_tex; /* texture index (constant rgb on the hot path)   */
+    int32_t shape;        /* area: index into ::shapes; -1 for environment emitters  */
+    int32_t radiance_tex; /* area / constant: texture index (constant: kind CONST)   */
     float   sampling_weight;
+    int32_t type;         /* B200PT_EMITTER_*                                        */
+    /* envmap only. `env_data` is the latitude-longitude map as float32 RGB, row-major
+     * env_height x env_width x 3, real columns only (the `data` parameter of the plugin
+     * without its two halo columns, envmap.cpp:155-192). The library adds the periodic
+     * halo, and builds the luminance x sin(theta) Hierarchical2D warp
+     * (envmap.cpp:474-529, core/distr_2d.h:403-540) and the bounding sphere of the
+     * scene (envmap.cpp:260-274) itself. */
+    uint32_t env_width, env_height;   /* >= 2 x 3 (Bitmap::pad_to, envmap.cpp:141)   */
+    const float *env_data;
+    float   env_scale;                /* `scale` (envmap.cpp:196)                    */
+    int32_t env_mis_compensation;     /* `mis_compensation` (envmap.cpp:197,497-517) */
+    float   to_world[16];             /* row-major; only the linear 3x3 part is used */
+    float   to_world_inv[16];         /* row-major inverse of to_world               */
 } b200pt_emitter;
 
 /* Reconstruction filter of the film (imageblock.cpp:192-574). */

@@ -12,11 +12,12 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SLOTS = 12
 
 # enums ---------------------------------------------------------------------
 TEX_CONST, TEX_BITMAP, TEX_CHECKERBOARD = 0, 1, 2
+EMITTER_AREA, EMITTER_CONSTANT, EMITTER_ENVMAP = 0, 1, 2
 WRAP_REPEAT, WRAP_MIRROR, WRAP_CLAMP = 0, 1, 2
 FILTER_BILINEAR, FILTER_NEAREST = 0, 1
 BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PRINCIPLED = 0, 1, 2, 3
@@ -62,7 +63,11 @@ class Shape(C.Structure):
 
 
 class Emitter(C.Structure):
-    _fields_ = [("shape", C.c_int32), ("radiance_tex", C.c_int32), ("sampling_weight", C.c_float)]
+    _fields_ = [("shape", C.c_int32), ("radiance_tex", C.c_int32), ("sampling_weight", C.c_float),
+                ("type", C.c_int32), ("env_width", C.c_uint32), ("env_height", C.c_uint32),
+                ("env_data", C.POINTER(C.c_float)), ("env_scale", C.c_float),
+                ("env_mis_compensation", C.c_int32), ("to_world", C.c_float * 16),
+                ("to_world_inv", C.c_float * 16)]
 
 
 class Sensor(C.Structure):

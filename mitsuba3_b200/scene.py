@@ -9,7 +9,7 @@ Supported plugin types (same property names as the reference):
   ``independent`` sampler (sample_count, seed); shapes ``rectangle`` / ``cube``
   (src/shapes/rectangle.cpp, cube.cpp) and ``mesh`` (packed arrays, as produced
   by the host's loaders); BSDFs ``diffuse`` / ``conductor`` / ``dielectric`` /
-  ``principled`` / ``twosided``; emitter ``area``; textures ``rgb`` / float /
+  ``principled`` / ``twosided``; emitters ``area`` / ``constant`` / ``envmap``; textures ``rgb`` / float /
   ``bitmap`` (raw float32 data); ``ref``.
 
 Everything else (XML, OBJ/PLY loaders, spectra, other plugins) stays in the
@@ -100,9 +100,15 @@ class ShapeData:
 
 @dataclass
 class EmitterData:
-    shape: int
-    radiance_tex: int
+    shape: int                # area: index of the shape; -1 for the environment emitter
+    radiance_tex: int         # area / constant
     sampling_weight: float = 1.0
+    type: int = abi.EMITTER_AREA
+    env_data: np.ndarray | None = None     # envmap: (H, W, 3) float32, real columns only
+    env_scale: float = 1.0
+    env_mis_compensation: bool = False
+    to_world: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=f32))
+    to_world_inv: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=f32))
 
 
 @dataclass
@@ -188,6 +194,15 @@ class Scene:
         ems = (abi.Emitter * max(1, len(self.emitters)))()
         for i, e in enumerate(self.emitters):
             ems[i].shape, ems[i].radiance_tex, ems[i].sampling_weight = e.shape, e.radiance_tex, e.sampling_weight
+            ems[i].type = e.type
+            ems[i].to_world = (C.c_float * 16)(*np.asarray(e.to_world, f32).reshape(16).tolist())
+            ems[i].to_world_inv = (C.c_float * 16)(*np.asarray(e.to_world_inv, f32).reshape(16).tolist())
+            if e.type == abi.EMITTER_ENVMAP:
+                data = np.ascontiguousarray(e.env_data, dtype=f32)
+                keep.append(data)
+                ems[i].env_height, ems[i].env_width = data.shape[0], data.shape[1]
+                ems[i].env_data = data.ctypes.data_as(C.POINTER(C.c_float))
+                ems[i].env_scale, ems[i].env_mis_compensation = float(e.env_scale), int(e.env_mis_compensation)
         d = abi.SceneDesc()
         d.abi_version = abi.ABI_VERSION
         d.n_shapes, d.shapes = len(self.shapes), shapes
@@ -405,6 +420,43 @@ class _Parser:
             pass
         self.scene.shapes.append(sh)
 
+    # -- environment emitters ------------------------------------------------
+    def environment(self, eid: str, d: dict):
+        """``constant`` (constant.cpp:60-74) and ``envmap`` (envmap.cpp:107-200). The map is passed
+        as a float32 array under ``bitmap`` / ``data`` (H x W x 3, linear RGB, real columns) or as a
+        ``.npy`` ``filename``; image decoding stays in the host."""
+        if any(e.type != abi.EMITTER_AREA for e in self.scene.emitters):
+            raise ValueError("Only one environment emitter can be specified per scene.")      # scene.cpp:64
+        tw = _as_transform(d.get("to_world"))
+        inv = np.ascontiguousarray(tw.inverse_transpose.T, dtype=f32)
+        if d["type"] == "constant":
+            rad = self.texture(f"{eid}.radiance", d.get("radiance"), 3, 1.0)
+            if self.scene.textures[rad].kind != abi.TEX_CONST:
+                raise ValueError("Expected a non-spatially varying radiance spectra!")        # constant.cpp:64
+            self.scene.emitters.append(EmitterData(shape=-1, radiance_tex=rad, type=abi.EMITTER_CONSTANT,
+                                                   sampling_weight=float(d.get("sampling_weight", 1.0))))
+            return
+        data = d.get("bitmap", d.get("data"))
+        if data is None and str(d.get("filename", "")).endswith(".npy"):
+            data = np.load(d["filename"])
+        if data is None:
+            raise NotImplementedError("envmap: pass the decoded image as a float32 array under `bitmap` (or a .npy `filename`)")
+        data = np.asarray(data, dtype=f32)
+        if data.ndim == 2:
+            data = np.repeat(data[..., None], 3, axis=2)
+        if data.ndim != 3 or data.shape[2] < 3:
+            raise ValueError("envmap: expected an (H, W, 3) array")
+        data = np.ascontiguousarray(data[..., :3])
+        # Bitmap::pad_to(2, 3) (envmap.cpp:141): replicate the last column / row
+        if data.shape[1] < 2:
+            data = np.concatenate([data, np.repeat(data[:, -1:, :], 2 - data.shape[1], axis=1)], axis=1)
+        if data.shape[0] < 3:
+            data = np.concatenate([data, np.repeat(data[-1:, :, :], 3 - data.shape[0], axis=0)], axis=0)
+        self.scene.emitters.append(EmitterData(
+            shape=-1, radiance_tex=-1, type=abi.EMITTER_ENVMAP, env_data=data, env_scale=float(d.get("scale", 1.0)),
+            env_mis_compensation=bool(d.get("mis_compensation", False)), to_world=tw.matrix.copy(), to_world_inv=inv,
+            sampling_weight=float(d.get("sampling_weight", 1.0))))
+
     # -- sensor --------------------------------------------------------------
     def sensor(self, d: dict):
         if d["type"] != "perspective":
@@ -457,6 +509,8 @@ class _Parser:
                 self.sensor(v)
             elif ty in ("rectangle", "cube", "mesh"):
                 self.shape(k, v)
+            elif ty in ("constant", "envmap"):
+                self.environment(k, v)
             elif ty in ("diffuse", "conductor", "dielectric", "principled", "twosided"):
                 pass
             else:

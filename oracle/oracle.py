@@ -23,7 +23,7 @@ class OrcStats(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "pt_oracle_principled.inc", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "pt_oracle_principled.inc", "pt_oracle_env.inc", "Makefile")]
     src.append(os.path.join(_HERE, "..", "include", "b200pt.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src)
@@ -50,6 +50,7 @@ def load():
         lib.orc_surface_interaction.argtypes = [vp, C.c_uint32, f32p, f32p]
         lib.orc_bsdf_eval_pdf_sample.argtypes = [vp, C.c_uint32, C.c_uint32, f32p, f32p]
         lib.orc_camera_rays.argtypes = [vp, C.c_uint32, f32p, f32p]
+        lib.orc_env_query.argtypes = [vp, C.c_uint32, f32p, f32p]
         lib.orc_rfilter_eval.argtypes = [vp, C.c_float]; lib.orc_rfilter_eval.restype = C.c_float
         lib.orc_tea32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
         lib.orc_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, f32p]
@@ -154,6 +155,14 @@ class OracleScene:
         q = np.ascontiguousarray(q, np.float32).reshape(-1, 11)
         out = np.zeros((q.shape[0], 14), np.float32)
         rc = self.lib.orc_bsdf_eval_pdf_sample(self.h, bsdf, q.shape[0], _fp(q), _fp(out))
+        assert rc == 0
+        return out
+
+    def env_query(self, q):
+        """q: (n, 8) = ref point, sample, direction -> (n, 20), see orc_env_query."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 8)
+        out = np.zeros((q.shape[0], 20), np.float32)
+        rc = self.lib.orc_env_query(self.h, q.shape[0], _fp(q), _fp(out))
         assert rc == 0
         return out
 

@@ -86,3 +86,35 @@ def multi_emitter_cbox(res=32, rfilter="box", spp=16, max_depth=6):
                        "bsdf": {"type": "ref", "id": "white"},
                        "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [6.0, 2.0, 9.0]}}}
     return d
+
+
+def env_scene(kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide=False, integrator="path", img=None):
+    """Floor + principled cube + mirror cube under an environment emitter (same scene as
+    gen_golden.py:env_scene; the lat-long image comes from the fixture tests/golden/env.npz)."""
+    import mitsuba3_b200 as mb
+    T = mb.Transform4f
+    if img is None:
+        img = golden("env.npz")["image"]
+    d = {"type": "scene",
+         "integrator": {"type": integrator, "max_depth": max_depth, "hide_emitters": hide},
+         "sensor": {"type": "perspective", "fov": 45, "near_clip": 0.01, "far_clip": 100,
+                    "to_world": T().look_at(origin=[2.5, 1.6, 3.2], target=[0, 0.3, 0], up=[0, 1, 0]),
+                    "film": {"type": "hdrfilm", "width": res, "height": res, "rfilter": {"type": "box"}, "pixel_format": "rgb"},
+                    "sampler": {"type": "independent", "sample_count": spp}},
+         "grey": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}},
+         "pr": {"type": "principled", "base_color": {"type": "rgb", "value": [0.8, 0.3, 0.2]}, "roughness": 0.35, "metallic": 0.6,
+                "specular": 0.5, "clearcoat": 0.3, "clearcoat_gloss": 0.7},
+         "mirror": {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}},
+         "floor": {"type": "rectangle", "to_world": T().rotate([1, 0, 0], -90).scale(3.0), "bsdf": {"type": "ref", "id": "grey"}},
+         "cube-a": {"type": "cube", "to_world": T().translate([-0.6, 0.4, 0.1]).rotate([0, 1, 0], 25).scale(0.4), "bsdf": {"type": "ref", "id": "pr"}},
+         "cube-b": {"type": "cube", "to_world": T().translate([0.7, 0.3, -0.4]).rotate([0, 1, 0], -35).scale(0.3), "bsdf": {"type": "ref", "id": "mirror"}}}
+    if area_light:
+        d["lamp"] = {"type": "rectangle", "to_world": T().translate([0.0, 1.8, 0.0]).rotate([1, 0, 0], 90).scale(0.3),
+                     "bsdf": {"type": "ref", "id": "grey"},
+                     "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [10.0, 9.0, 8.0]}}}
+    if kind == "envmap":
+        d["sky"] = {"type": "envmap", "bitmap": img, "scale": 1.5,
+                    "to_world": T().rotate([0, 1, 0], 40).rotate([1, 0, 0], 10)}
+    else:
+        d["sky"] = {"type": "constant", "radiance": {"type": "rgb", "value": [0.9, 1.1, 1.4]}}
+    return d

@@ -17,6 +17,7 @@ What is recorded (all from mitsuba scalar_rgb, reference v3.9.1):
   bsdf_tables.npz  BSDF eval/pdf/sample tables (diffuse, conductor, dielectric, principled)
   cbox_renders.npz scalar_rgb renders (single 32x32 / 64x64 block; box + gaussian), several seeds
   materials_renders.npz  same for a Cornell box with conductor / dielectric / principled boxes
+  env.npz          envmap / constant emitter tables (sample_direction, eval, pdf_direction) and renders
 """
 import os
 import sys
@@ -304,8 +305,102 @@ def gen_multi_emitter():
     save("multi_emitter_renders.npz", **out)
 
 
+# --------------------------------------------------------------------------- environment emitters
+def env_image(w=16, h=8):
+    """Small synthetic lat-long sky: gradient + a bright 'sun' blob + a dim ground (float32, linear RGB)."""
+    y, x = np.meshgrid((np.arange(h, dtype=np.float32) + 0.5) / h, (np.arange(w, dtype=np.float32) + 0.5) / w, indexing="ij")
+    sky = np.stack([0.3 + 0.5 * (1 - y), 0.4 + 0.5 * (1 - y), 0.6 + 0.6 * (1 - y)], -1)
+    ground = np.stack([0.25 * np.ones_like(y), 0.2 * np.ones_like(y), 0.15 * np.ones_like(y)], -1)
+    img = np.where((y < 0.55)[..., None], sky, ground)
+    sun = 40.0 * np.exp(-(((x - 0.3) / 0.07) ** 2 + ((y - 0.3) / 0.1) ** 2))
+    img = img + sun[..., None] * np.array([1.0, 0.9, 0.7], np.float32)
+    return np.ascontiguousarray(img, np.float32)
+
+
+def env_scene(T, img, bitmap, kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide=False, integrator="path"):
+    """Floor + principled cube + mirror cube under an environment emitter (+ optionally an area light
+    listed BEFORE the environment: emitter order = child order, scene.cpp:45-61)."""
+    d = {"type": "scene",
+         "integrator": {"type": integrator, "max_depth": max_depth, "hide_emitters": hide},
+         "sensor": {"type": "perspective", "fov": 45, "near_clip": 0.01, "far_clip": 100,
+                    "to_world": T().look_at(origin=[2.5, 1.6, 3.2], target=[0, 0.3, 0], up=[0, 1, 0]),
+                    "film": {"type": "hdrfilm", "width": res, "height": res, "rfilter": {"type": "box"}, "pixel_format": "rgb"},
+                    "sampler": {"type": "independent", "sample_count": spp}},
+         "grey": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}},
+         "pr": {"type": "principled", "base_color": {"type": "rgb", "value": [0.8, 0.3, 0.2]}, "roughness": 0.35, "metallic": 0.6,
+                "specular": 0.5, "clearcoat": 0.3, "clearcoat_gloss": 0.7},
+         "mirror": {"type": "conductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}},
+         "floor": {"type": "rectangle", "to_world": T().rotate([1, 0, 0], -90).scale(3.0), "bsdf": {"type": "ref", "id": "grey"}},
+         "cube-a": {"type": "cube", "to_world": T().translate([-0.6, 0.4, 0.1]).rotate([0, 1, 0], 25).scale(0.4), "bsdf": {"type": "ref", "id": "pr"}},
+         "cube-b": {"type": "cube", "to_world": T().translate([0.7, 0.3, -0.4]).rotate([0, 1, 0], -35).scale(0.3), "bsdf": {"type": "ref", "id": "mirror"}}}
+    if area_light:
+        d["lamp"] = {"type": "rectangle", "to_world": T().translate([0.0, 1.8, 0.0]).rotate([1, 0, 0], 90).scale(0.3),
+                     "bsdf": {"type": "ref", "id": "grey"},
+                     "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [10.0, 9.0, 8.0]}}}
+    if kind == "envmap":
+        d["sky"] = {"type": "envmap", "bitmap": bitmap(img), "scale": 1.5,
+                    "to_world": T().rotate([0, 1, 0], 40).rotate([1, 0, 0], 10)}
+    else:
+        d["sky"] = {"type": "constant", "radiance": {"type": "rgb", "value": [0.9, 1.1, 1.4]}}
+    return d
+
+
+def gen_env():
+    img = env_image()
+    T = mi.ScalarTransform4f
+    out = {"image": img}
+    for kind in ("envmap", "constant"):
+        scene = mi.load_dict(env_scene(T, img, mi.Bitmap, kind=kind), optimize=False)
+        em = [e for e in scene.emitters() if e.is_environment()][0]
+        n = 192
+        u = rng.random((n, 2)).astype(np.float32)
+        u[0] = [0.0, 0.0]; u[1] = [1.0, 1.0]; u[2] = [0.5, 0.0]
+        pts = (rng.random((n, 3)).astype(np.float32) - 0.5) * np.array([4, 2, 4], np.float32)
+        pts[3] = [40.0, 10.0, -30.0]                      # outside the bounding sphere
+        rec = np.zeros((n, 16), np.float32)
+        for i in range(n):
+            it = mi.Interaction3f()
+            it.p = mi.Point3f(*pts[i].tolist()); it.t = 1.0
+            ds, w = em.sample_direction(it, mi.Point2f(*u[i].tolist()))
+            si = mi.SurfaceInteraction3f()
+            si.wi = -ds.d
+            ev = em.eval(si)
+            pdf = em.pdf_direction(it, ds)
+            rec[i] = [ds.d[0], ds.d[1], ds.d[2], ds.pdf, ds.dist, ds.uv[0], ds.uv[1], w[0], w[1], w[2], ev[0], ev[1], ev[2], pdf, 0, 0]
+        # eval / pdf on arbitrary directions (not produced by the warp)
+        dirs = rng.normal(size=(n, 3)).astype(np.float32)
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        dirs[0] = [0, 1, 0]; dirs[1] = [0, -1, 0]; dirs[2] = [0, 0, 1]; dirs[3] = [0, 0, -1]; dirs[4] = [1, 0, 0]
+        rec2 = np.zeros((n, 4), np.float32)
+        for i in range(n):
+            si = mi.SurfaceInteraction3f(); si.wi = mi.Vector3f(*(-dirs[i]).tolist())
+            ds = mi.DirectionSample3f(); ds.d = mi.Vector3f(*dirs[i].tolist())
+            ev = em.eval(si)
+            rec2[i] = [ev[0], ev[1], ev[2], em.pdf_direction(mi.Interaction3f(), ds)]
+        out[f"{kind}_u"] = u; out[f"{kind}_p"] = pts; out[f"{kind}_sample"] = rec
+        out[f"{kind}_dirs"] = dirs; out[f"{kind}_eval"] = rec2
+    for (key, kw, spp, seed) in [("env_32_spp16_d6_seed0", dict(), 16, 0),
+                                 ("env_32_spp8_d3_seed1_hide", dict(max_depth=3, hide=True), 8, 1),
+                                 ("env_area_32_spp16_d6_seed2", dict(area_light=True), 16, 2),
+                                 ("const_32_spp16_d6_seed0", dict(kind="constant"), 16, 0),
+                                 ("const_area_32_spp8_d4_seed3", dict(kind="constant", area_light=True, max_depth=4), 8, 3)]:
+        d = env_scene(T, img, mi.Bitmap, spp=spp, **kw)
+        d["sensor"]["film"]["rfilter"] = {"type": "box"}
+        d["sensor"]["sampler"]["sample_count"] = spp
+        out[key] = render(block_one(d, 32), seed, spp)
+    d = env_scene(T, img, mi.Bitmap, res=64, spp=1024, area_light=True)
+    out["env_area_64_ref1024"] = render(d, 0, 1024)
+    save("env.npz", **out)
+
+
+def block_one(d, res):
+    """Single-block render (so that the per-pixel sampler streams follow integrator.cpp:209-222 for one block)."""
+    d["integrator"]["block_size"] = res
+    return d
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi"]
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env"]
     if "rng" in what:
         gen_rng()
     scene = None
@@ -321,3 +416,5 @@ if __name__ == "__main__":
         gen_material_renders()
     if "multi" in what:
         gen_multi_emitter()
+    if "env" in what:
+        gen_env()
