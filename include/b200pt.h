@@ -299,6 +299,17 @@ B200PT_API b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *scene, uint32
                                           uint32_t n, const float *in_host,
                                           float *out_host);
 
+/* Emitter::sample_direction / eval / pdf_direction of the scene's environment emitter
+ * (envmap.cpp:276-396, constant.cpp:95-152; Python: src/render/python/emitter_v.cpp),
+ * WITHOUT the scene's emitter-selection pmf. in_host = n*8 floats:
+ *   [0..2] reference point it.p, [3..4] sample, [5..7] a query direction d_q (unit, world)
+ * out_host = n*20 floats:
+ *   [0..2] ds.d, [3] ds.pdf, [4] ds.dist, [5..6] ds.uv, [7..9] weight (radiance / pdf),
+ *   [10..12] eval(-wi = ds.d), [13] pdf_direction(ds.d),
+ *   [14..16] eval(-wi = d_q), [17] pdf_direction(d_q), [18..19] unused */
+B200PT_API b200pt_status b200pt_env_query(b200pt_scene *scene, uint32_t n, const float *in_host,
+                               float *out_host);
+
 /* ---- measurement ------------------------------------------------------ */
 B200PT_API b200pt_status b200pt_get_stats(b200pt_scene *scene, b200pt_stats *out);
 /* sizeof() of the ABI structs as compiled: 0 texture, 1 bsdf, 2 shape, 3 emitter,

@@ -14,6 +14,7 @@
 
 #include "../../include/b200pt.h"
 #include "bvh.h"
+#include "env_host.h"
 #include "kernels.cuh"
 
 using namespace pt;
@@ -178,13 +179,39 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     }
     d.n_bsdfs = desc->n_bsdfs;
     std::vector<DevEmitter> he(desc->n_emitters);
+    DevEnv henv; memset(&henv, 0, sizeof(henv)); henv.type = -1; henv.emitter_index = -1; henv.radiance_tex = -1;
+    d.env = nullptr; d.env_type = -1; d.env_emitter = -1; d.env_radiance_tex = -1;
+    int env_index = -1;
     for (uint32_t i = 0; i < desc->n_emitters; ++i) {
         const b200pt_emitter &e = desc->emitters[i];
-        if (e.shape < 0 || e.shape >= (int32_t) desc->n_shapes || e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures)
-            S_FAIL(B200PT_ERR_INVALID, "emitter references a missing shape/texture");
-        if (desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST) S_FAIL(B200PT_ERR_UNSUPPORTED, "textured area lights are outside the hot-path scope");
         if (e.sampling_weight != 1.f) S_FAIL(B200PT_ERR_UNSUPPORTED, "non-uniform emitter sampling weights (Scene::m_emitter_distr, scene.cpp:259-262) are outside the hot-path scope");
-        he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].pad = 0.f;
+        he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].type = e.type;
+        if (e.type == B200PT_EMITTER_AREA) {
+            if (e.shape < 0 || e.shape >= (int32_t) desc->n_shapes || e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures)
+                S_FAIL(B200PT_ERR_INVALID, "emitter references a missing shape/texture");
+            if (desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST) S_FAIL(B200PT_ERR_UNSUPPORTED, "textured area lights are outside the hot-path scope");
+            continue;
+        }
+        if (e.type != B200PT_EMITTER_CONSTANT && e.type != B200PT_EMITTER_ENVMAP) S_FAIL(B200PT_ERR_UNSUPPORTED, "emitter type outside the hot-path scope");
+        if (env_index >= 0) S_FAIL(B200PT_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:63-65
+        env_index = (int) i;
+        he[i].shape = -1;
+        henv.type = e.type; d.env_type = e.type; d.env_emitter = (int32_t) i; d.env_radiance_tex = e.radiance_tex; henv.emitter_index = (int32_t) i; henv.radiance_tex = e.radiance_tex; henv.scale = e.env_scale;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { henv.m[r * 3 + c] = e.to_world[r * 4 + c]; henv.mi[r * 3 + c] = e.to_world_inv[r * 4 + c]; }
+        if (e.type == B200PT_EMITTER_CONSTANT) {
+            if (e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures || desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST)
+                S_FAIL(B200PT_ERR_INVALID, "constant emitter: expected a non-spatially varying radiance");                // constant.cpp:64
+        } else {
+            EnvHost eh;
+            if (!build_envmap(e, eh)) S_FAIL(B200PT_ERR_INVALID, "envmap: need float32 RGB data of at least 2 x 3 texels");
+            if (eh.lvl_width.size() > (size_t) ENV_MAX_LEVELS) S_FAIL(B200PT_ERR_UNSUPPORTED, "envmap resolution too large");
+            float *dt = nullptr, *dw = nullptr;
+            S_TRY(dev_upload(s, eh.tex.data(), eh.tex.size(), &dt)); S_TRY(dev_upload(s, eh.warp.data(), eh.warp.size(), &dw));
+            henv.tex = (const float4 *) dt; henv.warp = dw; henv.W = e.env_width; henv.H = e.env_height;
+            henv.n_levels = (uint32_t) eh.lvl_width.size();
+            for (size_t l = 0; l < eh.lvl_width.size(); ++l) { henv.lvl_width[l] = eh.lvl_width[l]; henv.lvl_offset[l] = eh.lvl_offset[l]; }
+            for (int k = 0; k < 2; ++k) { henv.patch_size[k] = eh.patch_size[k]; henv.inv_patch_size[k] = eh.inv_patch_size[k]; henv.max_patch_index[k] = eh.max_patch_index[k]; }
+        }
     }
     d.n_emitters = desc->n_emitters;
 
@@ -231,6 +258,10 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
             o.area_cdf = dc; o.area_pmf = dp; o.area_sum = cdf.empty() ? 0.f : cdf.back(); o.area_norm = 1.0f / o.area_sum;
         }
         vo += sh.n_vertices; po += sh.n_faces;
+    }
+    if (env_index >= 0) {
+        scene_bounding_sphere(verts.data(), n_verts, henv.center, henv.radius);
+        DevEnv *de = nullptr; S_TRY(dev_upload(s, &henv, 1, &de)); d.env = de;
     }
     { float *p; S_TRY(dev_upload(s, verts.data(), verts.size(), &p)); d.vertices = (const float4 *) p; }
     { uint32_t *p; S_TRY(dev_upload(s, pv.data(), pv.size(), &p)); d.prim_verts = (const uint4 *) p; }
@@ -341,6 +372,7 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
     for (int t = 0; t < N_BSDF_TYPES; ++t) {
         if (s->type_present[t]) CU_TRY(A(slack * 4, (void **) &w.q.slots[t])); else w.q.slots[t] = nullptr;
     }
+    if (s->dev.env_type >= 0) CU_TRY(A(slack * 4, (void **) &w.q.slots[Q_ENV])); else w.q.slots[Q_ENV] = nullptr;
     w.n_counts = (size_t) (MAX_BOUNCE_SLOTS + 2) * 8;
     CU_TRY(A(w.n_counts * 4, (void **) &w.counts));
     w.q.counts = w.counts;
@@ -407,6 +439,10 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     uint32_t max_b = std::min<uint32_t>(cfg.max_depth, MAX_BOUNCE_SLOTS);
     for (uint32_t b = 0; b < max_b; ++b) {
         uint32_t *cnt = w.counts + (size_t) b * 8;
+        if (d.env_type >= 0) {     // rays of this bounce that left the scene: environment emitter, then the path ends
+            launch_shade_env(d, cfg, w.buf[cur], w.q.slots[Q_ENV], cnt + QCOUNT_ENV, w.lane_result, g_all, st);
+            s->stats.kernel_launches++;
+        }
         for (int t = 0; t < N_BSDF_TYPES; ++t) {
             if (!s->type_present[t]) continue;
             launch_shade(t, d, cfg, w.buf[cur], w.hit, w.q.slots[t], cnt + t, w.buf[cur ^ 1], cnt + 4, w.lane_result, s->stats_dev, Ls, st);
@@ -419,7 +455,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
             uint32_t alive[8];
             CU_TRY(cudaMemcpyAsync(alive, w.counts + (size_t) (b + 1) * 8, sizeof(alive), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
-            if (alive[0] + alive[1] + alive[2] + alive[3] == 0) break;
+            if (alive[0] + alive[1] + alive[2] + alive[3] + alive[QCOUNT_ENV] == 0) break;
         }
     }
     CU_TRY(cudaGetLastError());
@@ -658,6 +694,22 @@ b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *s, uint32_t bsdf, uint32
     DevBsdf hb; CU_TRY(cudaMemcpy(&hb, s->dev.bsdfs + bsdf, sizeof(hb), cudaMemcpyDeviceToHost));
     launch_bsdf_eval(s->dev, bsdf, hb.type, n, di, dout, s->stream);
     CU_TRY(cudaMemcpyAsync(out_host, dout, (size_t) n * 56, cudaMemcpyDeviceToHost, s->stream));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(di); cudaFree(dout);
+    CU_TRY(e);
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_env_query(b200pt_scene *s, uint32_t n, const float *in_host, float *out_host) {
+    if (!s || (n && (!in_host || !out_host))) return fail(B200PT_ERR_INVALID, "null argument");
+    if (s->dev.env_type < 0) return fail(B200PT_ERR_INVALID, "the scene has no environment emitter");
+    if (n == 0) return B200PT_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    float *di, *dout;
+    CU_TRY(cudaMalloc(&di, (size_t) n * 32)); CU_TRY(cudaMalloc(&dout, (size_t) n * 80));
+    CU_TRY(cudaMemcpyAsync(di, in_host, (size_t) n * 32, cudaMemcpyHostToDevice, s->stream));
+    launch_env_query(s->dev, n, di, dout, s->stream);
+    CU_TRY(cudaMemcpyAsync(out_host, dout, (size_t) n * 80, cudaMemcpyDeviceToHost, s->stream));
     cudaError_t e = cudaStreamSynchronize(s->stream);
     cudaFree(di); cudaFree(dout);
     CU_TRY(e);

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                     hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
                     const DevShape &sh = sc.shapes[sc.prim_verts[h.prim].w];
                     mytype = sc.bsdfs[sh.bsdf].type;
-                } else finished = true;   // path.cpp:225: si invalid, no environment emitter
+                } else if (sc.env_type >= 0) mytype = Q_ENV;   // the ray left the scene: environment emitter (k_shade_env)
+                else finished = true;      // path.cpp:225: si invalid, no environment emitter
             }
             if (finished) {
                 if (!res_loaded) res = cur.result[i];
@@ -290,11 +291,11 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
         __syncwarp();
         // bucket pass: bin the slot by material id (one atomic per warp and material)
 #pragma unroll
-        for (int t = 0; t < N_BSDF_TYPES; ++t) {
+        for (int t = 0; t < N_QUEUES; ++t) {
             uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
             if (m) {
                 uint32_t leader = __ffs(m) - 1, off = 0;
-                if (lane_id == leader) off = atomicAdd(&qcounts[t], __popc(m));
+                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
                 off = __shfl_sync(0xffffffffu, off, leader);
                 if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = i;
             }
@@ -457,18 +458,19 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                     if (found) {
                         hit_out[slot] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
                         mytype = sc.bsdfs[sc.shapes[sc.prim_verts[hit.prim].w].bsdf].type;
-                    } else lane_result[cur.rng[slot].w] = cur.result[slot];
+                    } else if (sc.env_type >= 0) mytype = Q_ENV;     // the ray left the scene: environment emitter (k_shade_env)
+                    else lane_result[cur.rng[slot].w] = cur.result[slot];
                     kind = 0;
                 }
             }
         }
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < N_BSDF_TYPES; ++t) {
+        for (int t = 0; t < N_QUEUES; ++t) {
             uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
             if (m) {
                 uint32_t leader = __ffs(m) - 1, off = 0;
-                if (lane_id == leader) off = atomicAdd(&qcounts[t], __popc(m));
+                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
                 off = __shfl_sync(0xffffffffu, off, leader);
                 if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = slot;
             }
@@ -671,8 +673,9 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                     float3 g_dir = active_em ? dL * ((beta_vertex * mis_em) * em_weight) : V(0.f, 0.f, 0.f);
                     float3 g_ind = active ? dL * L : V(0.f, 0.f, 0.f);
                     gv1 = bsdf_backward<TYPE>(sc, bsdf, si.uv, si.wi, wo, br.bs.wo, g_dir, g_ind, gt1); guv1 = si.uv;
-                    if (active_em) {
-                        // emitter radiance inside em_weight = radiance / pdf (area.cpp:161)
+                    if (active_em && sc.emitters[ds.emitter].type != B200PT_EMITTER_ENVMAP) {
+                        // emitter radiance inside em_weight = radiance / pdf (area.cpp:161); the envmap
+                        // `data` parameter is not differentiated on this path
                         int32_t rt = sc.emitters[ds.emitter].radiance_tex;
                         float3 rad = tex_eval3(sc, rt, ds.uv);
                         gt2 = rt; guv2 = ds.uv;
@@ -722,6 +725,65 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
     for (int o = 16; o; o >>= 1) { n_bounces += __shfl_xor_sync(0xffffffffu, n_bounces, o); n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); }
     if (lane_id == 0 && n_bounces) atomicAdd(&stats[ST_BOUNCES], (unsigned long long) n_bounces);
     if (lane_id == 0 && n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+}
+
+// ---------------------------------------------------------------------------
+// k_shade_env -- the rays of this bounce that left the scene: direct emission of the
+// environment emitter with the MIS weight of the previous BSDF sample (path.cpp:115,
+// 206-231,343; prb.py:148-163), then the path ends. One thread per queued slot.
+// ---------------------------------------------------------------------------
+template <bool ADJOINT>
+__global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ DevScene sc, RenderCfg cfg, PathBuf cur, const uint32_t *__restrict__ queue,
+                                                     const uint32_t *__restrict__ qcount, float4 *__restrict__ lane_result) {
+    const uint32_t n = *qcount;
+    const bool prb = cfg.prb != 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        uint32_t i = base + (threadIdx.x & 31u);
+        int32_t gt = -1; float3 gv = V(0.f, 0.f, 0.f);
+        if (i < n) {
+            uint32_t slot = queue[i];
+            float4 rd = cur.ray_d[slot], th = cur.thr[slot], pv = cur.prev[slot], rs4 = cur.result[slot];
+            uint32_t flags = __float_as_uint(pv.w), depth = flags & PF_DEPTH_MASK;
+            bool prev_delta = (flags & PF_PREV_DELTA) != 0;
+            float3 d = V(rd.x, rd.y, rd.z), throughput = V(th.x, th.y, th.z), result = V(rs4.x, rs4.y, rs4.z);
+            float prev_bsdf_pdf = rd.w;
+            float em_pdf = prev_delta ? 0.f : env_pdf_direction(sc.env, d) * fdiv(1.f, (float) sc.n_emitters);   // scene.cpp:378-389
+            float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
+            bool em_active = prb ? !(cfg.hide_emitters && depth == 0) : prev_bsdf_pdf > 0.f;
+            float3 crad = sc.env_type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, sc.env_radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
+            float3 rad = em_active ? env_eval(sc.env, crad, d) : V(0.f, 0.f, 0.f);
+            if (prb) result = result + (throughput * mis_bsdf) * rad;
+            else result = vfma(throughput, rad * mis_bsdf, result);
+            // path.cpp:115,343: a primary ray that sees only the hidden environment is not a valid sample
+            if (!prb && cfg.hide_emitters && depth == 0) result = V(0.f, 0.f, 0.f);
+            if (!ADJOINT) lane_result[cur.rng[slot].w] = make_float4(result.x, result.y, result.z, 0.f);
+            else if (em_active && sc.env_type == B200PT_EMITTER_CONSTANT) {
+                float4 dl = cur.adj_dL[slot];
+                gt = sc.env_radiance_tex; gv = V(dl.x, dl.y, dl.z) * (throughput * mis_bsdf);
+            }
+        }
+        if (ADJOINT) { __syncwarp(); warp_scatter3(sc, gt, make_float2(0.f, 0.f), gv); }
+    }
+}
+
+// Emitter::sample_direction / eval / pdf_direction tables of the environment emitter
+// (b200pt_env_query): in n x 8 = ref point, sample, direction; out n x 20.
+__global__ void k_env_query(const __grid_constant__ DevScene sc, uint32_t n, const float *__restrict__ in, float *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *q = in + 8 * (size_t) i; float *o = out + 20 * (size_t) i;
+    DirectionSample ds; ds.pdf = 0.f; ds.emitter = -1; ds.uv = make_float2(0.f, 0.f);
+    float3 crad = sc.env_type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, sc.env_radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
+    float3 w = env_sample_direction(sc.env, crad, V(q[0], q[1], q[2]), q[3], q[4], ds);
+    o[0] = ds.d.x; o[1] = ds.d.y; o[2] = ds.d.z; o[3] = ds.pdf; o[4] = ds.dist; o[5] = ds.uv.x; o[6] = ds.uv.y;
+    o[7] = w.x; o[8] = w.y; o[9] = w.z;
+    float3 e = env_eval(sc.env, crad, ds.d);
+    o[10] = e.x; o[11] = e.y; o[12] = e.z; o[13] = env_pdf_direction(sc.env, ds.d);
+    float3 d = V(q[5], q[6], q[7]);
+    e = env_eval(sc.env, crad, d);
+    o[14] = e.x; o[15] = e.y; o[16] = e.z; o[17] = env_pdf_direction(sc.env, d);
+    o[18] = 0.f; o[19] = 0.f;
 }
 
 // ---------------------------------------------------------------------------
@@ -945,6 +1007,16 @@ void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cu
         case B200PT_BSDF_DIELECTRIC: launch_shade_t<B200PT_BSDF_DIELECTRIC>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
         default: launch_shade_t<B200PT_BSDF_PRINCIPLED>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, grid, st); break;
     }
+}
+
+void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
+                      float4 *lane_result, int grid, cudaStream_t st) {
+    if (cfg.adjoint) k_shade_env<true><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result);
+    else k_shade_env<false><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result);
+}
+
+void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st) {
+    k_env_query<<<(int) ((n + 127) / 128), 128, 0, st>>>(sc, n, in, out);
 }
 
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st) {

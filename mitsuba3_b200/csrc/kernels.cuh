@@ -31,9 +31,12 @@ struct PathBuf {
 #define PF_ALIVE        0x00040000u
 
 constexpr int N_BSDF_TYPES = 4;
+constexpr int N_QUEUES = N_BSDF_TYPES + 1;   // + the queue of the rays that left the scene (environment emitter)
+constexpr int Q_ENV = N_BSDF_TYPES;
+constexpr int QCOUNT_ENV = 6;                // index of the environment queue's size in a bounce's counter block
 
 struct Queues {
-    uint32_t *slots[N_BSDF_TYPES];  // material queues: slot ids of the current buffer
+    uint32_t *slots[N_QUEUES];      // material queues (+ environment queue): slot ids of the current buffer
     uint32_t *counts;               // [bounce][N_BSDF_TYPES] queue sizes, + in/out counters, see api.cu
 };
 
@@ -61,6 +64,9 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st);
 void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue,
                   const uint32_t *qcount, PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st);
+void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
+                      float4 *lane_result, int grid, cudaStream_t st);
+void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,
                           float4 *lane_dL, int grid, cudaStream_t st);

@@ -124,7 +124,25 @@ struct DevShape {
     float area_sum, area_norm; const float *area_cdf, *area_pmf; // B200PT_SAMPLING_MESH (core/distr_1d.h)
 };
 
-struct DevEmitter { int32_t shape, radiance_tex; float sampling_weight; float pad; };
+struct DevEmitter { int32_t shape, radiance_tex; float sampling_weight; int32_t type; };
+
+// The environment emitter of the scene (pt_env.cuh). `tex` holds the lat-long map with its
+// periodic halo columns, one float4 per texel; `warp` is the Hierarchical2D buffer
+// (level 0 row-major, levels >= 1 in 2x2 blocks, distr_2d.h:431-450).
+constexpr int ENV_MAX_LEVELS = 20;
+struct DevEnv {
+    int32_t type;                 // -1: none, else B200PT_EMITTER_CONSTANT / _ENVMAP
+    int32_t emitter_index, radiance_tex;
+    uint32_t W, H;                // real resolution
+    const float4 *tex;            // H x (W + 2)
+    const float *warp;
+    float scale;
+    float m[9], mi[9];            // linear part of to_world / its inverse, row-major
+    float center[3], radius;      // bounding sphere of the scene (envmap.cpp:260-274)
+    uint32_t n_levels, lvl_width[ENV_MAX_LEVELS], lvl_offset[ENV_MAX_LEVELS];
+    float patch_size[2], inv_patch_size[2];
+    uint32_t max_patch_index[2];
+};
 
 struct DevScene {
     // acceleration structure (bvh.h)
@@ -146,6 +164,9 @@ struct DevScene {
     uint32_t film_w, film_h, crop_w, crop_h, crop_x, crop_y;
     int32_t rfilter; float gauss_radius, gauss_alpha, gauss_bias; float gauss_coeff[10];
     uint32_t base_seed;
+    // environment emitter: the descriptor lives in global memory (the out-of-line functions of
+    // pt_env.cuh take the pointer, so kernels never spill a copy of the scene for them)
+    const DevEnv *env; int32_t env_type, env_emitter, env_radiance_tex;   // env_type -1: none
 };
 
 struct Ray { float3 o, d; float maxt; };
@@ -511,6 +532,10 @@ PT_DEV void shape_sample_position(const DevScene &sc, const DevShape &sh, float 
     else n = vnormalize(vcross(e0, e1));
 }
 
+} // namespace pt
+#include "pt_env.cuh"
+namespace pt {
+
 // Scene::sample_emitter_direction (scene.cpp:316-366) -> AreaLight::sample_direction
 // (area.cpp:118-168) -> Shape::sample_direction (shape.cpp:94-111); visibility is
 // resolved by the trace kernel. Returns em_weight.
@@ -524,6 +549,13 @@ PT_DEV float3 sample_emitter_direction(const DevScene &sc, float3 ref_p, float s
     float emitter_weight = n < 2 ? 1.f : nf;
     float pmf = fdiv(1.f, nf);
     const DevEmitter &em = sc.emitters[index];
+    if (em.type != B200PT_EMITTER_AREA) {
+        float3 crad = em.type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, em.radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
+        float3 spec_env = env_sample_direction(sc.env, crad, ref_p, sx_re, sy, ds);
+        ds.emitter = (int32_t) index;
+        ds.pdf *= pmf;
+        return spec_env * emitter_weight;
+    }
     const DevShape &sh = sc.shapes[em.shape];
     shape_sample_position(sc, sh, sx_re, sy, ds.p, ds.n, ds.pdf, ds.uv);
     ds.d = ds.p - ref_p;

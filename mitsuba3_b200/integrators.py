@@ -96,6 +96,14 @@ class DeviceScene:
         abi.check(self.lib.b200pt_bsdf_eval_pdf_sample(self.h, bsdf, q.shape[0], q.ctypes.data_as(f), out.ctypes.data_as(f)), self.lib)
         return out
 
+    def env_query(self, q):
+        """Environment emitter tables (``b200pt_env_query``): q (n, 8) = ref point, sample, direction."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 8)
+        out = np.zeros((q.shape[0], 20), np.float32)
+        f = C.POINTER(C.c_float)
+        abi.check(self.lib.b200pt_env_query(self.h, q.shape[0], q.ctypes.data_as(f), out.ctypes.data_as(f)), self.lib)
+        return out
+
 
 def device_scene(scene: Scene, device: int = 0) -> DeviceScene:
     """Cached device scene of a host scene (created on first use)."""
