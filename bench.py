@@ -33,6 +33,9 @@ WORKLOADS = {
     "cornell_box_256x256_64spp_8bounce": (256, 256, 64, 8, "gaussian"),
     # synthetic stand-in for the 200k-triangle config (BASELINE.json configs[4], asset not in the reference tree)
     "heightfield205k_1024x1024_64spp_8bounce": (1024, 1024, 64, 8, "gaussian"),
+    # synthetic stand-in for configs[3] (matpreview: principled BSDF + envmap; asset not in the reference tree):
+    # 261k-triangle principled sphere + metallic sphere on a checkerboard plane, lit only by a 1024x512 HDR envmap
+    "matpreview_like_1024x1024_128spp_8bounce": (1024, 1024, 128, 8, "gaussian"),
 }
 DEFAULT_WORKLOAD = "cornell_box_512x512_256spp_8bounce"
 METRIC = "Msamples/sec (fwd path, Cornell box)"
@@ -41,7 +44,12 @@ METRIC = "Msamples/sec (fwd path, Cornell box)"
 def build_scene(workload):
     import mitsuba3_b200 as mb
     w, h, spp, md, rf = WORKLOADS[workload]
-    d = mb.cornell_box_heightfield(320) if workload.startswith("heightfield") else mb.cornell_box()
+    if workload.startswith("heightfield"):
+        d = mb.cornell_box_heightfield(320)
+    elif workload.startswith("matpreview"):
+        d = mb.matpreview_like()
+    else:
+        d = mb.cornell_box()
     d["sensor"]["film"].update(width=w, height=h, rfilter={"type": rf})
     d["sensor"]["sampler"]["sample_count"] = spp
     d["integrator"] = {"type": "path", "max_depth": md}
@@ -106,7 +114,7 @@ def cpu_baseline_reference(workload, spp_sample, reps=1):
     runtime travels with the repo (oracle/ref_snapshot.sh); None otherwise."""
     from oracle.ref_env import reference_env
     env = reference_env(ROOT)
-    if env is None or workload.startswith("heightfield"):
+    if env is None or not workload.startswith("cornell_box"):
         return None
     w, h, spp, md, rf = WORKLOADS[workload]
     try:
@@ -309,7 +317,7 @@ def main():
         step_bytes = (144.0 + 304.0 * b_bar) * (samples_per_step // n_gpus)
         step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
         out = {
-            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.workload.startswith("cornell") else "Msamples/sec (fwd path, %s)" % args.workload, "value": value, "unit": "Msamples/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "spp_total": spp, "global_samples_per_step": samples_per_step,

@@ -440,7 +440,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     for (uint32_t b = 0; b < max_b; ++b) {
         uint32_t *cnt = w.counts + (size_t) b * 8;
         if (d.env_type >= 0) {     // rays of this bounce that left the scene: environment emitter, then the path ends
-            launch_shade_env(d, cfg, w.buf[cur], w.q.slots[Q_ENV], cnt + QCOUNT_ENV, w.lane_result, g_all, st);
+            launch_shade_env(d, cfg, w.buf[cur], w.q.slots[Q_ENV], cnt + QCOUNT_ENV, w.lane_result, s->stats_dev, g_all, st);
             s->stats.kernel_launches++;
         }
         for (int t = 0; t < N_BSDF_TYPES; ++t) {

@@ -734,10 +734,11 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
 // ---------------------------------------------------------------------------
 template <bool ADJOINT>
 __global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ DevScene sc, RenderCfg cfg, PathBuf cur, const uint32_t *__restrict__ queue,
-                                                     const uint32_t *__restrict__ qcount, float4 *__restrict__ lane_result) {
+                                                     const uint32_t *__restrict__ qcount, float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats) {
     const uint32_t n = *qcount;
     const bool prb = cfg.prb != 0;
     const uint32_t stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats[ST_BOUNCES], (unsigned long long) n);   // loop iterations (path.cpp:193)
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         uint32_t i = base + (threadIdx.x & 31u);
         int32_t gt = -1; float3 gv = V(0.f, 0.f, 0.f);
@@ -1010,9 +1011,9 @@ void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cu
 }
 
 void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
-                      float4 *lane_result, int grid, cudaStream_t st) {
-    if (cfg.adjoint) k_shade_env<true><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result);
-    else k_shade_env<false><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result);
+                      float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st) {
+    if (cfg.adjoint) k_shade_env<true><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result, stats);
+    else k_shade_env<false><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result, stats);
 }
 
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st) {

@@ -65,7 +65,7 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
 void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue,
                   const uint32_t *qcount, PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st);
 void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
-                      float4 *lane_result, int grid, cudaStream_t st);
+                      float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,

@@ -145,9 +145,12 @@ class _Extractor:
                 rad = self._texture(ep, "", "radiance", f"{sid}.emitter.radiance", 3)
                 if rad < 0 or self.out.textures[rad].kind != abi.TEX_CONST:
                     raise NotImplementedError("only uniform area lights are on the hot path")
-                self.out.emitters.append(EmitterData(shape=len(self.out.shapes), radiance_tex=rad,
-                                                     sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0))
-                sh.emitter = len(self.out.emitters) - 1
+                # the emitter list follows Scene::emitters() (scene.cpp:45-61): its order decides which
+                # emitter a sample picks (scene.cpp:248-271)
+                sh.emitter = self._emitter_slot(s.emitter())
+                self.out.emitters[sh.emitter] = EmitterData(
+                    shape=len(self.out.shapes), radiance_tex=rad,
+                    sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
                 sp = mi.traverse(s)
                 if "to_world" in sp and verts.shape[0] == 4 and faces.shape[0] == 2:
                     # Rectangle: sampled by its parameterisation (rectangle.cpp:159-172)
@@ -182,10 +185,47 @@ class _Extractor:
             crop_offset=tuple(off), rfilter=rfilter, rfilter_stddev=stddev, base_seed=0,
             sample_count=int(se.sampler().sample_count()), x_fov=float(p["x_fov"]))
 
+    # ---- emitters ----------------------------------------------------------------------------
+    def _emitter_slot(self, em) -> int:
+        for k, x in enumerate(self._ems):
+            if x is em or x == em:
+                return k
+        raise RuntimeError("emitter of a shape is not in Scene::emitters()")
+
+    def environment(self):
+        """`constant` / `envmap` (constant.cpp, envmap.cpp) from their traversed parameters. The envmap
+        `data` tensor carries the two periodic halo columns (envmap.cpp:155-192); they are dropped
+        here, the library rebuilds them."""
+        mi = self.mi
+        for k, em in enumerate(self._ems):
+            if not em.is_environment():
+                continue
+            ep = mi.traverse(em)
+            eid = em.id() or f"emitter_{k}"
+            if "data" in ep:
+                data = _np(ep["data"]).reshape(tuple(int(v) for v in ep["data"].shape))
+                if data.shape[2] != 3:
+                    raise NotImplementedError("spectral environment maps are outside the hot-path scope")
+                tw = Transform4f(_np(ep["to_world"].matrix), _np(ep["to_world"].inverse_transpose))
+                self.out.emitters[k] = EmitterData(
+                    shape=-1, radiance_tex=-1, type=abi.EMITTER_ENVMAP, env_data=np.ascontiguousarray(data[:, 1:-1, :], f32),
+                    env_scale=float(_np(ep["scale"]).reshape(-1)[0]), env_mis_compensation=False,
+                    to_world=tw.matrix.copy(), to_world_inv=np.ascontiguousarray(tw.inverse_transpose.T, f32))
+            elif any(key.startswith("radiance") for key in ep.keys()):
+                rad = self._texture(ep, "", "radiance", f"{eid}.radiance", 3)
+                if rad < 0 or self.out.textures[rad].kind != abi.TEX_CONST:
+                    raise NotImplementedError("constant emitter: expected a uniform radiance")
+                self.out.emitters[k] = EmitterData(shape=-1, radiance_tex=rad, type=abi.EMITTER_CONSTANT)
+            else:
+                raise NotImplementedError(f"environment emitter {em.class_name()} is outside the hot-path scope")
+
     def run(self) -> Scene:
-        if self.scene_mi.environment() is not None:
-            raise NotImplementedError("environment emitters are a 'next' row (SURVEY.md 8(f))")
+        self._ems = list(self.scene_mi.emitters())
+        self.out.emitters = [None] * len(self._ems)
         self.shapes()
+        self.environment()
+        if any(e is None for e in self.out.emitters):
+            raise NotImplementedError("only area lights, `constant` and `envmap` emitters are on the hot path (SURVEY.md 8)")
         self.sensor()
         return self.out
 

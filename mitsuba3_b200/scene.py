@@ -677,3 +677,70 @@ def cornell_box_heightfield(n: int = 64, **kw) -> dict:
     del d["floor"]
     d["floor"] = hf
     return d
+
+
+# ---------------------------------------------------------------------------
+# Synthetic stand-in for BASELINE.json configs[3] ("matpreview scene: principled BSDF + envmap");
+# the real asset (resources/data/scenes/matpreview) is not in the reference tree.
+# ---------------------------------------------------------------------------
+def uv_sphere_mesh(n_theta: int = 128, n_phi: int = 256, radius: float = 1.0, center=(0.0, 0.0, 0.0)) -> dict:
+    """Latitude-longitude sphere with smooth normals and texture coordinates:
+    2 * n_phi * (n_theta - 1) triangles."""
+    th = (np.arange(n_theta + 1, dtype=np.float64) / n_theta) * np.pi
+    ph = (np.arange(n_phi + 1, dtype=np.float64) / n_phi) * 2 * np.pi
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    nrm = np.stack([np.sin(T) * np.cos(P), np.cos(T), np.sin(T) * np.sin(P)], -1).reshape(-1, 3)
+    pos = nrm * radius + np.asarray(center, np.float64)
+    uv = np.stack([P / (2 * np.pi), T / np.pi], -1).reshape(-1, 2)
+    idx = lambda i, j: i * (n_phi + 1) + j
+    faces = []
+    for i in range(n_theta):
+        j = np.arange(n_phi)
+        a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+        if i > 0:
+            faces.append(np.stack([a, d, c], -1))      # counter-clockwise seen from outside
+        if i < n_theta - 1:
+            faces.append(np.stack([a, c, b], -1))
+    return {"type": "mesh", "positions": pos.astype(f32), "normals": nrm.astype(f32), "texcoords": uv.astype(f32),
+            "faces": np.concatenate(faces, 0).astype(np.uint32)}
+
+
+def synthetic_sky(width: int = 1024, height: int = 512) -> np.ndarray:
+    """Procedural lat-long HDR sky (float32 RGB): horizon gradient, a bright sun, soft 'clouds', dark ground."""
+    y, x = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    up = np.clip(1 - 2 * y, 0, 1)
+    sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.4 * (1 - up), 0.6 + 0.35 * up], -1)
+    clouds = 0.5 + 0.5 * np.sin(18 * x + 3 * np.sin(9 * y)) * np.sin(14 * y + 2 * np.cos(11 * x))
+    sky = sky * (0.8 + 0.5 * (clouds * up)[..., None])
+    ground = np.array([0.12, 0.1, 0.08]) * (0.6 + 0.4 * clouds)[..., None]
+    img = np.where((y < 0.5)[..., None], sky, ground)
+    dx = np.minimum(np.abs(x - 0.62), 1 - np.abs(x - 0.62))
+    sun = 6000.0 * np.exp(-((dx / 0.006) ** 2 + ((y - 0.27) / 0.012) ** 2)) + 6.0 * np.exp(-((dx / 0.05) ** 2 + ((y - 0.27) / 0.08) ** 2))
+    img = img + sun[..., None] * np.array([1.0, 0.93, 0.8])
+    return np.ascontiguousarray(img, f32)
+
+
+def matpreview_like(n_theta: int = 256, n_phi: int = 512, env_res=(1024, 512)) -> dict:
+    """Material-preview style scene: a principled sphere (2 * n_phi * (n_theta - 1) triangles, smooth
+    normals) and a rough metallic sphere on a checkerboard ground plane, lit ONLY by an HDR
+    environment map -- the feature mix of BASELINE.json configs[3] (principled BSDF + envmap)."""
+    T = Transform4f
+    d = {"type": "scene",
+         "integrator": {"type": "path", "max_depth": 8},
+         "sensor": {"type": "perspective", "fov": 38, "near_clip": 0.01, "far_clip": 100,
+                    "to_world": T().look_at(origin=[3.2, 2.1, 3.9], target=[0.1, 0.75, 0], up=[0, 1, 0]),
+                    "film": {"type": "hdrfilm", "width": 1024, "height": 1024, "rfilter": {"type": "gaussian"}, "pixel_format": "rgb"},
+                    "sampler": {"type": "independent", "sample_count": 128}},
+         "ground-mat": {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.35, 0.35, 0.35]},
+                                                            "color1": {"type": "rgb", "value": [0.7, 0.7, 0.7]},
+                                                            "to_uv": np.diag([10.0, 10.0, 1.0]).astype(f32)}},
+         "paint": {"type": "principled", "base_color": {"type": "rgb", "value": [0.8, 0.15, 0.1]}, "roughness": 0.25, "metallic": 0.1,
+                   "specular": 0.6, "clearcoat": 0.8, "clearcoat_gloss": 0.9, "sheen": 0.2},
+         "brushed": {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.75, 0.4]}, "roughness": 0.4, "metallic": 1.0},
+         "ground": {"type": "rectangle", "to_world": T().rotate([1, 0, 0], -90).scale(6.0), "bsdf": {"type": "ref", "id": "ground-mat"}}}
+    s1 = uv_sphere_mesh(n_theta, n_phi, 1.0, (0.0, 1.0, 0.0)); s1["bsdf"] = {"type": "ref", "id": "paint"}
+    s2 = uv_sphere_mesh(max(8, n_theta // 4), max(16, n_phi // 4), 0.45, (1.7, 0.45, 0.9)); s2["bsdf"] = {"type": "ref", "id": "brushed"}
+    d["preview-object"] = s1
+    d["small-sphere"] = s2
+    d["sky"] = {"type": "envmap", "bitmap": synthetic_sky(*env_res), "scale": 1.0, "to_world": T().rotate([0, 1, 0], 25)}
+    return d

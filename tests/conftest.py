@@ -88,11 +88,14 @@ def multi_emitter_cbox(res=32, rfilter="box", spp=16, max_depth=6):
     return d
 
 
-def env_scene(kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide=False, integrator="path", img=None):
+def env_scene(kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide=False, integrator="path", img=None,
+              T=None, bitmap=lambda a: a):
     """Floor + principled cube + mirror cube under an environment emitter (same scene as
-    gen_golden.py:env_scene; the lat-long image comes from the fixture tests/golden/env.npz)."""
-    import mitsuba3_b200 as mb
-    T = mb.Transform4f
+    gen_golden.py:env_scene; the lat-long image comes from the fixture tests/golden/env.npz).
+    `T` / `bitmap`: transform class and image wrapper (mi.ScalarTransform4f / mi.Bitmap for a live Mitsuba)."""
+    if T is None:
+        import mitsuba3_b200 as mb
+        T = mb.Transform4f
     if img is None:
         img = golden("env.npz")["image"]
     d = {"type": "scene",
@@ -113,7 +116,7 @@ def env_scene(kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide
                      "bsdf": {"type": "ref", "id": "grey"},
                      "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [10.0, 9.0, 8.0]}}}
     if kind == "envmap":
-        d["sky"] = {"type": "envmap", "bitmap": img, "scale": 1.5,
+        d["sky"] = {"type": "envmap", "bitmap": bitmap(img), "scale": 1.5,
                     "to_world": T().rotate([0, 1, 0], 40).rotate([1, 0, 0], 10)}
     else:
         d["sky"] = {"type": "constant", "radiance": {"type": "rgb", "value": [0.9, 1.1, 1.4]}}
