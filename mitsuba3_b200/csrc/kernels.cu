@@ -17,6 +17,7 @@
 // BVH nodes/triangles of the top of the tree are staged into shared memory with a
 // bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) once per persistent CTA.
 #include "kernels.cuh"
+#include <mutex>
 
 namespace pt {
 
@@ -1055,7 +1056,17 @@ void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, c
     }
 }
 
-void set_trace_smem_attr(size_t bytes) {
+void set_trace_smem_attr(size_t bytes_wanted) {
+    // the attribute is per kernel function (process-wide): never lower it, an earlier scene of this
+    // process may need more dynamic shared memory than the one being created now
+    // (and per device: the attribute belongs to the current device's context)
+    static std::mutex mu;
+    static size_t current[64] = { 0 };
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0; cudaGetDevice(&dev); dev = dev < 0 ? 0 : dev % 64;
+    if (bytes_wanted <= current[dev]) return;
+    current[dev] = bytes_wanted;
+    size_t bytes = bytes_wanted;
     cudaFuncSetAttribute(k_trace_dyn<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

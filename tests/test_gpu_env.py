@@ -79,3 +79,14 @@ def test_constant_environment_radiance_gradient(oracle_mod):
         ref_g = o.grad(sc.parameters()[k])
         assert np.abs(ref_g).max() > 0
         assert np.abs(g[k] - ref_g).max() / np.abs(ref_g).max() < 5e-3, (k, g[k], ref_g)
+
+
+def test_scenes_with_different_shared_memory_needs_coexist(oracle_mod):
+    """The dynamic shared-memory attribute of the kernels is process-wide: creating a second scene
+    that stages less into shared memory must not break launches of the first one."""
+    from conftest import materials_cbox
+    a = mb.load_dict(materials_cbox(res=32, spp=8, max_depth=6))
+    ia = mb.render(a, spp=8, seed=0)
+    b = mb.load_dict(env_scene(res=32, spp=8))
+    mb.render(b, spp=8, seed=0)
+    assert np.array_equal(mb.render(a, spp=8, seed=0), ia)
