@@ -201,7 +201,8 @@ typedef struct b200pt_render_params {
     int32_t  hide_emitters;
     uint32_t shard_rank;    /* this process' rank in [0, shard_count)         */
     uint32_t shard_count;   /* 1 = whole frame                                */
-    uint32_t tile_size;     /* pixel-tile edge for sharding (default 32)      */
+    uint32_t tile_size;     /* pixel-tile edge for sharding (default 32); tile (tx, ty) belongs to
+                               rank (tx + ty * (shard_count / 2 + 1)) % shard_count            */
     uint32_t chunk_lanes;   /* wavefront lanes per pass, 0 = library default  */
     int32_t  prb;           /* 0 = `path` estimator, 1 = `prb` primal rules   */
 } b200pt_render_params;

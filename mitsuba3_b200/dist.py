@@ -26,10 +26,11 @@ def world():
 
 
 def tile_owner(x, y, width, tile_size, world_size):
-    """Rank that renders pixel (x, y): tiles are dealt round-robin in scanline order
-    (same rule as ensure_pix_ids in csrc/api.cu)."""
-    tiles_x = (width + tile_size - 1) // tile_size
-    return ((y // tile_size) * tiles_x + (x // tile_size)) % world_size
+    """Rank that renders pixel (x, y): tile (tx, ty) goes to rank (tx + ty * (N // 2 + 1)) % N, a
+    diagonal deal that never gives a rank whole tile columns (same rule as ensure_pix_ids in
+    csrc/api.cu). ``width`` is kept for signature compatibility."""
+    del width
+    return ((x // tile_size) + (y // tile_size) * (world_size // 2 + 1)) % world_size
 
 
 def all_reduce_film(film):
