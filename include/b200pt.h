@@ -81,10 +81,12 @@ enum {
 enum {
     /* diffuse */
     B200PT_SLOT_REFLECTANCE = 0,
-    /* conductor */
+    /* conductor / roughconductor (alpha slots: B200PT_M_ROUGH only) */
     B200PT_SLOT_ETA = 0, B200PT_SLOT_K = 1, B200PT_SLOT_SPEC_REFL = 2,
-    /* dielectric */
+    B200PT_SLOT_ALPHA_U = 3, B200PT_SLOT_ALPHA_V = 4,
+    /* dielectric / roughdielectric */
     B200PT_SLOT_D_SPEC_REFL = 0, B200PT_SLOT_D_SPEC_TRANS = 1,
+    B200PT_SLOT_D_ALPHA_U = 2, B200PT_SLOT_D_ALPHA_V = 3,
     /* principled (principled.cpp:190-330) */
     B200PT_SLOT_P_BASE_COLOR = 0, B200PT_SLOT_P_ROUGHNESS = 1,
     B200PT_SLOT_P_ANISOTROPIC = 2, B200PT_SLOT_P_METALLIC = 3,
@@ -104,6 +106,13 @@ enum {
     B200PT_P_ETA_SPECULAR = 1u << 8  /* eta given explicitly, not `specular` */
 };
 
+/* Microfacet variants of B200PT_BSDF_CONDUCTOR / _DIELECTRIC: `roughconductor`
+ * (src/bsdfs/roughconductor.cpp) and `roughdielectric` (src/bsdfs/roughdielectric.cpp) are the
+ * same types with B200PT_M_ROUGH set and the alpha_u / alpha_v slots filled; the
+ * distribution is Beckmann unless B200PT_M_GGX (microfacet.h:36-43), visible-normal
+ * sampling only (`sample_visible = true`, the default). */
+enum { B200PT_M_ROUGH = 1u << 16, B200PT_M_GGX = 1u << 17 };
+
 typedef struct b200pt_bsdf {
     int32_t  type;                  /* B200PT_BSDF_*                        */
     int32_t  twosided;              /* wrapped in `twosided` (twosided.cpp) */
@@ -112,7 +121,7 @@ typedef struct b200pt_bsdf {
     float    spec_srate;            /* principled: main_specular_sampling_rate */
     float    clearcoat_srate;       /* principled: clearcoat_sampling_rate  */
     float    diff_refl_srate;       /* principled: diffuse_reflectance_sampling_rate */
-    uint32_t flags;                 /* B200PT_P_*                           */
+    uint32_t flags;                 /* B200PT_P_* | B200PT_M_*              */
 } b200pt_bsdf;
 
 /* How an emitter's shape is sampled by position

@@ -27,8 +27,8 @@ RFILTER_BOX, RFILTER_GAUSSIAN, RFILTER_GAUSSIAN_EXP2, RFILTER_GAUSSIAN_TABLE = 0
 
 # texture slots
 SLOT_REFLECTANCE = 0
-SLOT_ETA, SLOT_K, SLOT_SPEC_REFL = 0, 1, 2
-SLOT_D_SPEC_REFL, SLOT_D_SPEC_TRANS = 0, 1
+SLOT_ETA, SLOT_K, SLOT_SPEC_REFL, SLOT_ALPHA_U, SLOT_ALPHA_V = 0, 1, 2, 3, 4
+SLOT_D_SPEC_REFL, SLOT_D_SPEC_TRANS, SLOT_D_ALPHA_U, SLOT_D_ALPHA_V = 0, 1, 2, 3
 (SLOT_P_BASE_COLOR, SLOT_P_ROUGHNESS, SLOT_P_ANISOTROPIC, SLOT_P_METALLIC,
  SLOT_P_SPEC_TRANS, SLOT_P_SPECULAR, SLOT_P_SPEC_TINT, SLOT_P_SHEEN,
  SLOT_P_SHEEN_TINT, SLOT_P_FLATNESS, SLOT_P_CLEARCOAT, SLOT_P_CLEARCOAT_GLOSS) = range(12)
@@ -36,6 +36,7 @@ SLOT_D_SPEC_REFL, SLOT_D_SPEC_TRANS = 0, 1
 P_HAS_CLEARCOAT, P_HAS_SHEEN, P_HAS_SPEC_TRANS, P_HAS_METALLIC = 1, 2, 4, 8
 P_HAS_SPEC_TINT, P_HAS_SHEEN_TINT, P_HAS_ANISOTROPIC, P_HAS_FLATNESS = 16, 32, 64, 128
 P_ETA_SPECULAR = 256
+M_ROUGH, M_GGX = 1 << 16, 1 << 17     # roughconductor / roughdielectric (B200PT_M_*)
 
 STATUS = {0: "ok", 1: "invalid argument", 2: "CUDA error / no device",
           3: "unsupported", 4: "out of memory"}

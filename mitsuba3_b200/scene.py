@@ -9,7 +9,7 @@ Supported plugin types (same property names as the reference):
   ``independent`` sampler (sample_count, seed); shapes ``rectangle`` / ``cube``
   (src/shapes/rectangle.cpp, cube.cpp) and ``mesh`` (packed arrays, as produced
   by the host's loaders); BSDFs ``diffuse`` / ``conductor`` / ``dielectric`` /
-  ``principled`` / ``twosided``; emitters ``area`` / ``constant`` / ``envmap``; textures ``rgb`` / float /
+  ``principled`` / ``roughconductor`` / ``roughdielectric`` / ``twosided``; emitters ``area`` / ``constant`` / ``envmap``; textures ``rgb`` / float /
   ``bitmap`` (raw float32 data); ``ref``.
 
 Everything else (XML, OBJ/PLY loaders, spectra, other plugins) stays in the
@@ -236,6 +236,9 @@ def _as_transform(t) -> Transform4f:
     return Transform4f(np.asarray(t, f32).reshape(4, 4))
 
 
+_BSDF_TYPES = ("diffuse", "conductor", "roughconductor", "dielectric", "roughdielectric", "principled", "twosided")
+
+
 class _Parser:
     def __init__(self):
         self.scene = Scene()
@@ -307,7 +310,7 @@ class _Parser:
         if ty == "diffuse":
             b.type = abi.BSDF_DIFFUSE
             b.tex[abi.SLOT_REFLECTANCE] = self.texture(f"{bid}.reflectance", d.get("reflectance"), 3, 0.5)
-        elif ty == "conductor":
+        elif ty in ("conductor", "roughconductor"):
             b.type = abi.BSDF_CONDUCTOR
             mat = d.get("material")
             if mat not in (None, "none") and ("eta" not in d):
@@ -315,9 +318,16 @@ class _Parser:
             eta, k = (d.get("eta", 0.0), d.get("k", 1.0))
             b.tex[abi.SLOT_ETA] = self.texture(f"{bid}.eta", eta, 3)
             b.tex[abi.SLOT_K] = self.texture(f"{bid}.k", k, 3)
-            b.tex[abi.SLOT_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3, 1.0)
-        elif ty == "dielectric":
+            if ty == "roughconductor":
+                # roughconductor.cpp:172-205: specular_reflectance only if given
+                b.tex[abi.SLOT_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3)
+                self._microfacet(b, bid, d, abi.SLOT_ALPHA_U, abi.SLOT_ALPHA_V)
+            else:
+                b.tex[abi.SLOT_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3, 1.0)
+        elif ty in ("dielectric", "roughdielectric"):
             b.type = abi.BSDF_DIELECTRIC
+            if ty == "roughdielectric":
+                self._microfacet(b, bid, d, abi.SLOT_D_ALPHA_U, abi.SLOT_D_ALPHA_V)
             b.eta = float(f32(f32(lookup_ior(d.get("int_ior"), "bk7")) / f32(lookup_ior(d.get("ext_ior"), "air"))))
             b.tex[abi.SLOT_D_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3)
             b.tex[abi.SLOT_D_SPEC_TRANS] = self.texture(f"{bid}.specular_transmittance", d.get("specular_transmittance"), 3)
@@ -327,6 +337,25 @@ class _Parser:
             raise NotImplementedError(f"BSDF {ty!r} is outside the hot-path scope (SURVEY.md 8(a))")
         self.scene.bsdfs.append(b)
         return len(self.scene.bsdfs) - 1
+
+    def _microfacet(self, b: BsdfData, bid: str, d: dict, slot_u: int, slot_v: int):
+        """Microfacet parameters shared by roughconductor / roughdielectric (roughconductor.cpp:172-200,
+        roughdielectric.cpp:190-225): `distribution` beckmann (default) | ggx, `alpha` or `alpha_u`+`alpha_v`."""
+        distr = d.get("distribution", "beckmann")
+        if distr not in ("beckmann", "ggx"):
+            raise ValueError(f'Specified an invalid distribution "{distr}", must be "beckmann" or "ggx"!')
+        if not bool(d.get("sample_visible", True)):
+            raise NotImplementedError("sample_visible=false is outside the hot-path scope")
+        b.flags |= abi.M_ROUGH | (abi.M_GGX if distr == "ggx" else 0)
+        if "alpha_u" in d or "alpha_v" in d:
+            if "alpha_u" not in d or "alpha_v" not in d:
+                raise ValueError("Microfacet model: both 'alpha_u' and 'alpha_v' must be specified.")
+            if "alpha" in d:
+                raise ValueError("Microfacet model: please specify either 'alpha' or 'alpha_u'/'alpha_v'.")
+            b.tex[slot_u] = self.texture(f"{bid}.alpha_u", d["alpha_u"], 1)
+            b.tex[slot_v] = self.texture(f"{bid}.alpha_v", d["alpha_v"], 1)
+        else:
+            b.tex[slot_u] = b.tex[slot_v] = self.texture(f"{bid}.alpha", d.get("alpha"), 1, 0.1)
 
     def _principled(self, b: BsdfData, bid: str, d: dict):
         # principled.cpp:190-330 constructor
@@ -387,12 +416,20 @@ class _Parser:
         bs = d.get("bsdf")
         if bs is None:
             for k, v in d.items():
-                if isinstance(v, dict) and v.get("type") in ("diffuse", "conductor", "dielectric", "principled", "twosided", "ref") and k != "emitter":
+                if isinstance(v, dict) and v.get("type") in _BSDF_TYPES + ("ref",) and k != "emitter":
                     bs = v
                     break
         if bs is None:
             bs = {"type": "diffuse"}     # Shape default BSDF (shape.cpp: diffuse 0.5)
         bidx = self.bsdf(f"{sid}.bsdf", bs)
+        bd = self.scene.bsdfs[bidx]
+        aniso = (bd.type == abi.BSDF_PRINCIPLED and bd.flags & abi.P_HAS_ANISOTROPIC) or \
+                (bd.type == abi.BSDF_CONDUCTOR and bd.flags & abi.M_ROUGH and bd.tex[abi.SLOT_ALPHA_U] != bd.tex[abi.SLOT_ALPHA_V]) or \
+                (bd.type == abi.BSDF_DIELECTRIC and bd.flags & abi.M_ROUGH and bd.tex[abi.SLOT_D_ALPHA_U] != bd.tex[abi.SLOT_D_ALPHA_V])
+        if aniso:
+            # BSDFFlags::Anisotropic makes the reference's meshes pack per-vertex tangent frames
+            # (mesh.cpp:2417-2429, interaction.h:570-598); those are outside the hot-path scope
+            raise NotImplementedError("anisotropic BSDFs need packed tangent frames, which are outside the hot-path scope")
         to_world = _as_transform(d.get("to_world"))
         flip = bool(d.get("flip_normals", False))
         if ty == "rectangle":
@@ -494,7 +531,7 @@ class _Parser:
             raise ValueError("top-level dictionary must have type 'scene'")
         # first pass: named BSDFs (so that refs resolve irrespective of order)
         for k, v in d.items():
-            if isinstance(v, dict) and v.get("type") in ("diffuse", "conductor", "dielectric", "principled", "twosided"):
+            if isinstance(v, dict) and v.get("type") in _BSDF_TYPES:
                 self.named_bsdfs[k] = self.bsdf(k, v)
         for k, v in d.items():
             if not isinstance(v, dict):
@@ -511,7 +548,7 @@ class _Parser:
                 self.shape(k, v)
             elif ty in ("constant", "envmap"):
                 self.environment(k, v)
-            elif ty in ("diffuse", "conductor", "dielectric", "principled", "twosided"):
+            elif ty in _BSDF_TYPES:
                 pass
             else:
                 raise NotImplementedError(f"plugin type {ty!r} is outside the hot-path scope (SURVEY.md 8)")

@@ -23,7 +23,7 @@ class OrcStats(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "pt_oracle_principled.inc", "pt_oracle_env.inc", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "pt_oracle_principled.inc", "pt_oracle_env.inc", "pt_oracle_rough.inc", "Makefile")]
     src.append(os.path.join(_HERE, "..", "include", "b200pt.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src)

@@ -121,3 +121,39 @@ def env_scene(kind="envmap", res=32, spp=16, max_depth=6, area_light=False, hide
     else:
         d["sky"] = {"type": "constant", "radiance": {"type": "rgb", "value": [0.9, 1.1, 1.4]}}
     return d
+
+
+# rough conductor / dielectric (same specs as gen_golden.py:ROUGH_SPECS)
+ROUGH_SPECS = {
+    "roughconductor_beckmann": {"type": "roughconductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}},
+    "roughconductor_beckmann_rough": {"type": "roughconductor", "alpha": 0.5, "eta": {"type": "rgb", "value": [1.6, 0.9, 0.5]},
+                                      "k": {"type": "rgb", "value": [2.9, 2.0, 1.6]}},
+    "roughconductor_ggx_aniso": {"type": "roughconductor", "distribution": "ggx", "alpha_u": 0.05, "alpha_v": 0.3,
+                                 "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
+                                 "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+    "roughdielectric_beckmann": {"type": "roughdielectric", "alpha": 0.2},
+    "roughdielectric_ggx_aniso_tinted": {"type": "roughdielectric", "distribution": "ggx", "alpha_u": 0.1, "alpha_v": 0.4,
+                                         "int_ior": "water", "ext_ior": "air",
+                                         "specular_reflectance": {"type": "rgb", "value": [0.9, 0.95, 1.0]},
+                                         "specular_transmittance": {"type": "rgb", "value": [0.8, 0.9, 0.7]}},
+    "roughconductor_ggx_tinted": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
+                                  "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
+                                  "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+    "twosided_roughconductor_ggx": {"type": "twosided", "bsdf": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
+                                                                   "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}},
+}
+
+
+def rough_cbox(res=32, rfilter="box", spp=16, max_depth=8):
+    """Cornell box with rough conductor / rough dielectric boxes and back wall (gen_golden.py:rough_materials)."""
+    import copy
+    import mitsuba3_b200 as mb
+    d = cbox(res, rfilter, spp, max_depth)
+    d["rc"] = copy.deepcopy(ROUGH_SPECS["roughconductor_ggx_tinted"])
+    d["rd"] = copy.deepcopy(ROUGH_SPECS["roughdielectric_beckmann"])
+    d["rb"] = copy.deepcopy(ROUGH_SPECS["roughconductor_beckmann_rough"])
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "rd"}
+    d["small-box"]["to_world"] = mb.Transform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "rc"}
+    d["back"]["bsdf"] = {"type": "ref", "id": "rb"}
+    return d

@@ -17,6 +17,7 @@ What is recorded (all from mitsuba scalar_rgb, reference v3.9.1):
   bsdf_tables.npz  BSDF eval/pdf/sample tables (diffuse, conductor, dielectric, principled)
   cbox_renders.npz scalar_rgb renders (single 32x32 / 64x64 block; box + gaussian), several seeds
   materials_renders.npz  same for a Cornell box with conductor / dielectric / principled boxes
+  rough.npz        roughconductor / roughdielectric eval_pdf_sample tables (Beckmann + GGX) and Cornell renders
   env.npz          envmap / constant emitter tables (sample_direction, eval, pdf_direction) and renders
 """
 import os
@@ -305,6 +306,48 @@ def gen_multi_emitter():
     save("multi_emitter_renders.npz", **out)
 
 
+# --------------------------------------------------------------------------- rough conductor / dielectric
+ROUGH_SPECS = {
+    "roughconductor_beckmann": {"type": "roughconductor", "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}},
+    "roughconductor_beckmann_rough": {"type": "roughconductor", "alpha": 0.5, "eta": {"type": "rgb", "value": [1.6, 0.9, 0.5]},
+                                      "k": {"type": "rgb", "value": [2.9, 2.0, 1.6]}},
+    "roughconductor_ggx_aniso": {"type": "roughconductor", "distribution": "ggx", "alpha_u": 0.05, "alpha_v": 0.3,
+                                 "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
+                                 "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+    "roughdielectric_beckmann": {"type": "roughdielectric", "alpha": 0.2},
+    "roughdielectric_ggx_aniso_tinted": {"type": "roughdielectric", "distribution": "ggx", "alpha_u": 0.1, "alpha_v": 0.4,
+                                         "int_ior": "water", "ext_ior": "air",
+                                         "specular_reflectance": {"type": "rgb", "value": [0.9, 0.95, 1.0]},
+                                         "specular_transmittance": {"type": "rgb", "value": [0.8, 0.9, 0.7]}},
+    "roughconductor_ggx_tinted": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
+                                  "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
+                                  "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+    "twosided_roughconductor_ggx": {"type": "twosided", "bsdf": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
+                                                                   "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}},
+}
+
+
+def rough_materials(d):
+    # (isotropic models only: anisotropic BSDFs make the reference's meshes pack tangent frames, mesh.cpp:2417-2429)
+    d["rc"] = ROUGH_SPECS["roughconductor_ggx_tinted"]
+    d["rd"] = ROUGH_SPECS["roughdielectric_beckmann"]
+    d["rb"] = ROUGH_SPECS["roughconductor_beckmann_rough"]
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "rd"}
+    d["small-box"]["to_world"] = mi.ScalarTransform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "rc"}
+    d["back"]["bsdf"] = {"type": "ref", "id": "rb"}
+
+
+def gen_rough():
+    out = {}
+    for name, spec in ROUGH_SPECS.items():
+        q, o = bsdf_table(spec, n=96, seed=11, transmissive=("dielectric" in name or "twosided" in name))
+        out[name + "_in"] = q; out[name + "_out"] = o
+    for (res, spp, md, seed) in [(32, 16, 8, 0), (32, 8, 5, 3)]:
+        out[f"rough_{res}_box_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter="box", spp=spp, max_depth=md, extra=rough_materials), seed, spp)
+    save("rough.npz", **out)
+
+
 # --------------------------------------------------------------------------- environment emitters
 def env_image(w=16, h=8):
     """Small synthetic lat-long sky: gradient + a bright 'sun' blob + a dim ground (float32, linear RGB)."""
@@ -400,7 +443,7 @@ def block_one(d, res):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env"]
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env", "rough"]
     if "rng" in what:
         gen_rng()
     scene = None
@@ -418,3 +461,5 @@ if __name__ == "__main__":
         gen_multi_emitter()
     if "env" in what:
         gen_env()
+    if "rough" in what:
+        gen_rough()

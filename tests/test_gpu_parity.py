@@ -65,9 +65,8 @@ def test_ray_intersect_random_rays_large_batch(cbox_pair):
 
 def _bsdf_scene(spec):
     d = cbox()
-    d["probe"] = spec
-    d["back"]["bsdf"] = {"type": "ref", "id": "probe"}
-    sc = mb.load_dict(d)
+    d["probe"] = spec      # a named, unattached BSDF: the tables do not depend on a shape (and anisotropic
+    sc = mb.load_dict(d)   # models may not be attached to meshes without tangent frames)
     idx = [i for i, b in enumerate(sc.bsdfs) if b.id == "probe"][0]
     return sc, idx
 
