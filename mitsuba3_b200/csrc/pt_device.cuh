@@ -393,8 +393,8 @@ struct BsdfResult { float3 value; float pdf; BsdfSample bs; float3 weight; };
 PT_DEV uint32_t bsdf_flags(const DevBsdf &b) {
     switch (b.type) {
         case B200PT_BSDF_DIFFUSE: return F_DIFFUSE_REFLECTION;
-        case B200PT_BSDF_CONDUCTOR: return F_DELTA_REFLECTION;
-        case B200PT_BSDF_DIELECTRIC: return F_DELTA_REFLECTION | F_DELTA_TRANSMISSION;
+        case B200PT_BSDF_CONDUCTOR: return (b.flags & B200PT_M_ROUGH) ? F_GLOSSY_REFLECTION : F_DELTA_REFLECTION;
+        case B200PT_BSDF_DIELECTRIC: return (b.flags & B200PT_M_ROUGH) ? (F_GLOSSY_REFLECTION | F_GLOSSY_TRANSMISSION) : (F_DELTA_REFLECTION | F_DELTA_TRANSMISSION);
         default: return F_DIFFUSE_REFLECTION | F_GLOSSY_REFLECTION | ((b.flags & B200PT_P_HAS_SPEC_TRANS) ? F_GLOSSY_TRANSMISSION : 0u);
     }
 }
@@ -402,6 +402,7 @@ PT_DEV uint32_t bsdf_flags(const DevBsdf &b) {
 } // namespace pt
 
 #include "pt_principled.cuh"
+#include "pt_rough.cuh"
 
 namespace pt {
 
@@ -417,6 +418,10 @@ PT_DEV void bsdf_eval_pdf_inner(const DevScene &sc, const DevBsdf &b, float2 uv,
         }
     } else if (TYPE == B200PT_BSDF_PRINCIPLED) {
         principled_eval_pdf(sc, b, uv, wi, wo, value, pdf);
+    } else if (TYPE == B200PT_BSDF_CONDUCTOR) {
+        if (b.flags & B200PT_M_ROUGH) roughconductor_eval_pdf(sc, b, uv, wi, wo, value, pdf);      // smooth: delta lobe, 0
+    } else if (TYPE == B200PT_BSDF_DIELECTRIC) {
+        if (b.flags & B200PT_M_ROUGH) roughdielectric_eval_pdf(sc, b, uv, wi, wo, value, pdf);
     }
 }
 
@@ -432,6 +437,7 @@ PT_DEV void bsdf_sample_inner(const DevScene &sc, const DevBsdf &b, float2 uv, f
         bs.eta = 1.f; bs.sampled_type = F_DIFFUSE_REFLECTION;
         if (bs.pdf > 0.f) weight = tex_eval3(sc, b.tex[B200PT_SLOT_REFLECTANCE], uv);
     } else if (TYPE == B200PT_BSDF_CONDUCTOR) {
+        if (b.flags & B200PT_M_ROUGH) { roughconductor_sample(sc, b, uv, wi, s2x, s2y, bs, weight); return; }
         // conductor.cpp:247-307
         if (!(wi.z > 0.f)) return;
         bs.sampled_type = F_DELTA_REFLECTION; bs.wo = V(-wi.x, -wi.y, wi.z); bs.eta = 1.f; bs.pdf = 1.f;
@@ -439,6 +445,7 @@ PT_DEV void bsdf_sample_inner(const DevScene &sc, const DevBsdf &b, float2 uv, f
         float3 refl = b.tex[B200PT_SLOT_SPEC_REFL] >= 0 ? tex_eval3(sc, b.tex[B200PT_SLOT_SPEC_REFL], uv) : V(1.f, 1.f, 1.f);
         weight = V(refl.x * fresnel_conductor(wi.z, eta.x, k.x), refl.y * fresnel_conductor(wi.z, eta.y, k.y), refl.z * fresnel_conductor(wi.z, eta.z, k.z));
     } else if (TYPE == B200PT_BSDF_DIELECTRIC) {
+        if (b.flags & B200PT_M_ROUGH) { roughdielectric_sample(sc, b, uv, wi, s1, s2x, s2y, bs, weight); return; }
         // dielectric.cpp:245-370
         float r_i, ctt, eta_it, eta_ti;
         fresnel(wi.z, b.eta, r_i, ctt, eta_it, eta_ti);
