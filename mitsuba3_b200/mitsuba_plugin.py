@@ -26,7 +26,8 @@ from .scene import (BsdfData, EmitterData, Scene, SensorData, ShapeData, Texture
 from .transform import _cross, _normalize, _sqnorm, Transform4f
 
 _BSDF_CLASS = {"SmoothDiffuse": abi.BSDF_DIFFUSE, "SmoothConductor": abi.BSDF_CONDUCTOR,
-               "SmoothDielectric": abi.BSDF_DIELECTRIC, "Principled": abi.BSDF_PRINCIPLED}
+               "SmoothDielectric": abi.BSDF_DIELECTRIC, "Principled": abi.BSDF_PRINCIPLED,
+               "RoughConductor": abi.BSDF_CONDUCTOR, "RoughDielectric": abi.BSDF_DIELECTRIC}
 
 
 def _np(x, dtype=np.float32):
@@ -79,6 +80,9 @@ class _Extractor:
             twosided, prefix = True, "brdf_0."
             inner = [k for k in params.keys() if k.startswith("brdf_0.")]
             cls = self._guess_class(inner)
+            desc = str(b)
+        else:
+            desc = str(b)
         if cls not in _BSDF_CLASS:
             raise NotImplementedError(f"BSDF class {cls!r} is outside the hot-path scope (SURVEY.md 8(a))")
         d = BsdfData(id=key, type=_BSDF_CLASS[cls], twosided=twosided)
@@ -87,11 +91,17 @@ class _Extractor:
             d.tex[abi.SLOT_REFLECTANCE] = T("reflectance", 3, 0.5)
         elif d.type == abi.BSDF_CONDUCTOR:
             d.tex[abi.SLOT_ETA], d.tex[abi.SLOT_K] = T("eta", 3, 0.0), T("k", 3, 1.0)
-            d.tex[abi.SLOT_SPEC_REFL] = T("specular_reflectance", 3, 1.0)
+            if cls == "RoughConductor":
+                d.tex[abi.SLOT_SPEC_REFL] = T("specular_reflectance", 3)
+                self._microfacet(d, desc, T, abi.SLOT_ALPHA_U, abi.SLOT_ALPHA_V)
+            else:
+                d.tex[abi.SLOT_SPEC_REFL] = T("specular_reflectance", 3, 1.0)
         elif d.type == abi.BSDF_DIELECTRIC:
             d.eta = float(params[f"{prefix}eta"])
             d.tex[abi.SLOT_D_SPEC_REFL] = T("specular_reflectance", 3)
             d.tex[abi.SLOT_D_SPEC_TRANS] = T("specular_transmittance", 3)
+            if cls == "RoughDielectric":
+                self._microfacet(d, desc, T, abi.SLOT_D_ALPHA_U, abi.SLOT_D_ALPHA_V)
         else:
             flags = 0
             slots = [("base_color", abi.SLOT_P_BASE_COLOR, 3, 0), ("roughness", abi.SLOT_P_ROUGHNESS, 1, 0),
@@ -119,9 +129,31 @@ class _Extractor:
         return self.bsdf_index[key]
 
     @staticmethod
+    def _microfacet(d, desc, T, slot_u, slot_v):
+        """alpha / alpha_u, alpha_v come from mi.traverse; the distribution type and `sample_visible` are
+        only visible in the plugin's string form (roughconductor.cpp:531-550, roughdielectric.cpp:612-640)."""
+        import re
+        m = re.search(r"distribution\s*=\s*(\w+)", desc)
+        distr = m.group(1).lower() if m else "beckmann"
+        if distr not in ("beckmann", "ggx"):
+            raise NotImplementedError(f"microfacet distribution {distr!r}")
+        m = re.search(r"sample_visible\s*=\s*(\w+)", desc)
+        if m and m.group(1).lower() in ("0", "false"):
+            raise NotImplementedError("sample_visible=false is outside the hot-path scope")
+        d.flags |= abi.M_ROUGH | (abi.M_GGX if distr == "ggx" else 0)
+        au = T("alpha", 1)
+        if au >= 0:
+            d.tex[slot_u] = d.tex[slot_v] = au
+        else:
+            d.tex[slot_u], d.tex[slot_v] = T("alpha_u", 1), T("alpha_v", 1)
+            raise NotImplementedError("anisotropic BSDFs need packed tangent frames, which are outside the hot-path scope")
+
+    @staticmethod
     def _guess_class(keys):
         ks = " ".join(keys)
         if "base_color" in ks: return "Principled"
+        if "alpha" in ks and ".k." in ks: return "RoughConductor"
+        if "alpha" in ks: return "RoughDielectric"
         if "specular_transmittance" in ks or ".eta" in ks and ".k" not in ks and "reflectance.value" not in ks: return "SmoothDielectric"
         if ".k." in ks: return "SmoothConductor"
         return "SmoothDiffuse"

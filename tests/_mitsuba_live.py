@@ -68,6 +68,22 @@ def main(mode):
           img3 = oracle.OracleScene(host3).render(spp=16, seed=2, mode=1, max_depth=6)
           rel = np.abs(img3 - ref3) / np.maximum(np.abs(ref3), 1e-2)
           assert rel.max() < 2e-4, (kw, rel.max())
+      # rough conductor / dielectric (the distribution type is read from the plugin's string form)
+      from conftest import ROUGH_SPECS
+      def rough(d):
+          d["rc"], d["rd"], d["rb"] = ROUGH_SPECS["roughconductor_ggx_tinted"], ROUGH_SPECS["roughdielectric_beckmann"], ROUGH_SPECS["roughconductor_beckmann_rough"]
+          d["small-box"]["bsdf"] = {"type": "ref", "id": "rd"}
+          d["small-box"]["to_world"] = mi.ScalarTransform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
+          d["large-box"]["bsdf"] = {"type": "ref", "id": "rc"}
+          d["back"]["bsdf"] = {"type": "ref", "id": "rb"}
+          return d
+      sm4 = mi.load_dict(rough(cbox(32, {"type": "path", "max_depth": 8, "block_size": 32})))
+      host4 = plug.extract_scene(mi, sm4)
+      assert sorted(hex(b.flags) for b in host4.bsdfs if b.flags) == ["0x10000", "0x10000", "0x30000"]
+      ref4 = np.array(mi.render(sm4, seed=0, spp=16))
+      img4 = oracle.OracleScene(host4).render(spp=16, seed=0, mode=1, max_depth=8)
+      rel = np.abs(img4 - ref4) / np.maximum(np.abs(ref4), 1e-2)
+      assert rel.max() < 5e-4, rel.max()
       plug.register(mi)
       integ = mi.load_dict({"type": "b200_path", "max_depth": 8})
       assert "max_depth = 8" in str(integ)
