@@ -74,7 +74,8 @@ enum {
     B200PT_BSDF_DIFFUSE    = 0, /* src/bsdfs/diffuse.cpp    */
     B200PT_BSDF_CONDUCTOR  = 1, /* src/bsdfs/conductor.cpp  */
     B200PT_BSDF_DIELECTRIC = 2, /* src/bsdfs/dielectric.cpp */
-    B200PT_BSDF_PRINCIPLED = 3  /* src/bsdfs/principled.cpp */
+    B200PT_BSDF_PRINCIPLED = 3, /* src/bsdfs/principled.cpp */
+    B200PT_BSDF_PLASTIC    = 4  /* src/bsdfs/plastic.cpp (smooth plastic) */
 };
 
 /* Texture slots (indices into b200pt_bsdf::tex). */
@@ -84,6 +85,8 @@ enum {
     /* conductor / roughconductor (alpha slots: B200PT_M_ROUGH only) */
     B200PT_SLOT_ETA = 0, B200PT_SLOT_K = 1, B200PT_SLOT_SPEC_REFL = 2,
     B200PT_SLOT_ALPHA_U = 3, B200PT_SLOT_ALPHA_V = 4,
+    /* plastic */
+    B200PT_SLOT_PL_DIFFUSE = 0, B200PT_SLOT_PL_SPEC_REFL = 1,
     /* dielectric / roughdielectric */
     B200PT_SLOT_D_SPEC_REFL = 0, B200PT_SLOT_D_SPEC_TRANS = 1,
     B200PT_SLOT_D_ALPHA_U = 2, B200PT_SLOT_D_ALPHA_V = 3,
@@ -111,7 +114,8 @@ enum {
  * same types with B200PT_M_ROUGH set and the alpha_u / alpha_v slots filled; the
  * distribution is Beckmann unless B200PT_M_GGX (microfacet.h:36-43), visible-normal
  * sampling only (`sample_visible = true`, the default). */
-enum { B200PT_M_ROUGH = 1u << 16, B200PT_M_GGX = 1u << 17 };
+enum { B200PT_M_ROUGH = 1u << 16, B200PT_M_GGX = 1u << 17,
+       B200PT_M_NONLINEAR = 1u << 18 /* plastic: `nonlinear` (plastic.cpp:176) */ };
 
 typedef struct b200pt_bsdf {
     int32_t  type;                  /* B200PT_BSDF_*                        */
@@ -122,6 +126,8 @@ typedef struct b200pt_bsdf {
     float    clearcoat_srate;       /* principled: clearcoat_sampling_rate  */
     float    diff_refl_srate;       /* principled: diffuse_reflectance_sampling_rate */
     uint32_t flags;                 /* B200PT_P_* | B200PT_M_*              */
+    float    plastic_fdr_int;       /* plastic: fresnel_diffuse_reflectance(1/eta) (plastic.cpp:199, fresnel.h:326-360) */
+    float    plastic_spec_weight;   /* plastic: m_specular_sampling_weight (plastic.cpp:202-208)                       */
 } b200pt_bsdf;
 
 /* How an emitter's shape is sampled by position

@@ -20,7 +20,7 @@ TEX_CONST, TEX_BITMAP, TEX_CHECKERBOARD = 0, 1, 2
 EMITTER_AREA, EMITTER_CONSTANT, EMITTER_ENVMAP = 0, 1, 2
 WRAP_REPEAT, WRAP_MIRROR, WRAP_CLAMP = 0, 1, 2
 FILTER_BILINEAR, FILTER_NEAREST = 0, 1
-BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PRINCIPLED = 0, 1, 2, 3
+BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_PRINCIPLED, BSDF_PLASTIC = 0, 1, 2, 3, 4
 SAMPLING_NONE, SAMPLING_RECTANGLE, SAMPLING_MESH = 0, 1, 2
 LAYOUT_NORMALS, LAYOUT_TANGENTS, LAYOUT_TEXCOORDS = 1, 2, 4
 RFILTER_BOX, RFILTER_GAUSSIAN, RFILTER_GAUSSIAN_EXP2, RFILTER_GAUSSIAN_TABLE = 0, 1, 2, 3
@@ -36,7 +36,8 @@ SLOT_D_SPEC_REFL, SLOT_D_SPEC_TRANS, SLOT_D_ALPHA_U, SLOT_D_ALPHA_V = 0, 1, 2, 3
 P_HAS_CLEARCOAT, P_HAS_SHEEN, P_HAS_SPEC_TRANS, P_HAS_METALLIC = 1, 2, 4, 8
 P_HAS_SPEC_TINT, P_HAS_SHEEN_TINT, P_HAS_ANISOTROPIC, P_HAS_FLATNESS = 16, 32, 64, 128
 P_ETA_SPECULAR = 256
-M_ROUGH, M_GGX = 1 << 16, 1 << 17     # roughconductor / roughdielectric (B200PT_M_*)
+M_ROUGH, M_GGX, M_NONLINEAR = 1 << 16, 1 << 17, 1 << 18     # roughconductor / roughdielectric / plastic (B200PT_M_*)
+SLOT_PL_DIFFUSE, SLOT_PL_SPEC_REFL = 0, 1
 
 STATUS = {0: "ok", 1: "invalid argument", 2: "CUDA error / no device",
           3: "unsupported", 4: "out of memory"}
@@ -52,7 +53,8 @@ class Texture(C.Structure):
 class Bsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("twosided", C.c_int32), ("tex", C.c_int32 * MAX_SLOTS),
                 ("eta", C.c_float), ("spec_srate", C.c_float), ("clearcoat_srate", C.c_float),
-                ("diff_refl_srate", C.c_float), ("flags", C.c_uint32)]
+                ("diff_refl_srate", C.c_float), ("flags", C.c_uint32),
+                ("plastic_fdr_int", C.c_float), ("plastic_spec_weight", C.c_float)]
 
 
 class Shape(C.Structure):

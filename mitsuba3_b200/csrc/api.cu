@@ -172,10 +172,12 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     std::vector<DevBsdf> hb(desc->n_bsdfs);
     for (uint32_t i = 0; i < desc->n_bsdfs; ++i) {
         const b200pt_bsdf &b = desc->bsdfs[i];
-        if (b.type < 0 || b.type >= N_BSDF_TYPES) S_FAIL(B200PT_ERR_UNSUPPORTED, "BSDF model outside the hot-path scope");
+        if (b.type < 0 || b.type > B200PT_BSDF_PLASTIC) S_FAIL(B200PT_ERR_UNSUPPORTED, "BSDF model outside the hot-path scope");
         hb[i].type = b.type; hb[i].twosided = b.twosided; memcpy(hb[i].tex, b.tex, sizeof(b.tex));
         for (int k = 0; k < B200PT_MAX_SLOTS; ++k) if (b.tex[k] >= (int32_t) desc->n_textures) S_FAIL(B200PT_ERR_INVALID, "BSDF references a missing texture");
-        hb[i].eta = b.eta; hb[i].spec_srate = b.spec_srate; hb[i].clearcoat_srate = b.clearcoat_srate; hb[i].diff_refl_srate = b.diff_refl_srate; hb[i].flags = b.flags;
+        hb[i].eta = b.eta; hb[i].spec_srate = b.spec_srate; hb[i].clearcoat_srate = b.clearcoat_srate; hb[i].diff_refl_srate = b.diff_refl_srate; hb[i].flags = b.flags & ~PT_M_PLASTIC;
+        hb[i].plastic_fdr_int = b.plastic_fdr_int; hb[i].plastic_spec_weight = b.plastic_spec_weight;
+        if (b.type == B200PT_BSDF_PLASTIC) { hb[i].type = B200PT_BSDF_CONDUCTOR; hb[i].flags |= PT_M_PLASTIC; }   // shares the conductor queue / kernel
     }
     d.n_bsdfs = desc->n_bsdfs;
     std::vector<DevEmitter> he(desc->n_emitters);
@@ -231,7 +233,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         o.layout = sh.layout; o.bsdf = sh.bsdf; o.emitter = sh.emitter; o.sampling = sh.sampling;
         o.first_prim = (uint32_t) po; o.n_prims = sh.n_faces; o.first_vertex = (uint32_t) vo;
         memcpy(o.to_world, sh.to_world, sizeof(o.to_world)); memcpy(o.frame_n, sh.frame_n, sizeof(o.frame_n)); o.inv_area = sh.inv_area;
-        s->type_present[desc->bsdfs[sh.bsdf].type] = true;
+        s->type_present[hb[sh.bsdf].type] = true;       // the queue / kernel class (plastic -> conductor)
         memcpy(&verts[vo * 8], sh.vertices, (size_t) sh.n_vertices * 8 * sizeof(float));
         std::vector<float> cdf, pmf;
         double acc = 0;

@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                 if (!ADJOINT) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
             } else {
                 // ---- emitter sampling (path.cpp:238-259): the two randoms are always drawn (JIT semantics)
-                const bool smooth = TYPE == B200PT_BSDF_DIFFUSE || TYPE == B200PT_BSDF_PRINCIPLED || (bsdf.flags & B200PT_M_ROUGH);   // BSDFFlags::Smooth (path.cpp:238)
+                const bool smooth = TYPE == B200PT_BSDF_DIFFUSE || TYPE == B200PT_BSDF_PRINCIPLED || (bsdf.flags & (B200PT_M_ROUGH | PT_M_PLASTIC));   // BSDFFlags::Smooth (path.cpp:238)
                 float ex = rng.next_f32(), ey = rng.next_f32();
                 DirectionSample ds; ds.pdf = 0.f; ds.emitter = -1; ds.uv = make_float2(0.f, 0.f);
                 float3 em_weight = V(0.f, 0.f, 0.f), wo = V(0.f, 0.f, 0.f);

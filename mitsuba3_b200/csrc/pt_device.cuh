@@ -114,7 +114,10 @@ struct DevBsdf {
     int32_t tex[B200PT_MAX_SLOTS];
     float eta, spec_srate, clearcoat_srate, diff_refl_srate;
     uint32_t flags;
+    float plastic_fdr_int, plastic_spec_weight;
 };
+// internal: `plastic` shades in the conductor queue (type = B200PT_BSDF_CONDUCTOR + this flag)
+#define PT_M_PLASTIC (1u << 24)
 
 struct DevShape {
     uint32_t layout; int32_t bsdf, emitter, sampling;
@@ -393,7 +396,7 @@ struct BsdfResult { float3 value; float pdf; BsdfSample bs; float3 weight; };
 PT_DEV uint32_t bsdf_flags(const DevBsdf &b) {
     switch (b.type) {
         case B200PT_BSDF_DIFFUSE: return F_DIFFUSE_REFLECTION;
-        case B200PT_BSDF_CONDUCTOR: return (b.flags & B200PT_M_ROUGH) ? F_GLOSSY_REFLECTION : F_DELTA_REFLECTION;
+        case B200PT_BSDF_CONDUCTOR: return (b.flags & PT_M_PLASTIC) ? (F_DELTA_REFLECTION | F_DIFFUSE_REFLECTION) : (b.flags & B200PT_M_ROUGH) ? F_GLOSSY_REFLECTION : F_DELTA_REFLECTION;
         case B200PT_BSDF_DIELECTRIC: return (b.flags & B200PT_M_ROUGH) ? (F_GLOSSY_REFLECTION | F_GLOSSY_TRANSMISSION) : (F_DELTA_REFLECTION | F_DELTA_TRANSMISSION);
         default: return F_DIFFUSE_REFLECTION | F_GLOSSY_REFLECTION | ((b.flags & B200PT_P_HAS_SPEC_TRANS) ? F_GLOSSY_TRANSMISSION : 0u);
     }
@@ -419,7 +422,8 @@ PT_DEV void bsdf_eval_pdf_inner(const DevScene &sc, const DevBsdf &b, float2 uv,
     } else if (TYPE == B200PT_BSDF_PRINCIPLED) {
         principled_eval_pdf(sc, b, uv, wi, wo, value, pdf);
     } else if (TYPE == B200PT_BSDF_CONDUCTOR) {
-        if (b.flags & B200PT_M_ROUGH) roughconductor_eval_pdf(sc, b, uv, wi, wo, value, pdf);      // smooth: delta lobe, 0
+        if (b.flags & PT_M_PLASTIC) plastic_eval_pdf(sc, b, uv, wi, wo, value, pdf);
+        else if (b.flags & B200PT_M_ROUGH) roughconductor_eval_pdf(sc, b, uv, wi, wo, value, pdf); // smooth: delta lobe, 0
     } else if (TYPE == B200PT_BSDF_DIELECTRIC) {
         if (b.flags & B200PT_M_ROUGH) roughdielectric_eval_pdf(sc, b, uv, wi, wo, value, pdf);
     }
@@ -437,6 +441,7 @@ PT_DEV void bsdf_sample_inner(const DevScene &sc, const DevBsdf &b, float2 uv, f
         bs.eta = 1.f; bs.sampled_type = F_DIFFUSE_REFLECTION;
         if (bs.pdf > 0.f) weight = tex_eval3(sc, b.tex[B200PT_SLOT_REFLECTANCE], uv);
     } else if (TYPE == B200PT_BSDF_CONDUCTOR) {
+        if (b.flags & PT_M_PLASTIC) { plastic_sample(sc, b, uv, wi, s1, s2x, s2y, bs, weight); return; }
         if (b.flags & B200PT_M_ROUGH) { roughconductor_sample(sc, b, uv, wi, s2x, s2y, bs, weight); return; }
         // conductor.cpp:247-307
         if (!(wi.z > 0.f)) return;

@@ -195,3 +195,52 @@ PT_DEV void roughdielectric_sample(const DevScene &sc, const DevBsdf &b, float2 
 }
 
 } // namespace pt
+
+namespace pt {
+
+// ---- plastic.cpp:209-380 (smooth plastic, both components enabled). Shares the conductor
+// queue / kernel: DevBsdf.type = B200PT_BSDF_CONDUCTOR with PT_M_PLASTIC set (api.cu). ------
+PT_DEV float3 plastic_diffuse(const DevScene &sc, const DevBsdf &b, float2 uv) {
+    float3 diff = tex_eval3(sc, b.tex[B200PT_SLOT_PL_DIFFUSE], uv);
+    float f = b.plastic_fdr_int;
+    if (b.flags & B200PT_M_NONLINEAR) return V(fdiv(diff.x, 1.f - diff.x * f), fdiv(diff.y, 1.f - diff.y * f), fdiv(diff.z, 1.f - diff.z * f));
+    return V(fdiv(diff.x, 1.f - f), fdiv(diff.y, 1.f - f), fdiv(diff.z, 1.f - f));
+}
+
+PT_DEV void plastic_eval_pdf(const DevScene &sc, const DevBsdf &b, float2 uv, float3 wi, float3 wo, float3 &value, float &pdf) {
+    float cti = wi.z, cto = wo.z;
+    if (!(cti > 0.f && cto > 0.f)) return;
+    float f_i, f_o, t0, t1, t2;
+    fresnel(cti, b.eta, f_i, t0, t1, t2); fresnel(cto, b.eta, f_o, t0, t1, t2);
+    float3 diff = plastic_diffuse(sc, b, uv);
+    float hemi_pdf = PT_INV_PI * cto, inv_eta_2 = fdiv(1.f, b.eta * b.eta);
+    value = diff * (hemi_pdf * inv_eta_2 * (1.f - f_i) * (1.f - f_o));
+    float w = b.plastic_spec_weight, prob_specular = f_i * w, prob_diffuse = (1.f - f_i) * (1.f - w);
+    prob_diffuse = fdiv(prob_diffuse, prob_specular + prob_diffuse);
+    pdf = hemi_pdf * prob_diffuse;
+}
+
+PT_DEV void plastic_sample(const DevScene &sc, const DevBsdf &b, float2 uv, float3 wi, float s1, float s2x, float s2y, BsdfSample &bs, float3 &weight) {
+    float cti = wi.z;
+    if (!(cti > 0.f)) return;
+    float f_i, t0, t1, t2; fresnel(cti, b.eta, f_i, t0, t1, t2);
+    float w = b.plastic_spec_weight, prob_specular = f_i * w, prob_diffuse = (1.f - f_i) * (1.f - w);
+    prob_specular = fdiv(prob_specular, prob_specular + prob_diffuse);
+    prob_diffuse = 1.f - prob_specular;
+    bs.eta = 1.f;
+    if (s1 < prob_specular) {
+        bs.wo = V(-wi.x, -wi.y, wi.z); bs.pdf = prob_specular; bs.sampled_component = 0; bs.sampled_type = F_DELTA_REFLECTION;
+        float v = fdiv(f_i, bs.pdf); float3 val = V(v, v, v);
+        if (b.tex[B200PT_SLOT_PL_SPEC_REFL] >= 0) val = val * tex_eval3(sc, b.tex[B200PT_SLOT_PL_SPEC_REFL], uv);
+        weight = val;
+    } else {
+        bs.wo = square_to_cosine_hemisphere(s2x, s2y);
+        bs.pdf = prob_diffuse * (PT_INV_PI * bs.wo.z); bs.sampled_component = 1; bs.sampled_type = F_DIFFUSE_REFLECTION;
+        float f_o; fresnel(bs.wo.z, b.eta, f_o, t0, t1, t2);
+        float3 val = plastic_diffuse(sc, b, uv);
+        float inv_eta_2 = fdiv(1.f, b.eta * b.eta);
+        weight = val * fdiv(inv_eta_2 * (1.f - f_i) * (1.f - f_o), prob_diffuse);
+    }
+}
+
+} // namespace pt

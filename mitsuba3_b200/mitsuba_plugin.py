@@ -27,7 +27,8 @@ from .transform import _cross, _normalize, _sqnorm, Transform4f
 
 _BSDF_CLASS = {"SmoothDiffuse": abi.BSDF_DIFFUSE, "SmoothConductor": abi.BSDF_CONDUCTOR,
                "SmoothDielectric": abi.BSDF_DIELECTRIC, "Principled": abi.BSDF_PRINCIPLED,
-               "RoughConductor": abi.BSDF_CONDUCTOR, "RoughDielectric": abi.BSDF_DIELECTRIC}
+               "RoughConductor": abi.BSDF_CONDUCTOR, "RoughDielectric": abi.BSDF_DIELECTRIC,
+               "SmoothPlastic": abi.BSDF_PLASTIC}
 
 
 def _np(x, dtype=np.float32):
@@ -102,6 +103,16 @@ class _Extractor:
             d.tex[abi.SLOT_D_SPEC_TRANS] = T("specular_transmittance", 3)
             if cls == "RoughDielectric":
                 self._microfacet(d, desc, T, abi.SLOT_D_ALPHA_U, abi.SLOT_D_ALPHA_V)
+        elif d.type == abi.BSDF_PLASTIC:
+            import re
+            d.eta = float(params[f"{prefix}eta"])
+            d.tex[abi.SLOT_PL_DIFFUSE] = T("diffuse_reflectance", 3, 0.5)
+            d.tex[abi.SLOT_PL_SPEC_REFL] = T("specular_reflectance", 3)
+            # derived members (plastic.cpp:196-208) as the plugin reports them (to_string, plastic.cpp:382-398)
+            num = lambda k: float(re.search(k + r"\s*=\s*\[?([-+0-9.eE]+)", desc).group(1))
+            d.plastic_fdr_int, d.plastic_spec_weight = num("fdr_int"), num("specular_sampling_weight")
+            if int(num("nonlinear")):
+                d.flags |= abi.M_NONLINEAR
         else:
             flags = 0
             slots = [("base_color", abi.SLOT_P_BASE_COLOR, 3, 0), ("roughness", abi.SLOT_P_ROUGHNESS, 1, 0),
@@ -152,6 +163,7 @@ class _Extractor:
     def _guess_class(keys):
         ks = " ".join(keys)
         if "base_color" in ks: return "Principled"
+        if "diffuse_reflectance" in ks: return "SmoothPlastic"
         if "alpha" in ks and ".k." in ks: return "RoughConductor"
         if "alpha" in ks: return "RoughDielectric"
         if "specular_transmittance" in ks or ".eta" in ks and ".k" not in ks and "reflectance.value" not in ks: return "SmoothDielectric"

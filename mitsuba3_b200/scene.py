@@ -9,7 +9,7 @@ Supported plugin types (same property names as the reference):
   ``independent`` sampler (sample_count, seed); shapes ``rectangle`` / ``cube``
   (src/shapes/rectangle.cpp, cube.cpp) and ``mesh`` (packed arrays, as produced
   by the host's loaders); BSDFs ``diffuse`` / ``conductor`` / ``dielectric`` /
-  ``principled`` / ``roughconductor`` / ``roughdielectric`` / ``twosided``; emitters ``area`` / ``constant`` / ``envmap``; textures ``rgb`` / float /
+  ``principled`` / ``roughconductor`` / ``roughdielectric`` / ``plastic`` / ``twosided``; emitters ``area`` / ``constant`` / ``envmap``; textures ``rgb`` / float /
   ``bitmap`` (raw float32 data); ``ref``.
 
 Everything else (XML, OBJ/PLY loaders, spectra, other plugins) stays in the
@@ -82,6 +82,8 @@ class BsdfData:
     clearcoat_srate: float = 1.0
     diff_refl_srate: float = 1.0
     flags: int = 0
+    plastic_fdr_int: float = 0.0
+    plastic_spec_weight: float = 0.0
 
 
 @dataclass
@@ -179,6 +181,7 @@ class Scene:
             cb.tex = (C.c_int32 * abi.MAX_SLOTS)(*b.tex)
             cb.eta, cb.spec_srate, cb.clearcoat_srate, cb.diff_refl_srate = b.eta, b.spec_srate, b.clearcoat_srate, b.diff_refl_srate
             cb.flags = b.flags
+            cb.plastic_fdr_int, cb.plastic_spec_weight = b.plastic_fdr_int, b.plastic_spec_weight
         shapes = (abi.Shape * max(1, len(self.shapes)))()
         for i, s in enumerate(self.shapes):
             cs = shapes[i]
@@ -236,7 +239,17 @@ def _as_transform(t) -> Transform4f:
     return Transform4f(np.asarray(t, f32).reshape(4, 4))
 
 
-_BSDF_TYPES = ("diffuse", "conductor", "roughconductor", "dielectric", "roughdielectric", "principled", "twosided")
+_BSDF_TYPES = ("diffuse", "conductor", "roughconductor", "dielectric", "roughdielectric", "plastic", "principled", "twosided")
+
+
+def fresnel_diffuse_reflectance(eta):
+    """fresnel.h:326-360 in fp32 (fmadd chains / Horner as written there)."""
+    eta = f32(eta); inv_eta = f32(1) / eta
+    approx_1 = fma(f32(0.0636), inv_eta, fma(eta, fma(eta, f32(-1.4399), f32(0.7099)), f32(0.6681)))
+    acc = f32(-1.36881)
+    for c in (4.98554, -7.80989, 6.75335, -3.4793, 0.919317):
+        acc = fma(inv_eta, acc, f32(c))
+    return approx_1 if eta < f32(1) else acc
 
 
 class _Parser:
@@ -331,6 +344,23 @@ class _Parser:
             b.eta = float(f32(f32(lookup_ior(d.get("int_ior"), "bk7")) / f32(lookup_ior(d.get("ext_ior"), "air"))))
             b.tex[abi.SLOT_D_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3)
             b.tex[abi.SLOT_D_SPEC_TRANS] = self.texture(f"{bid}.specular_transmittance", d.get("specular_transmittance"), 3)
+        elif ty == "plastic":
+            # plastic.cpp:156-208
+            b.type = abi.BSDF_PLASTIC
+            b.eta = float(f32(f32(lookup_ior(d.get("int_ior"), "polypropylene")) / f32(lookup_ior(d.get("ext_ior"), "air"))))
+            b.tex[abi.SLOT_PL_DIFFUSE] = self.texture(f"{bid}.diffuse_reflectance", d.get("diffuse_reflectance"), 3, 0.5)
+            b.tex[abi.SLOT_PL_SPEC_REFL] = self.texture(f"{bid}.specular_reflectance", d.get("specular_reflectance"), 3)
+            if bool(d.get("nonlinear", False)):
+                b.flags |= abi.M_NONLINEAR
+            b.plastic_fdr_int = float(fresnel_diffuse_reflectance(f32(1) / f32(b.eta)))
+            def mean(ti):      # Texture::mean (srgb.cpp:117-122; bitmap: average of all texels)
+                t = self.scene.textures[ti]
+                return f32(np.mean(t.data, dtype=np.float64)) if t.kind == abi.TEX_BITMAP else f32((f32(t.value[0]) + f32(t.value[1]) + f32(t.value[2])) / f32(3))
+            if self.scene.textures[b.tex[abi.SLOT_PL_DIFFUSE]].kind == abi.TEX_CHECKERBOARD:
+                raise NotImplementedError("plastic with a checkerboard reflectance: Texture::mean() of checkerboard is not restated")
+            d_mean = mean(b.tex[abi.SLOT_PL_DIFFUSE])
+            s_mean = mean(b.tex[abi.SLOT_PL_SPEC_REFL]) if b.tex[abi.SLOT_PL_SPEC_REFL] >= 0 else f32(1)
+            b.plastic_spec_weight = float(f32(s_mean / f32(d_mean + s_mean)))
         elif ty == "principled":
             self._principled(b, bid, d)
         else:

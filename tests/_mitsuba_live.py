@@ -76,10 +76,15 @@ def main(mode):
           d["small-box"]["to_world"] = mi.ScalarTransform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
           d["large-box"]["bsdf"] = {"type": "ref", "id": "rc"}
           d["back"]["bsdf"] = {"type": "ref", "id": "rb"}
+          d["pl"] = ROUGH_SPECS["plastic_tinted_nonlinear"]
+          d["floor"]["bsdf"] = {"type": "ref", "id": "pl"}
           return d
       sm4 = mi.load_dict(rough(cbox(32, {"type": "path", "max_depth": 8, "block_size": 32})))
       host4 = plug.extract_scene(mi, sm4)
-      assert sorted(hex(b.flags) for b in host4.bsdfs if b.flags) == ["0x10000", "0x10000", "0x30000"]
+      assert sorted(hex(b.flags) for b in host4.bsdfs if b.flags) == ["0x10000", "0x10000", "0x30000", "0x40000"]
+      mine4 = [b for b in mb.load_dict(__import__("conftest").rough_cbox()).bsdfs if b.type == mb.abi.BSDF_PLASTIC][0]
+      got4 = [b for b in host4.bsdfs if b.type == mb.abi.BSDF_PLASTIC][0]
+      assert abs(got4.plastic_fdr_int - mine4.plastic_fdr_int) < 1e-6 and abs(got4.plastic_spec_weight - mine4.plastic_spec_weight) < 1e-6
       ref4 = np.array(mi.render(sm4, seed=0, spp=16))
       img4 = oracle.OracleScene(host4).render(spp=16, seed=0, mode=1, max_depth=8)
       rel = np.abs(img4 - ref4) / np.maximum(np.abs(ref4), 1e-2)

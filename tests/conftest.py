@@ -139,6 +139,9 @@ ROUGH_SPECS = {
     "roughconductor_ggx_tinted": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
                                   "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]},
                                   "specular_reflectance": {"type": "rgb", "value": [0.9, 0.8, 0.7]}},
+    "plastic_default": {"type": "plastic"},
+    "plastic_tinted_nonlinear": {"type": "plastic", "int_ior": 1.9, "diffuse_reflectance": {"type": "rgb", "value": [0.1, 0.27, 0.36]},
+                                 "specular_reflectance": {"type": "rgb", "value": [0.9, 0.7, 0.8]}, "nonlinear": True},
     "twosided_roughconductor_ggx": {"type": "twosided", "bsdf": {"type": "roughconductor", "distribution": "ggx", "alpha": 0.15,
                                                                    "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}}},
 }
@@ -156,4 +159,6 @@ def rough_cbox(res=32, rfilter="box", spp=16, max_depth=8):
     d["small-box"]["to_world"] = mb.Transform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
     d["large-box"]["bsdf"] = {"type": "ref", "id": "rc"}
     d["back"]["bsdf"] = {"type": "ref", "id": "rb"}
+    d["pl"] = copy.deepcopy(ROUGH_SPECS["plastic_tinted_nonlinear"])
+    d["floor"]["bsdf"] = {"type": "ref", "id": "pl"}
     return d
