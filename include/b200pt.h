@@ -283,6 +283,15 @@ B200PT_API b200pt_status b200pt_render_backward_device(b200pt_scene *scene,
                                             const b200pt_render_params *p,
                                             const float *grad_in_device,
                                             void *cuda_stream);
+/* ---- forward mode: replaces RBIntegrator.render_forward (common.py:560-623) + PRBIntegrator.sample
+ *      Forward mode. The parameter tangents (dr.set_grad of the reference) are written per
+ *      differentiable texture, in the layout of the texture's data; out_host: H*W*3 = d(image). */
+B200PT_API b200pt_status b200pt_tangent_zero(b200pt_scene *scene);
+B200PT_API b200pt_status b200pt_tangent_write(b200pt_scene *scene, uint32_t tex,
+                                   const float *host_in, size_t n);
+B200PT_API b200pt_status b200pt_render_forward(b200pt_scene *scene,
+                                    const b200pt_render_params *p, float *out_host);
+
 B200PT_API b200pt_status b200pt_grad_zero(b200pt_scene *scene);
 /* Copy the gradient of differentiable texture `tex` to the host. */
 B200PT_API b200pt_status b200pt_grad_read(b200pt_scene *scene, uint32_t tex,

@@ -110,6 +110,7 @@ SYMBOLS = [
     "b200pt_scene_create", "b200pt_scene_destroy", "b200pt_scene_update_texture",
     "b200pt_render", "b200pt_render_accumulate", "b200pt_develop",
     "b200pt_render_backward", "b200pt_render_backward_device", "b200pt_grad_zero",
+    "b200pt_tangent_zero", "b200pt_tangent_write", "b200pt_render_forward",
     "b200pt_grad_read", "b200pt_grad_device_view", "b200pt_grad_offset",
     "b200pt_ray_intersect", "b200pt_ray_test", "b200pt_bsdf_eval_pdf_sample", "b200pt_env_query",
     "b200pt_get_stats", "b200pt_abi_sizeof",
@@ -154,6 +155,9 @@ def load() -> C.CDLL:
     lib.b200pt_ray_intersect.argtypes = [vp, u32, f32p, f32p, f32p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     lib.b200pt_ray_test.argtypes = [vp, u32, f32p, C.POINTER(C.c_uint8)]
     lib.b200pt_bsdf_eval_pdf_sample.argtypes = [vp, u32, u32, f32p, f32p]
+    lib.b200pt_tangent_zero.argtypes = [vp]
+    lib.b200pt_tangent_write.argtypes = [vp, u32, f32p, C.c_size_t]
+    lib.b200pt_render_forward.argtypes = [vp, C.POINTER(RenderParams), f32p]
     lib.b200pt_env_query.argtypes = [vp, u32, f32p, f32p]
     lib.b200pt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.b200pt_abi_sizeof.argtypes = [C.c_int]

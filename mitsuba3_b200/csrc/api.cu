@@ -167,6 +167,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     s->grad_floats = grad_off;
     d.n_textures = desc->n_textures;
     { float *g = nullptr; S_TRY(cudaMalloc(&g, std::max<size_t>(grad_off, 1) * sizeof(float))); s->allocs.push_back(g); S_TRY(cudaMemset(g, 0, std::max<size_t>(grad_off, 1) * sizeof(float))); d.grad = g; }
+    { float *g = nullptr; S_TRY(cudaMalloc(&g, std::max<size_t>(grad_off, 1) * sizeof(float))); s->allocs.push_back(g); S_TRY(cudaMemset(g, 0, std::max<size_t>(grad_off, 1) * sizeof(float))); d.tangent = g; }
 
     // ---- bsdfs / emitters ----------------------------------------------------
     std::vector<DevBsdf> hb(desc->n_bsdfs);
@@ -420,12 +421,13 @@ static int grid_for(const b200pt_scene *s, size_t n) {
 }
 
 // One chunk of the wavefront: lanes [pix0*spp, (pix0+npix)*spp) of this shard.
-// mode 0: primal (path / prb) -> lane_result; mode 1: PRB adjoint replay.
+// mode 0: primal (path / prb) -> lane_result; mode 1: PRB adjoint replay; mode 2: PRB forward-mode
+// replay (lane_result <- dL of every sample).
 static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStream_t st) {
     Wavefront &w = s->wf;
     const DevScene &d = s->dev;
     uint32_t lanes = cfg.chunk_lanes;
-    cfg.adjoint = mode == 1;
+    cfg.adjoint = mode >= 1; cfg.forward = mode == 2;
     CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
     int g_all = grid_for(s, lanes);
     launch_generate(d, cfg, s->pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
@@ -617,6 +619,55 @@ b200pt_status b200pt_render_backward(b200pt_scene *s, const b200pt_render_params
     CU_TRY(cudaMemcpyAsync(s->grad_in_dev, grad_in_host, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     b200pt_status e = b200pt_render_backward_device(s, p, s->grad_in_dev, s->stream); if (e) return e;
     CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
+}
+
+// RBIntegrator.render_forward (common.py:560-623): primal pass (L per lane), forward-mode replay
+// (dL per lane, the parameter tangents come from b200pt_tangent_write), splat + develop of the dL.
+b200pt_status b200pt_render_forward(b200pt_scene *s, const b200pt_render_params *p_, float *out_host) {
+    b200pt_status vs = validate_params(s, p_); if (vs) return vs;
+    if (!out_host) return fail(B200PT_ERR_INVALID, "null argument");
+    b200pt_render_params p = *p_; p.prb = 1;
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    size_t npix = (size_t) s->dev.crop_w * s->dev.crop_h;
+    CU_TRY(cudaMemsetAsync(s->film_own, 0, npix * 4 * sizeof(float), st));
+    b200pt_status e = ensure_pix_ids(s, &p); if (e) return e;
+    begin_stats(s, st);
+    if (p.max_depth != 0 && s->n_pix_ids != 0) {
+        RenderCfg cfg = make_cfg(s, &p);
+        size_t cpx = chunk_pixels(s, &p, s->n_pix_ids);
+        e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
+        for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
+            size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
+            cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
+            e = run_chunk(s, cfg, 0, st); if (e) return e;      // primal: L per lane
+            e = run_chunk(s, cfg, 2, st); if (e) return e;      // forward replay: dL per lane
+            launch_splat(s->dev, cfg, s->pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+            s->stats.kernel_launches++;
+        }
+    }
+    e = end_stats(s, st, (uint64_t) s->n_pix_ids * p.spp); if (e) return e;
+    e = b200pt_develop(s, s->film_own, s->out_dev, st); if (e) return e;
+    CU_TRY(cudaMemcpyAsync(out_host, s->out_dev, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_tangent_zero(b200pt_scene *s) {
+    if (!s) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaMemsetAsync((void *) s->dev.tangent, 0, std::max<size_t>(s->grad_floats, 1) * sizeof(float), s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
+}
+
+b200pt_status b200pt_tangent_write(b200pt_scene *s, uint32_t tex, const float *host_in, size_t n) {
+    size_t off = 0, cnt = 0;
+    b200pt_status e = b200pt_grad_offset(s, tex, &off, &cnt); if (e) return e;
+    if (n != cnt || !host_in) return fail(B200PT_ERR_INVALID, "tangent size mismatch");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaMemcpy((void *) (s->dev.tangent + off), host_in, n * sizeof(float), cudaMemcpyHostToDevice));
     return B200PT_OK;
 }
 

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
         buf.prev[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PF_PREV_DELTA | PF_ALIVE));
         buf.rng[i] = make_uint4((uint32_t) rng.state, (uint32_t) (rng.state >> 32), lane, i);
         buf.result[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cfg.adjoint) { buf.adj_L[i] = adj_L_lane[i]; buf.adj_dL[i] = adj_dL_lane[i]; }
+        if (cfg.adjoint) { buf.adj_L[i] = adj_L_lane[i]; buf.adj_dL[i] = cfg.forward ? make_float4(1.f, 1.f, 1.f, 0.f) : adj_dL_lane[i]; }
     }
 }
 
@@ -524,6 +524,27 @@ PT_DEV void warp_scatter3(const DevScene &sc, int32_t tex, float2 uv, float3 g) 
     }
 }
 
+// Forward mode: the contraction of a scatter request (tex, uv, g) with the parameter tangents,
+// i.e. sum_texels w * g (.) d(parameter)[texel] -- the transpose of warp_scatter3.
+PT_DEV float3 tangent_dot(const DevScene &sc, int32_t tex, float2 uv, float3 g) {
+    if (tex < 0) return V(0.f, 0.f, 0.f);
+    const DevTexture &t = sc.textures[tex];
+    if (!t.differentiable) return V(0.f, 0.f, 0.f);
+    TexTaps tp; tp.n = 0;
+    if (t.kind == B200PT_TEX_CONST) { tp.n = 1; tp.idx[0] = 0; tp.w[0] = 1.f; }
+    else if (t.kind == B200PT_TEX_CHECKERBOARD) { tp.n = 1; tp.idx[0] = checker_masks_equal(t, uv) ? 0 : 1; tp.w[0] = 1.f; }
+    else tex_lookup(t, uv, tp);
+    const float *tg = sc.tangent + t.grad_offset;
+    int C = t.channels;
+    float3 acc = V(0.f, 0.f, 0.f);
+    for (int k = 0; k < tp.n; ++k) {
+        const float *q = tg + (size_t) tp.idx[k] * C;
+        float3 tv = C == 1 ? V(q[0], q[0], q[0]) : V(q[0], q[1], q[2]);
+        acc = V(__fmaf_rn(tp.w[k] * tv.x, g.x, acc.x), __fmaf_rn(tp.w[k] * tv.y, g.y, acc.y), __fmaf_rn(tp.w[k] * tv.z, g.z, acc.z));
+    }
+    return acc;
+}
+
 // BSDF parameter adjoint at one vertex (prb.py:263-313 restricted to texture parameters):
 //   d/dtheta [ g_dir . f(wo_em; theta) + g_ind . f(wo_s; theta) / f(wo_s) ]
 // Returns the gradient w.r.t. the (single) differentiable colour texture of the model and its slot.
@@ -576,6 +597,7 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
     const uint32_t lane_id = threadIdx.x & 31u;
     const uint32_t warp_stride = gridDim.x * blockDim.x;
     const bool prb = cfg.prb != 0;
+    const bool fwd = ADJOINT && cfg.forward != 0;     // forward-mode replay: `result` carries the sample's dL
     uint32_t n_bounces = 0, n_shadow = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
         uint32_t qi = base + lane_id;
@@ -616,13 +638,15 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                 float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
                 bool em_active = si.wi.z > 0.f && (prb || prev_bsdf_pdf > 0.f);
                 float3 rad = em_active ? tex_eval3(sc, sc.emitters[sh.emitter].radiance_tex, si.uv) : V(0.f, 0.f, 0.f);
-                if (prb) { Le = (throughput * mis_bsdf) * rad; result = result + Le; }
+                if (prb) { Le = (throughput * mis_bsdf) * rad; if (!fwd) result = result + Le; }
                 else { Le = throughput * (rad * mis_bsdf); result = vfma(throughput, rad * mis_bsdf, result); }
                 if (ADJOINT && em_active) { gt0 = sc.emitters[sh.emitter].radiance_tex; guv0 = si.uv; gv0 = dL * (throughput * mis_bsdf); }
             }
             bool active_next = depth + 1 < cfg.max_depth;
             if (!active_next) {
-                if (!ADJOINT) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
+                if (fwd) result = result + tangent_dot(sc, gt0, guv0, gv0);     // forward mode: dLe
+                if (!ADJOINT || fwd) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
+                if (fwd) gt0 = -1;
             } else {
                 // ---- emitter sampling (path.cpp:238-259): the two randoms are always drawn (JIT semantics)
                 const bool smooth = TYPE == B200PT_BSDF_DIFFUSE || TYPE == B200PT_BSDF_PRINCIPLED || (bsdf.flags & (B200PT_M_ROUGH | PT_M_PLASTIC));   // BSDFFlags::Smooth (path.cpp:238)
@@ -683,8 +707,13 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                         gv2 = dL * V(rad.x != 0.f ? fdiv(Lr_dir.x, rad.x) : 0.f, rad.y != 0.f ? fdiv(Lr_dir.y, rad.y) : 0.f, rad.z != 0.f ? fdiv(Lr_dir.z, rad.z) : 0.f);
                     }
                 }
+                if (fwd) {
+                    // forward mode: dL of this vertex = <derivative coefficients, parameter tangents>
+                    result = result + tangent_dot(sc, gt0, guv0, gv0) + tangent_dot(sc, gt1, guv1, gv1) + tangent_dot(sc, gt2, guv2, gv2);
+                    gt0 = gt1 = gt2 = -1;
+                }
                 if (!active && !has_shadow) {
-                    if (!ADJOINT) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
+                    if (!ADJOINT || fwd) lane_result[rs.w] = make_float4(result.x, result.y, result.z, 0.f);
                 } else {
                     write_next = true;
                     uint32_t nf = (depth + 1) | ((br.bs.sampled_type & F_DELTA) ? PF_PREV_DELTA : 0u) | (has_shadow ? PF_HAS_SHADOW : 0u) | (active ? PF_ALIVE : 0u);
@@ -755,11 +784,16 @@ __global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ Dev
             bool em_active = prb ? !(cfg.hide_emitters && depth == 0) : prev_bsdf_pdf > 0.f;
             float3 crad = sc.env_type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, sc.env_radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
             float3 rad = em_active ? env_eval(sc.env, crad, d) : V(0.f, 0.f, 0.f);
-            if (prb) result = result + (throughput * mis_bsdf) * rad;
+            const bool fwd = ADJOINT && cfg.forward != 0;
+            if (fwd) {
+                // forward mode: `result` carries dL; dLe = (beta * mis) (.) d(radiance) for the constant emitter
+                if (em_active && sc.env_type == B200PT_EMITTER_CONSTANT)
+                    result = result + tangent_dot(sc, sc.env_radiance_tex, make_float2(0.f, 0.f), throughput * mis_bsdf);
+            } else if (prb) result = result + (throughput * mis_bsdf) * rad;
             else result = vfma(throughput, rad * mis_bsdf, result);
             // path.cpp:115,343: a primary ray that sees only the hidden environment is not a valid sample
             if (!prb && cfg.hide_emitters && depth == 0) result = V(0.f, 0.f, 0.f);
-            if (!ADJOINT) lane_result[cur.rng[slot].w] = make_float4(result.x, result.y, result.z, 0.f);
+            if (!ADJOINT || fwd) lane_result[cur.rng[slot].w] = make_float4(result.x, result.y, result.z, 0.f);
             else if (em_active && sc.env_type == B200PT_EMITTER_CONSTANT) {
                 float4 dl = cur.adj_dL[slot];
                 gt = sc.env_radiance_tex; gv = V(dl.x, dl.y, dl.z) * (throughput * mis_bsdf);

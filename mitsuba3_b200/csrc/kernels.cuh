@@ -45,6 +45,8 @@ struct RenderCfg {
     uint32_t spp;
     uint32_t max_depth, rr_depth;
     int32_t hide_emitters, prb, adjoint;
+    int32_t forward;       // with adjoint = 1: forward-mode replay (render_forward): dL = 1, the parameter
+                           // derivatives are contracted with DevScene::tangent and summed into `result`
     uint32_t chunk_pix0;   // first local pixel of the chunk (index into pix_ids)
     uint32_t chunk_lanes;  // lanes in this chunk
 };

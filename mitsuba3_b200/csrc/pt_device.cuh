@@ -157,6 +157,7 @@ struct DevScene {
     const DevShape *shapes; const DevBsdf *bsdfs; const DevEmitter *emitters; const DevTexture *textures;
     uint32_t n_shapes, n_bsdfs, n_emitters, n_textures;
     float *grad;               // flat gradient buffer of all differentiable textures
+    const float *tangent;      // forward mode: d(parameter) in the same layout (b200pt_tangent_write)
     // The four tables above live in ONE contiguous blob (shapes | bsdfs | emitters | textures);
     // kernels stage it into shared memory when it is small (kernels.cu: stage_tables).
     const unsigned char *tables; uint32_t tables_bytes, off_bsdfs, off_emitters, off_textures;

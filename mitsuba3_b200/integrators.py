@@ -179,8 +179,24 @@ class PRBIntegrator(PathIntegrator):
     prb = True
     default_max_depth = 6      # common.py:31
 
-    def render_forward(self, *a, **k):
-        raise NotImplementedError("forward-mode differentiation is outside the hot-path scope (SURVEY.md 8)")
+    # -- RBIntegrator.render_forward (common.py:560-623) -------------------------------
+    def render_forward(self, scene: Scene, params: dict, sensor=0, seed: int = 0, spp: int = 0, device: int = 0) -> np.ndarray:
+        """Forward-mode derivative of the image: ``params`` maps parameter names to their tangents
+        (what ``dr.set_grad`` attaches in the reference); returns d(image) as an (H, W, 3) array."""
+        ds = device_scene(scene, device)
+        names = scene.parameters()
+        f = C.POINTER(C.c_float)
+        abi.check(ds.lib.b200pt_tangent_zero(ds.h), ds.lib)
+        for k, v in params.items():
+            i = names[k]
+            if not scene.textures[i].differentiable:
+                raise RuntimeError(f"parameter {k!r} is not differentiable")
+            d = np.ascontiguousarray(v, np.float32).reshape(-1)
+            abi.check(ds.lib.b200pt_tangent_write(ds.h, i, d.ctypes.data_as(f), d.size), ds.lib)
+        p = self.params(scene, seed, spp)
+        out = np.empty(scene.film_shape, np.float32)
+        abi.check(ds.lib.b200pt_render_forward(ds.h, C.byref(p), out.ctypes.data_as(f)), ds.lib)
+        return out
 
     # -- RBIntegrator.render_backward (common.py:625-783) ------------------------------
     def render_backward(self, scene: Scene, grad_in, params=None, sensor=0, seed: int = 0, spp: int = 0, device: int = 0,

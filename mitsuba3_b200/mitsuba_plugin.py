@@ -334,6 +334,15 @@ def register(mi):
                 if name in params and dr.grad_enabled(params[name]):
                     dr.accum_grad(params[name], type(params[name])(g))     # opt.step() reads dr.grad (drjit/opt.py:451)
 
+        def render_forward(self, scene, params, sensor=0, seed=0, spp=0):
+            # tangents = the gradients the caller attached with dr.set_grad (common.py:536-539)
+            host = self._host_scene(scene, sensor)
+            self._sync_params(host, scene)
+            names = host.parameters()
+            tangents = {k: np.array(dr.grad(params[k]), np.float32) for k in names
+                        if k in params and host.textures[names[k]].differentiable and dr.grad_enabled(params[k])}
+            return mi.TensorXf(self._impl.render_forward(host, tangents, seed=int(seed), spp=int(spp)))
+
     mi.register_integrator("b200_path", lambda props: B200Path(props))
     mi.register_integrator("b200_prb", lambda props: B200PRB(props))
     return B200Path, B200PRB

@@ -44,6 +44,9 @@ def load():
         lib.orc_render.argtypes = [vp, C.POINTER(abi.RenderParams), C.c_int, f32p, f32p, C.POINTER(OrcStats)]
         lib.orc_render_backward.argtypes = [vp, C.POINTER(abi.RenderParams), f32p]
         lib.orc_grad_zero.argtypes = [vp]
+        lib.orc_render_forward.argtypes = [vp, C.POINTER(abi.RenderParams), f32p]
+        lib.orc_tangent_write.argtypes = [vp, C.c_uint32, f32p, C.c_size_t]
+        lib.orc_tangent_zero.argtypes = [vp]
         lib.orc_grad_read.argtypes = [vp, C.c_uint32, f32p, C.c_size_t]
         lib.orc_ray_intersect.argtypes = [vp, C.c_uint32, f32p, f32p, f32p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.orc_ray_test.argtypes = [vp, C.c_uint32, f32p, C.POINTER(C.c_uint8)]
@@ -114,6 +117,18 @@ class OracleScene:
         p = make_params(self.scene, spp=spp, seed=seed, prb=1, **kw)
         g = np.ascontiguousarray(grad_in, np.float32)
         self.lib.orc_render_backward(self.h, C.byref(p), _fp(g))
+
+    def render_forward(self, tangents, spp=None, seed=0, **kw):
+        """Forward-mode derivative image for the parameter tangents {texture index: array}."""
+        H, W, _ = self.scene.film_shape
+        p = make_params(self.scene, spp=spp, seed=seed, prb=1, **kw)
+        self.lib.orc_tangent_zero(self.h)
+        for tex, v in tangents.items():
+            d = np.ascontiguousarray(v, np.float32).reshape(-1)
+            assert self.lib.orc_tangent_write(self.h, tex, _fp(d), d.size) == 0
+        out = np.zeros((H, W, 3), np.float32)
+        self.lib.orc_render_forward(self.h, C.byref(p), _fp(out))
+        return out
 
     def grad_zero(self):
         self.lib.orc_grad_zero(self.h)

@@ -121,3 +121,38 @@ def test_inverse_rendering_loop_converges(built):
     # the loss sits on a Monte Carlo noise floor (32 spp vs the 256 spp reference): the parameters are the criterion
     assert np.abs(p.detach().numpy() - target).max() < 0.08, (p, target, losses[::8])
     update_params(sc, {key: target})
+
+
+def test_forward_mode_matches_oracle_fd_and_is_the_transpose_of_backward(built):
+    """b200pt_render_forward (RBIntegrator.render_forward, common.py:560-623): (a) equals the oracle's
+    forward replay at equal seeds, (b) equals central finite differences of the primal at equal seeds,
+    (c) <grad_in, forward(v)> == <backward(grad_in), v> (same samples: exact transpose up to fp32)."""
+    from oracle import oracle
+    from mitsuba3_b200.integrators import PRBIntegrator, update_params
+    tex = (0.3 + 0.4 * np.random.default_rng(1).random((8, 8, 3))).astype(np.float32)
+    sc = _prb_scene(rfilter="gaussian", tex=tex)
+    integ = PRBIntegrator(max_depth=5)
+    P = sc.parameters()
+    rng = np.random.default_rng(7)
+    tangents = {"tex.reflectance.data": rng.random(tex.shape).astype(np.float32),
+                "white.reflectance.value": rng.random(3).astype(np.float32),
+                "light.emitter.radiance.value": rng.random(3).astype(np.float32)}
+    fwd = integ.render_forward(sc, tangents, seed=4, spp=32)
+    o = oracle.OracleScene(sc)
+    ref = o.render_forward({P[k]: v for k, v in tangents.items()}, spp=32, seed=4, max_depth=5)
+    assert np.isfinite(fwd).all() and np.abs(ref).max() > 0
+    assert np.linalg.norm(fwd - ref) / np.linalg.norm(ref) < 2e-3
+    # (c) transpose test
+    gi = rng.normal(size=sc.film_shape).astype(np.float32)
+    g = integ.render_backward(sc, gi, seed=4, spp=32)
+    lhs = float((gi.astype(np.float64) * fwd).sum())
+    rhs = float(sum((g[k].astype(np.float64) * v).sum() for k, v in tangents.items()))
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+    # (b) finite differences of the primal (prb estimator) along the same direction
+    base = {k: sc.textures[P[k]].array().copy() for k in tangents}
+    h = 2e-3
+    update_params(sc, {k: base[k] + h * tangents[k] for k in tangents}); a = integ.render(sc, seed=4, spp=32)
+    update_params(sc, {k: base[k] - h * tangents[k] for k in tangents}); b = integ.render(sc, seed=4, spp=32)
+    update_params(sc, base)
+    fd = (a.astype(np.float64) - b) / (2 * h)
+    assert np.linalg.norm(fwd - fd) / np.linalg.norm(fd) < 2e-2
