@@ -3,14 +3,18 @@
 // One wavefront per bounce:
 //
 //   k_generate      lane -> pixel, TEA/PCG32 seeding, primary ray          (integrator.cpp:322-339,448-485)
-//   k_trace         persistent BVH traversal: resolves the pending NEE shadow ray of
+//   k_trace_dyn     persistent BVH traversal with dynamic work fetch (default; k_trace is the
+//                   static grid-stride variant): resolves the pending NEE shadow ray of
 //                   every slot (Scene::ray_test), then the closest hit of its path ray
 //                   (Scene::ray_intersect_preliminary) and bins the slot into the
-//                   queue of the material it hit (warp-ballot bucket pass)
+//                   queue of the material it hit, or into the queue of the rays that
+//                   left the scene (warp-ballot bucket pass)
+//   k_shade_env     escaped rays: environment emitter (envmap / constant) x MIS, path ends
 //   k_shade<TYPE>   one branch-flattened kernel per BSDF model over its material
 //                   queue: surface interaction, emitter hit + MIS, NEE sample, BSDF
 //                   eval/sample, russian roulette; writes the survivors COMPACTED
-//                   into the other state buffer (warp-aggregated slot allocation)
+//                   into the other state buffer (warp-aggregated slot allocation).
+//                   <TYPE, true>: PRB replay -- adjoint (gradient scatter) or forward mode
 //   k_splat_*       ImageBlock::put (box / gaussian), k_develop: HDRFilm::develop
 //
 // The path state lives in HBM as structure-of-arrays float4 vectors (kernels.cuh).
