@@ -162,14 +162,15 @@ typedef struct b200pt_emitter {
     int32_t radiance_tex; /* area / constant: texture index (constant: kind CONST)   */
     float   sampling_weight;
     int32_t type;         /* B200PT_EMITTER_*                                        */
-    /* envmap only. `env_data` is the latitude-longitude map as float32 RGB, row-major
-     * env_height x env_width x 3, real columns only (the `data` parameter of the plugin
-     * without its two halo columns, envmap.cpp:155-192). The library adds the periodic
-     * halo, and builds the luminance x sin(theta) Hierarchical2D warp
-     * (envmap.cpp:474-529, core/distr_2d.h:403-540) and the bounding sphere of the
-     * scene (envmap.cpp:260-274) itself. */
-    uint32_t env_width, env_height;   /* >= 2 x 3 (Bitmap::pad_to, envmap.cpp:141)   */
-    const float *env_data;
+    /* envmap: `radiance_tex` is a B200PT_TEX_BITMAP texture (3 channels) holding the
+     * latitude-longitude map, row-major height x width, REAL columns only (the `data`
+     * parameter of the plugin without its two halo columns, envmap.cpp:155-192); at least
+     * 2 x 3 texels (Bitmap::pad_to, envmap.cpp:141). Its wrap / filter fields are ignored.
+     * The library adds the periodic halo, and builds the luminance x sin(theta)
+     * Hierarchical2D warp (envmap.cpp:474-529, core/distr_2d.h:403-540) and the bounding
+     * sphere of the scene (envmap.cpp:260-274) itself; b200pt_scene_update_texture on that
+     * texture rebuilds them (EnvironmentMapEmitter::parameters_changed, envmap.cpp:207-258).
+     * If the texture is differentiable, PRB accumulates d/d(data) into its gradient. */
     float   env_scale;                /* `scale` (envmap.cpp:196)                    */
     int32_t env_mis_compensation;     /* `mis_compensation` (envmap.cpp:197,497-517) */
     float   to_world[16];             /* row-major; only the linear 3x3 part is used */

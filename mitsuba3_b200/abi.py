@@ -67,8 +67,7 @@ class Shape(C.Structure):
 
 class Emitter(C.Structure):
     _fields_ = [("shape", C.c_int32), ("radiance_tex", C.c_int32), ("sampling_weight", C.c_float),
-                ("type", C.c_int32), ("env_width", C.c_uint32), ("env_height", C.c_uint32),
-                ("env_data", C.POINTER(C.c_float)), ("env_scale", C.c_float),
+                ("type", C.c_int32), ("env_scale", C.c_float),
                 ("env_mis_compensation", C.c_int32), ("to_world", C.c_float * 16),
                 ("to_world_inv", C.c_float * 16)]
 

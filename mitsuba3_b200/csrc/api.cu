@@ -66,6 +66,9 @@ struct b200pt_scene {
     std::vector<cudaEvent_t> trace_events; size_t trace_ev_used = 0;
     bool profile = false;
     b200pt_stats stats;
+    // envmap emitter: its `data` texture and the device buffers rebuilt when that texture is updated
+    int32_t env_tex = -1; bool env_mis_compensation = false; float *env_dev_tex = nullptr, *env_dev_warp = nullptr;
+    uint32_t env_w = 0, env_h = 0;
 };
 
 template <typename T>
@@ -199,18 +202,23 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         if (env_index >= 0) S_FAIL(B200PT_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:63-65
         env_index = (int) i;
         he[i].shape = -1;
-        henv.type = e.type; d.env_type = e.type; d.env_emitter = (int32_t) i; d.env_radiance_tex = e.radiance_tex; henv.emitter_index = (int32_t) i; henv.radiance_tex = e.radiance_tex; henv.scale = e.env_scale;
+        henv.type = e.type; d.env_type = e.type; d.env_emitter = (int32_t) i; d.env_radiance_tex = e.radiance_tex; d.env_scale = e.env_scale; henv.emitter_index = (int32_t) i; henv.radiance_tex = e.radiance_tex; henv.scale = e.env_scale;
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { henv.m[r * 3 + c] = e.to_world[r * 4 + c]; henv.mi[r * 3 + c] = e.to_world_inv[r * 4 + c]; }
         if (e.type == B200PT_EMITTER_CONSTANT) {
             if (e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures || desc->textures[e.radiance_tex].kind != B200PT_TEX_CONST)
                 S_FAIL(B200PT_ERR_INVALID, "constant emitter: expected a non-spatially varying radiance");                // constant.cpp:64
         } else {
+            if (e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures) S_FAIL(B200PT_ERR_INVALID, "envmap: radiance_tex must name the bitmap texture holding the map");
+            const b200pt_texture &et = desc->textures[e.radiance_tex];
+            if (et.kind != B200PT_TEX_BITMAP || et.channels != 3 || !et.data) S_FAIL(B200PT_ERR_INVALID, "envmap: the map must be a 3-channel bitmap texture");
             EnvHost eh;
-            if (!build_envmap(e, eh)) S_FAIL(B200PT_ERR_INVALID, "envmap: need float32 RGB data of at least 2 x 3 texels");
+            if (!build_envmap(et.data, (uint32_t) et.width, (uint32_t) et.height, e.env_mis_compensation != 0, eh)) S_FAIL(B200PT_ERR_INVALID, "envmap: need float32 RGB data of at least 2 x 3 texels");
             if (eh.lvl_width.size() > (size_t) ENV_MAX_LEVELS) S_FAIL(B200PT_ERR_UNSUPPORTED, "envmap resolution too large");
             float *dt = nullptr, *dw = nullptr;
             S_TRY(dev_upload(s, eh.tex.data(), eh.tex.size(), &dt)); S_TRY(dev_upload(s, eh.warp.data(), eh.warp.size(), &dw));
-            henv.tex = (const float4 *) dt; henv.warp = dw; henv.W = e.env_width; henv.H = e.env_height;
+            henv.tex = (const float4 *) dt; henv.warp = dw; henv.W = (uint32_t) et.width; henv.H = (uint32_t) et.height;
+            s->env_tex = e.radiance_tex; s->env_mis_compensation = e.env_mis_compensation != 0; s->env_dev_tex = dt; s->env_dev_warp = dw; s->env_w = (uint32_t) et.width; s->env_h = (uint32_t) et.height;
+            htex[e.radiance_tex].wrap = PT_WRAP_ENVMAP;      // gradient / tangent taps follow eval_spectrum (pt_device.cuh: tex_lookup)
             henv.n_levels = (uint32_t) eh.lvl_width.size();
             for (size_t l = 0; l < eh.lvl_width.size(); ++l) { henv.lvl_width[l] = eh.lvl_width[l]; henv.lvl_offset[l] = eh.lvl_offset[l]; }
             for (int k = 0; k < 2; ++k) { henv.patch_size[k] = eh.patch_size[k]; henv.inv_patch_size[k] = eh.inv_patch_size[k]; henv.max_patch_index[k] = eh.max_patch_index[k]; }
@@ -338,7 +346,17 @@ b200pt_status b200pt_scene_update_texture(b200pt_scene *s, uint32_t tex, const f
     if (tex >= s->tex.size() || n != s->tex[tex].n) return fail(B200PT_ERR_INVALID, "texture index/size mismatch");
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    if (s->tex[tex].kind == B200PT_TEX_BITMAP) CU_TRY(cudaMemcpy(s->tex[tex].dev_data, host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (s->tex[tex].kind == B200PT_TEX_BITMAP) {
+        CU_TRY(cudaMemcpy(s->tex[tex].dev_data, host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+        if ((int32_t) tex == s->env_tex) {
+            // EnvironmentMapEmitter::parameters_changed (envmap.cpp:207-258): refresh the halo texture and
+            // rebuild the sampling distribution (same sizes: the device buffers are reused)
+            EnvHost eh;
+            if (!build_envmap(host_data, s->env_w, s->env_h, s->env_mis_compensation, eh)) return fail(B200PT_ERR_INVALID, "envmap rebuild failed");
+            CU_TRY(cudaMemcpy(s->env_dev_tex, eh.tex.data(), eh.tex.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(s->env_dev_warp, eh.warp.data(), eh.warp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
     else {
         const DevTexture *dt = s->dev.textures + tex;
         int ch = s->tex[tex].channels;

@@ -87,14 +87,13 @@ static void build_hierarchy(const float *data, uint32_t sx, uint32_t sy, EnvHost
     }
 }
 
-bool build_envmap(const b200pt_emitter &em, EnvHost &out) {
-    uint32_t W = em.env_width, H = em.env_height;
-    if (W < 2 || H < 3 || !em.env_data || (uint64_t) (W + 2) * H >= (1ull << 30)) return false;
+bool build_envmap(const float *env_data, uint32_t W, uint32_t H, bool mis_compensation, EnvHost &out) {
+    if (W < 2 || H < 3 || !env_data || (uint64_t) (W + 2) * H >= (1ull << 30)) return false;
     uint32_t sw = W + 2;
     out.tex.assign((size_t) sw * H * 4, 0.f);
     for (uint32_t y = 0; y < H; ++y) {
         float *row = out.tex.data() + (size_t) y * sw * 4;
-        for (uint32_t x = 0; x < W; ++x) std::memcpy(row + (size_t) (x + 1) * 4, em.env_data + ((size_t) y * W + x) * 3, 3 * sizeof(float));
+        for (uint32_t x = 0; x < W; ++x) std::memcpy(row + (size_t) (x + 1) * 4, env_data + ((size_t) y * W + x) * 3, 3 * sizeof(float));
         std::memcpy(row, row + (size_t) W * 4, 4 * sizeof(float));                    // col 0   <- last real column
         std::memcpy(row + (size_t) (W + 1) * 4, row + 4, 4 * sizeof(float));          // col W+1 <- first real column
     }
@@ -107,7 +106,7 @@ bool build_envmap(const b200pt_emitter &em, EnvHost &out) {
             lum[(size_t) y * rx + x] = c[0] * 0.212671f + c[1] * 0.715160f + c[2] * 0.072169f;
         }
     float offset = 0.f;
-    if (em.env_mis_compensation) {
+    if (mis_compensation) {
         float min_lum = std::numeric_limits<float>::infinity(); double acc = 0.0;
         for (uint32_t y = 0; y < ry; ++y)
             for (uint32_t x = 0; x < rx - 1u; ++x) { float l = lum[(size_t) y * rx + x]; min_lum = std::fmin(min_lum, l); acc += (double) l; }

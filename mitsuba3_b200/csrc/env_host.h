@@ -17,8 +17,9 @@ struct EnvHost {
     uint32_t max_patch_index[2];
 };
 
-// Builds texture + warp of an `envmap` emitter. Returns false on an invalid descriptor.
-bool build_envmap(const b200pt_emitter &em, EnvHost &out);
+// Builds texture + warp of an `envmap` emitter from its lat-long map `data` (height x width x 3,
+// real columns). Returns false on an invalid size.
+bool build_envmap(const float *data, uint32_t width, uint32_t height, bool mis_compensation, EnvHost &out);
 
 // Bounding sphere of all vertices (8 floats per vertex, position first), inflated as the
 // environment emitters do; center[3], radius.

@@ -702,11 +702,13 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                     float3 g_dir = active_em ? dL * ((beta_vertex * mis_em) * em_weight) : V(0.f, 0.f, 0.f);
                     float3 g_ind = active ? dL * L : V(0.f, 0.f, 0.f);
                     gv1 = bsdf_backward<TYPE>(sc, bsdf, si.uv, si.wi, wo, br.bs.wo, g_dir, g_ind, gt1); guv1 = si.uv;
-                    if (active_em && sc.emitters[ds.emitter].type != B200PT_EMITTER_ENVMAP) {
-                        // emitter radiance inside em_weight = radiance / pdf (area.cpp:161); the envmap
-                        // `data` parameter is not differentiated on this path
+                    if (active_em) {
+                        // emitter radiance inside em_weight = radiance / pdf (area.cpp:161, envmap.cpp:374-377;
+                        // the sampling density is detached); envmap: rad = scale * sum_taps w * data[texel]
                         int32_t rt = sc.emitters[ds.emitter].radiance_tex;
-                        float3 rad = tex_eval3(sc, rt, ds.uv);
+                        bool is_env = sc.emitters[ds.emitter].type == B200PT_EMITTER_ENVMAP;
+                        float3 rad = is_env ? env_eval_spectrum(*sc.env, ds.uv.x, ds.uv.y) : tex_eval3(sc, rt, ds.uv);
+                        if (is_env) Lr_dir = Lr_dir * sc.env_scale;
                         gt2 = rt; guv2 = ds.uv;
                         gv2 = dL * V(rad.x != 0.f ? fdiv(Lr_dir.x, rad.x) : 0.f, rad.y != 0.f ? fdiv(Lr_dir.y, rad.y) : 0.f, rad.z != 0.f ? fdiv(Lr_dir.z, rad.z) : 0.f);
                     }
@@ -775,7 +777,7 @@ __global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ Dev
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&stats[ST_BOUNCES], (unsigned long long) n);   // loop iterations (path.cpp:193)
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         uint32_t i = base + (threadIdx.x & 31u);
-        int32_t gt = -1; float3 gv = V(0.f, 0.f, 0.f);
+        int32_t gt = -1; float3 gv = V(0.f, 0.f, 0.f); float2 guv = make_float2(0.f, 0.f);
         if (i < n) {
             uint32_t slot = queue[i];
             float4 rd = cur.ray_d[slot], th = cur.thr[slot], pv = cur.prev[slot], rs4 = cur.result[slot];
@@ -791,19 +793,23 @@ __global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ Dev
             const bool fwd = ADJOINT && cfg.forward != 0;
             if (fwd) {
                 // forward mode: `result` carries dL; dLe = (beta * mis) (.) d(radiance) for the constant emitter
-                if (em_active && sc.env_type == B200PT_EMITTER_CONSTANT)
-                    result = result + tangent_dot(sc, sc.env_radiance_tex, make_float2(0.f, 0.f), throughput * mis_bsdf);
+                if (em_active) {
+                    bool is_map = sc.env_type == B200PT_EMITTER_ENVMAP;
+                    float2 tuv = is_map ? env_direction_to_uv(env_xform(sc.env->mi, d)) : make_float2(0.f, 0.f);
+                    result = result + tangent_dot(sc, sc.env_radiance_tex, tuv, (throughput * mis_bsdf) * (is_map ? sc.env_scale : 1.f));
+                }
             } else if (prb) result = result + (throughput * mis_bsdf) * rad;
             else result = vfma(throughput, rad * mis_bsdf, result);
             // path.cpp:115,343: a primary ray that sees only the hidden environment is not a valid sample
             if (!prb && cfg.hide_emitters && depth == 0) result = V(0.f, 0.f, 0.f);
             if (!ADJOINT || fwd) lane_result[cur.rng[slot].w] = make_float4(result.x, result.y, result.z, 0.f);
-            else if (em_active && sc.env_type == B200PT_EMITTER_CONSTANT) {
+            else if (em_active) {
                 float4 dl = cur.adj_dL[slot];
                 gt = sc.env_radiance_tex; gv = V(dl.x, dl.y, dl.z) * (throughput * mis_bsdf);
+                if (sc.env_type == B200PT_EMITTER_ENVMAP) { guv = env_direction_to_uv(env_xform(sc.env->mi, d)); gv = gv * sc.env_scale; }
             }
         }
-        if (ADJOINT) { __syncwarp(); warp_scatter3(sc, gt, make_float2(0.f, 0.f), gv); }
+        if (ADJOINT) { __syncwarp(); warp_scatter3(sc, gt, guv, gv); }
     }
 }
 

@@ -170,7 +170,8 @@ struct DevScene {
     uint32_t base_seed;
     // environment emitter: the descriptor lives in global memory (the out-of-line functions of
     // pt_env.cuh take the pointer, so kernels never spill a copy of the scene for them)
-    const DevEnv *env; int32_t env_type, env_emitter, env_radiance_tex;   // env_type -1: none
+    const DevEnv *env; int32_t env_type, env_emitter, env_radiance_tex;   // env_type -1: none; radiance_tex: constant rgb / envmap `data`
+    float env_scale;
 };
 
 struct Ray { float3 o, d; float maxt; };
@@ -265,7 +266,27 @@ PT_DEV int32_t tex_wrap(int32_t pos, int32_t shape, int mode) {
     return mod;
 }
 struct TexTaps { int32_t idx[4]; float w[4]; int n; };
+// internal wrap mode of the envmap's `data` texture: taps of EnvironmentMapEmitter::eval_spectrum
+// (envmap.cpp:531-590) in the halo storage, mapped back to the REAL column of the parameter
+// (halo col 0 <- last real column, col W+1 <- first; envmap.cpp:228-246 routes gradients the same way)
+#define PT_WRAP_ENVMAP 100
 PT_DEV void tex_lookup(const DevTexture &t, float2 uv, TexTaps &tp) {
+    if (t.wrap == PT_WRAP_ENVMAP) {
+        int32_t W = t.width, H = t.height, resx = W + 2;
+        float rx = (float) W, ry = (float) H;
+        float u = uv.x - floorf(uv.x), v = fminf(fmaxf(uv.y, 0.f), 1.f);
+        float posx = fdiv(__fmaf_rn(u, rx, 1.f), rx + 2.f), posy = fdiv(__fmaf_rn(v, ry - 1.f, 0.5f), ry);
+        float fx = __fmaf_rn(posx, (float) resx, -0.5f), fy = __fmaf_rn(posy, (float) H, -0.5f);
+        int32_t ix = (int32_t) floorf(fx), iy = (int32_t) floorf(fy);
+        float wx1 = fx - (float) ix, wx0 = 1.f - wx1, wy1 = fy - (float) iy, wy0 = 1.f - wy1;
+        int32_t xs0 = min(max(ix, 0), resx - 1), xs1 = min(max(ix + 1, 0), resx - 1);
+        int32_t y0 = min(max(iy, 0), H - 1), y1 = min(max(iy + 1, 0), H - 1);
+        int32_t x0 = xs0 == 0 ? W - 1 : (xs0 == W + 1 ? 0 : xs0 - 1), x1 = xs1 == 0 ? W - 1 : (xs1 == W + 1 ? 0 : xs1 - 1);
+        tp.n = 4;
+        tp.idx[0] = y0 * W + x0; tp.w[0] = (1.f * wx0) * wy0; tp.idx[1] = y0 * W + x1; tp.w[1] = (1.f * wx1) * wy0;
+        tp.idx[2] = y1 * W + x0; tp.w[2] = (1.f * wx0) * wy1; tp.idx[3] = y1 * W + x1; tp.w[3] = (1.f * wx1) * wy1;
+        return;
+    }
     float u = __fmaf_rn(t.to_uv[1], uv.y, __fmaf_rn(t.to_uv[0], uv.x, t.to_uv[2]));
     float v = __fmaf_rn(t.to_uv[4], uv.y, __fmaf_rn(t.to_uv[3], uv.x, t.to_uv[5]));
     int32_t W = t.width, H = t.height;

@@ -251,8 +251,12 @@ class _Extractor:
                 if data.shape[2] != 3:
                     raise NotImplementedError("spectral environment maps are outside the hot-path scope")
                 tw = Transform4f(_np(ep["to_world"].matrix), _np(ep["to_world"].inverse_transpose))
+                t = TextureData(name=f"{eid}.data", channels=3)
+                t.kind, t.data = abi.TEX_BITMAP, np.ascontiguousarray(data[:, 1:-1, :], f32)
+                t.wrap, t.filter = abi.WRAP_CLAMP, abi.FILTER_BILINEAR
+                self.out.textures.append(t)
                 self.out.emitters[k] = EmitterData(
-                    shape=-1, radiance_tex=-1, type=abi.EMITTER_ENVMAP, env_data=np.ascontiguousarray(data[:, 1:-1, :], f32),
+                    shape=-1, radiance_tex=len(self.out.textures) - 1, type=abi.EMITTER_ENVMAP,
                     env_scale=float(_np(ep["scale"]).reshape(-1)[0]), env_mis_compensation=False,
                     to_world=tw.matrix.copy(), to_world_inv=np.ascontiguousarray(tw.inverse_transpose.T, f32))
             elif any(key.startswith("radiance") for key in ep.keys()):
@@ -306,9 +310,13 @@ def register(mi):
             """Push the current values of the differentiable parameters (optimiser steps)."""
             params = mi.traverse(scene)
             vals = {}
+            env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
             for name in host.parameters():
                 if name in params:
-                    vals[name] = np.array(params[name], np.float32)
+                    v = np.array(params[name], np.float32)
+                    if name in env_tex:      # the plugin's `data` tensor carries two halo columns (envmap.cpp:155-192)
+                        v = np.ascontiguousarray(v.reshape(tuple(int(n) for n in params[name].shape))[:, 1:-1, :])
+                    vals[name] = v
             update_params(host, vals)
 
         def render(self, scene, sensor=0, seed=0, spp=0, develop=True, evaluate=True):
@@ -330,7 +338,10 @@ def register(mi):
             host = self._host_scene(scene, sensor)
             self._sync_params(host, scene)
             grads = self._impl.render_backward(host, np.array(grad_in, np.float32), seed=int(seed), spp=int(spp))
+            env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
             for name, g in grads.items():
+                if name in env_tex:          # gradients of the halo columns are routed to the real ones (envmap.cpp:228-246)
+                    g = np.pad(g, ((0, 0), (1, 1), (0, 0)))
                 if name in params and dr.grad_enabled(params[name]):
                     dr.accum_grad(params[name], type(params[name])(g))     # opt.step() reads dr.grad (drjit/opt.py:451)
 
@@ -339,8 +350,14 @@ def register(mi):
             host = self._host_scene(scene, sensor)
             self._sync_params(host, scene)
             names = host.parameters()
-            tangents = {k: np.array(dr.grad(params[k]), np.float32) for k in names
-                        if k in params and host.textures[names[k]].differentiable and dr.grad_enabled(params[k])}
+            env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
+            tangents = {}
+            for k in names:
+                if k in params and host.textures[names[k]].differentiable and dr.grad_enabled(params[k]):
+                    t = np.array(dr.grad(params[k]), np.float32)
+                    if k in env_tex:         # the leaf's halo entries are overwritten from the real columns (envmap.cpp:228-246)
+                        t = np.ascontiguousarray(t.reshape(tuple(int(n) for n in params[k].shape))[:, 1:-1, :])
+                    tangents[k] = t
             return mi.TensorXf(self._impl.render_forward(host, tangents, seed=int(seed), spp=int(spp)))
 
     mi.register_integrator("b200_path", lambda props: B200Path(props))

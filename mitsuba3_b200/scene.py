@@ -103,10 +103,9 @@ class ShapeData:
 @dataclass
 class EmitterData:
     shape: int                # area: index of the shape; -1 for the environment emitter
-    radiance_tex: int         # area / constant
+    radiance_tex: int         # area / constant: rgb texture; envmap: bitmap texture with the (H, W, 3) map, real columns
     sampling_weight: float = 1.0
     type: int = abi.EMITTER_AREA
-    env_data: np.ndarray | None = None     # envmap: (H, W, 3) float32, real columns only
     env_scale: float = 1.0
     env_mis_compensation: bool = False
     to_world: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=f32))
@@ -201,10 +200,6 @@ class Scene:
             ems[i].to_world = (C.c_float * 16)(*np.asarray(e.to_world, f32).reshape(16).tolist())
             ems[i].to_world_inv = (C.c_float * 16)(*np.asarray(e.to_world_inv, f32).reshape(16).tolist())
             if e.type == abi.EMITTER_ENVMAP:
-                data = np.ascontiguousarray(e.env_data, dtype=f32)
-                keep.append(data)
-                ems[i].env_height, ems[i].env_width = data.shape[0], data.shape[1]
-                ems[i].env_data = data.ctypes.data_as(C.POINTER(C.c_float))
                 ems[i].env_scale, ems[i].env_mis_compensation = float(e.env_scale), int(e.env_mis_compensation)
         d = abi.SceneDesc()
         d.abi_version = abi.ABI_VERSION
@@ -519,8 +514,12 @@ class _Parser:
             data = np.concatenate([data, np.repeat(data[:, -1:, :], 2 - data.shape[1], axis=1)], axis=1)
         if data.shape[0] < 3:
             data = np.concatenate([data, np.repeat(data[-1:, :, :], 3 - data.shape[0], axis=0)], axis=0)
+        t = TextureData(name=f"{eid}.data", channels=3)
+        t.kind, t.data = abi.TEX_BITMAP, data
+        t.wrap, t.filter = abi.WRAP_CLAMP, abi.FILTER_BILINEAR      # ignored for the environment map
+        self.scene.textures.append(t)
         self.scene.emitters.append(EmitterData(
-            shape=-1, radiance_tex=-1, type=abi.EMITTER_ENVMAP, env_data=data, env_scale=float(d.get("scale", 1.0)),
+            shape=-1, radiance_tex=len(self.scene.textures) - 1, type=abi.EMITTER_ENVMAP, env_scale=float(d.get("scale", 1.0)),
             env_mis_compensation=bool(d.get("mis_compensation", False)), to_world=tw.matrix.copy(), to_world_inv=inv,
             sampling_weight=float(d.get("sampling_weight", 1.0))))
 

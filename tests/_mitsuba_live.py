@@ -61,8 +61,9 @@ def main(mode):
           assert sorted(e.type for e in host3.emitters) == sorted(e.type for e in mine3.emitters)
           for a in host3.emitters:
               b = [e for e in mine3.emitters if e.type == a.type][0]
-              if a.env_data is not None:
-                  assert np.array_equal(a.env_data, b.env_data) and np.array_equal(a.to_world, b.to_world) and np.array_equal(a.to_world_inv, b.to_world_inv)
+              if a.type == mb.abi.EMITTER_ENVMAP:
+                  assert np.array_equal(host3.textures[a.radiance_tex].data, mine3.textures[b.radiance_tex].data)
+                  assert np.array_equal(a.to_world, b.to_world) and np.array_equal(a.to_world_inv, b.to_world_inv)
                   assert a.env_scale == b.env_scale
           ref3 = np.array(mi.render(sm3, seed=2, spp=16))
           img3 = oracle.OracleScene(host3).render(spp=16, seed=2, mode=1, max_depth=6)
