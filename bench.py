@@ -311,7 +311,10 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_trace_traffic.json")))
-            traffic = tj["dram_bytes_per_lane"] * (trace_rays / 2.0) / max(1, trace_launches)   # ~2 rays (shadow + closest) per lane
+            if "dram_bytes_per_ray" in tj:      # ncu dram__bytes_{read,write}.sum summed over ALL traversal launches of a frame / rays traced
+                traffic = tj["dram_bytes_per_ray"] * trace_rays / max(1, trace_launches)
+            else:
+                traffic = tj["dram_bytes_per_lane"] * (trace_rays / 2.0) / max(1, trace_launches)   # ~2 rays (shadow + closest) per lane
         except Exception:
             pass
         step_bytes = (144.0 + 304.0 * b_bar) * (samples_per_step // n_gpus)
@@ -329,7 +332,7 @@ def main():
                          "achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (trace_gbs / hbm_peak) if trace_gbs else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": trace_bytes / max(1, trace_launches), "peak_source": peak_src,
-                         "avg_launch_ms": trace_avg_ms, "launches": int(trace_launches),
+                         "avg_launch_ms": trace_avg_ms, "launches": int(trace_launches), "rays_per_launch": trace_rays / max(1, trace_launches),
                          "share_of_step": trace_ms / max(dev_ms, 1e-9),
                          "step": {"bytes_per_sample": 144.0 + 304.0 * b_bar, "achieved": step_gbs, "frac": step_gbs / hbm_peak}},
         }
