@@ -16,7 +16,7 @@ ScalarTransform4f = Transform4f
 def __getattr__(name):
     # integrators import the CUDA library lazily so that host-only logic
     # (scene parsing, sharding, descriptors) stays importable on CPU boxes.
-    if name in ("PathIntegrator", "PRBIntegrator", "render", "DeviceScene", "render_torch"):
+    if name in ("PathIntegrator", "PRBIntegrator", "render", "DeviceScene", "render_torch", "update_params", "update_vertices"):
         from . import integrators
         return getattr(integrators, name)
     raise AttributeError(name)

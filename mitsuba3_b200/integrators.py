@@ -248,6 +248,25 @@ def update_params(scene: Scene, values: dict, device: int = 0) -> None:
             scene._handle.update_texture(i, t.array())
 
 
+def update_vertices(scene: Scene, shape_id: str, packed_vertices) -> None:
+    """Geometry update (``params['<shape>.vertex_positions'] = ...; params.update()`` in the reference,
+    scene.cpp:517-540): replaces the packed (V, 8) records of one mesh and drops the device scene, which
+    is re-created -- BVH rebuilt on the host, everything uploaded again -- by the next render. The
+    topology must stay the same. (A device-side refit is later work)"""
+    sh = next((s for s in scene.shapes if s.id == shape_id), None)
+    if sh is None:
+        raise KeyError(shape_id)
+    v = np.ascontiguousarray(packed_vertices, np.float32).reshape(-1, 8)
+    if v.shape != sh.vertices.shape:
+        raise ValueError(f"expected packed vertices of shape {sh.vertices.shape}, got {v.shape}")
+    if sh.sampling == abi.SAMPLING_RECTANGLE:
+        raise NotImplementedError("rectangle emitters are sampled through their to_world transform; re-create the shape instead")
+    sh.vertices = v
+    if scene._handle is not None:
+        scene._handle.close()
+        scene._handle = None
+
+
 def render_torch(scene: Scene, params: dict, integrator=None, seed: int = 0, seed_grad=None, spp: int = 0, spp_grad: int = 0,
                  device: int = 0):
     """Differentiable ``mi.render(scene, params, ...)``: ``params`` maps parameter

@@ -279,3 +279,17 @@ def test_rough_materials_scene_matches_oracle(oracle_mod):
     img = mb.render(sc, spp=16, seed=0)
     ref = oracle_mod.OracleScene(sc).render(spp=16, seed=0, mode=0)
     compare_images(img, ref, max_bad_frac=0.01)
+
+
+def test_vertex_update_recreates_the_device_scene(oracle_mod):
+    """update_vertices: moving a mesh = the image of a scene created with the moved mesh."""
+    sc = mb.load_dict(cbox(res=32, spp=8, max_depth=4))
+    img0 = mb.render(sc, spp=8, seed=1)
+    sh = next(s for s in sc.shapes if s.id == "small-box")
+    moved = sh.vertices.copy(); moved[:, 0] -= 0.25; moved[:, 1] += 0.1
+    mb.update_vertices(sc, "small-box", moved)
+    img1 = mb.render(sc, spp=8, seed=1)
+    assert np.abs(img1 - img0).max() > 1e-3
+    compare_images(img1, oracle_mod.OracleScene(sc).render(spp=8, seed=1, mode=0))
+    with pytest.raises(ValueError):
+        mb.update_vertices(sc, "small-box", moved[:4])
