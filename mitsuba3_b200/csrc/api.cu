@@ -190,7 +190,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     int env_index = -1;
     for (uint32_t i = 0; i < desc->n_emitters; ++i) {
         const b200pt_emitter &e = desc->emitters[i];
-        if (e.sampling_weight != 1.f) S_FAIL(B200PT_ERR_UNSUPPORTED, "non-uniform emitter sampling weights (Scene::m_emitter_distr, scene.cpp:259-262) are outside the hot-path scope");
+        if (!(e.sampling_weight >= 0.f)) S_FAIL(B200PT_ERR_INVALID, "emitter sampling_weight must be non-negative");
         he[i].shape = e.shape; he[i].radiance_tex = e.radiance_tex; he[i].sampling_weight = e.sampling_weight; he[i].type = e.type;
         if (e.type == B200PT_EMITTER_AREA) {
             if (e.shape < 0 || e.shape >= (int32_t) desc->n_shapes || e.radiance_tex < 0 || e.radiance_tex >= (int32_t) desc->n_textures)
@@ -225,6 +225,21 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         }
     }
     d.n_emitters = desc->n_emitters;
+    {
+        // Scene::update_emitter_sampling_distribution (scene.cpp:120-140): DiscreteDistribution over the
+        // sampling weights only if one of them differs from 1 (cdf accumulated in double, core/distr_1d.h:236-267)
+        bool non_uniform = false;
+        for (uint32_t i = 0; i < desc->n_emitters; ++i) if (desc->emitters[i].sampling_weight != 1.f) non_uniform = true;
+        d.em_cdf = d.em_pmf = nullptr; d.em_sum = d.em_norm = 0.f;
+        if (non_uniform) {
+            std::vector<float> cdf(desc->n_emitters), pmf(desc->n_emitters);
+            double acc = 0;
+            for (uint32_t i = 0; i < desc->n_emitters; ++i) { pmf[i] = desc->emitters[i].sampling_weight; acc += (double) pmf[i]; cdf[i] = (float) acc; }
+            if (!(cdf.back() > 0.f)) S_FAIL(B200PT_ERR_INVALID, "all emitter sampling weights are zero");
+            float *dc = nullptr, *dp = nullptr; S_TRY(dev_upload(s, cdf.data(), cdf.size(), &dc)); S_TRY(dev_upload(s, pmf.data(), pmf.size(), &dp));
+            d.em_cdf = dc; d.em_pmf = dp; d.em_sum = cdf.back(); d.em_norm = 1.0f / d.em_sum;
+        }
+    }
 
     // ---- shapes: flatten to one vertex / primitive array ---------------------
     size_t n_verts = 0, n_prims = 0;

@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(BLOCK) k_shade_env(const __grid_constant__ Dev
             bool prev_delta = (flags & PF_PREV_DELTA) != 0;
             float3 d = V(rd.x, rd.y, rd.z), throughput = V(th.x, th.y, th.z), result = V(rs4.x, rs4.y, rs4.z);
             float prev_bsdf_pdf = rd.w;
-            float em_pdf = prev_delta ? 0.f : env_pdf_direction(sc.env, d) * fdiv(1.f, (float) sc.n_emitters);   // scene.cpp:378-389
+            float em_pdf = prev_delta ? 0.f : env_pdf_direction(sc.env, d) * emitter_pmf(sc, sc.env_emitter);   // scene.cpp:378-389
             float mis_bsdf = mis_weight(prev_bsdf_pdf, em_pdf);
             bool em_active = prb ? !(cfg.hide_emitters && depth == 0) : prev_bsdf_pdf > 0.f;
             float3 crad = sc.env_type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, sc.env_radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);

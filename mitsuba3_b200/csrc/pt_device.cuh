@@ -172,6 +172,8 @@ struct DevScene {
     // pt_env.cuh take the pointer, so kernels never spill a copy of the scene for them)
     const DevEnv *env; int32_t env_type, env_emitter, env_radiance_tex;   // env_type -1: none; radiance_tex: constant rgb / envmap `data`
     float env_scale;
+    // Scene::m_emitter_distr (scene.cpp:120-140): set only when some sampling_weight != 1
+    const float *em_cdf, *em_pmf; float em_sum, em_norm;
 };
 
 struct Ray { float3 o, d; float maxt; };
@@ -582,6 +584,19 @@ PT_DEV float3 sample_emitter_direction(const DevScene &sc, float3 ref_p, float s
     float sx_re = n < 2 ? sx : scaled - (float) index;
     float emitter_weight = n < 2 ? 1.f : nf;
     float pmf = fdiv(1.f, nf);
+    if (sc.em_cdf) {
+        // m_emitter_distr->sample_reuse_pmf (scene.cpp:257-260, core/distr_1d.h:137-216)
+        pmf = 1.f; index = 0; sx_re = sx; emitter_weight = 1.f;
+        if (n >= 2) {
+            float value = sx * sc.em_sum;
+            uint32_t lo = 0, hi = n - 1;
+            while (lo < hi) { uint32_t mid = (lo + hi) / 2; float c = __ldg(&sc.em_cdf[mid]); if (((c < value) || c == 0.f) && c != sc.em_sum) lo = mid + 1; else hi = mid; }
+            index = lo;
+            float cdf_n = index ? __ldg(&sc.em_cdf[index - 1]) * sc.em_norm : 0.f;
+            pmf = __ldg(&sc.em_pmf[index]) * sc.em_norm;
+            sx_re = fdiv(sx - cdf_n, pmf); emitter_weight = rcp_(pmf);
+        } else pmf = __ldg(&sc.em_pmf[0]) * sc.em_norm;
+    }
     const DevEmitter &em = sc.emitters[index];
     if (em.type != B200PT_EMITTER_AREA) {
         float3 crad = em.type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, em.radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
@@ -607,6 +622,11 @@ PT_DEV float3 sample_emitter_direction(const DevScene &sc, float3 ref_p, float s
     return spec * emitter_weight;
 }
 
+// scene.cpp:378-389: m_emitter_pmf, or sampling_weight * normalization of the emitter distribution
+PT_DEV float emitter_pmf(const DevScene &sc, int32_t emitter) {
+    return sc.em_cdf ? sc.emitters[emitter].sampling_weight * sc.em_norm : fdiv(1.f, (float) sc.n_emitters);
+}
+
 // Scene::pdf_emitter_direction (scene.cpp:378-389) -> area.cpp:170-197 -> shape.cpp:113-124
 PT_DEV float pdf_emitter_direction(const DevScene &sc, int32_t emitter, float3 d, float3 n, float dist) {
     float dp = vdot(d, n);
@@ -615,7 +635,7 @@ PT_DEV float pdf_emitter_direction(const DevScene &sc, int32_t emitter, float3 d
     float pdf = sh.sampling == B200PT_SAMPLING_RECTANGLE ? sh.inv_area : sh.area_norm;
     float adp = fabsf(dp);
     pdf *= adp != 0.f ? fdiv(dist * dist, adp) : 0.f;
-    return pdf * fdiv(1.f, (float) sc.n_emitters);
+    return pdf * emitter_pmf(sc, emitter);
 }
 
 // path.cpp:359-364

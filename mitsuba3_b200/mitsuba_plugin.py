@@ -257,13 +257,15 @@ class _Extractor:
                 self.out.textures.append(t)
                 self.out.emitters[k] = EmitterData(
                     shape=-1, radiance_tex=len(self.out.textures) - 1, type=abi.EMITTER_ENVMAP,
+                    sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0,
                     env_scale=float(_np(ep["scale"]).reshape(-1)[0]), env_mis_compensation=False,
                     to_world=tw.matrix.copy(), to_world_inv=np.ascontiguousarray(tw.inverse_transpose.T, f32))
             elif any(key.startswith("radiance") for key in ep.keys()):
                 rad = self._texture(ep, "", "radiance", f"{eid}.radiance", 3)
                 if rad < 0 or self.out.textures[rad].kind != abi.TEX_CONST:
                     raise NotImplementedError("constant emitter: expected a uniform radiance")
-                self.out.emitters[k] = EmitterData(shape=-1, radiance_tex=rad, type=abi.EMITTER_CONSTANT)
+                self.out.emitters[k] = EmitterData(shape=-1, radiance_tex=rad, type=abi.EMITTER_CONSTANT,
+                                                   sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
             else:
                 raise NotImplementedError(f"environment emitter {em.class_name()} is outside the hot-path scope")
 

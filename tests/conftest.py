@@ -74,6 +74,15 @@ def compare_images(img, ref, rtol=1e-3, floor=1e-2, max_bad_frac=0.005, max_mean
     return bad, l2
 
 
+def weighted_emitter_cbox(res=32, rfilter="box", spp=16, max_depth=6):
+    """multi_emitter_cbox with sampling weights 0.5 / 2 / 1 (gen_golden.py:weighted_emitters)."""
+    d = multi_emitter_cbox(res, rfilter, spp, max_depth)
+    d["light"]["emitter"]["sampling_weight"] = 0.5
+    d["cube-light"]["emitter"]["sampling_weight"] = 2.0
+    d["side-light"]["emitter"]["sampling_weight"] = 1.0
+    return d
+
+
 def multi_emitter_cbox(res=32, rfilter="box", spp=16, max_depth=6):
     """Cornell box with three emitters (same scene as gen_golden.py:multi_emitter)."""
     import mitsuba3_b200 as mb

@@ -299,10 +299,20 @@ def multi_emitter(d):
     return d
 
 
+def weighted_emitters(d):
+    """Non-uniform emitter selection: Scene::m_emitter_distr (scene.cpp:120-140,257-260,378-389)."""
+    multi_emitter(d)
+    d["light"]["emitter"]["sampling_weight"] = 0.5
+    d["cube-light"]["emitter"]["sampling_weight"] = 2.0
+    d["side-light"]["emitter"]["sampling_weight"] = 1.0
+    return d
+
+
 def gen_multi_emitter():
     out = {}
     for (res, spp, md, seed) in [(32, 16, 6, 0), (32, 8, 3, 2)]:
         out[f"multi_{res}_box_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter="box", spp=spp, max_depth=md, extra=multi_emitter), seed, spp)
+    out["weighted_32_box_spp16_d6_seed1"] = render(cbox_dict(res=32, rfilter="box", spp=16, max_depth=6, extra=weighted_emitters), 1, 16)
     save("multi_emitter_renders.npz", **out)
 
 

@@ -293,3 +293,17 @@ def test_vertex_update_recreates_the_device_scene(oracle_mod):
     compare_images(img1, oracle_mod.OracleScene(sc).render(spp=8, seed=1, mode=0))
     with pytest.raises(ValueError):
         mb.update_vertices(sc, "small-box", moved[:4])
+
+
+def test_weighted_emitter_selection_matches_oracle(oracle_mod):
+    from conftest import weighted_emitter_cbox
+    sc = mb.load_dict(weighted_emitter_cbox(res=48, spp=16, max_depth=6))
+    img = mb.render(sc, spp=16, seed=4)
+    compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=4, mode=0))
+    from mitsuba3_b200.integrators import PRBIntegrator
+    gi = np.random.default_rng(1).random(sc.film_shape).astype(np.float32) * 1e-2
+    g = PRBIntegrator(max_depth=4).render_backward(sc, gi, seed=2, spp=8)
+    o = oracle_mod.OracleScene(sc); o.grad_zero(); o.render_backward(gi, spp=8, seed=2, max_depth=4)
+    for k in ("light.emitter.radiance.value", "cube-light.emitter.radiance.value", "side-light.emitter.radiance.value"):
+        ref_g = o.grad(sc.parameters()[k])
+        assert np.abs(g[k] - ref_g).max() / np.abs(ref_g).max() < 5e-3, (k, g[k], ref_g)
