@@ -577,7 +577,7 @@ PT_DEV float3 bsdf_backward(const DevScene &sc, const DevBsdf &b, float2 uv, flo
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4
 #endif
-template <int TYPE, bool ADJOINT>
+template <int TYPE, bool ADJOINT, bool EXT>
 __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
                                                  const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, PathBuf nxt,
                                                  uint32_t *__restrict__ nxt_count, float4 *__restrict__ lane_result,
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                 bool active_em = false;
                 Ray sray; sray.o = V(0.f, 0.f, 0.f); sray.d = V(0.f, 0.f, 0.f); sray.maxt = 0.f;
                 if (smooth) {
-                    em_weight = sample_emitter_direction(sc, si.p, ex, ey, ds);
+                    em_weight = sample_emitter_direction<EXT>(sc, si.p, ex, ey, ds);
                     active_em = ds.pdf != 0.f;
                     wo = si.to_local(ds.d);
                     if (ADJOINT && active_em) {
@@ -1041,8 +1041,11 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
 template <int TYPE>
 static void launch_shade_t(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
                            PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st) {
-    if (cfg.adjoint) k_shade<TYPE, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-    else k_shade<TYPE, false><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    // EXT: environment emitter or non-uniform emitter selection present (pt_device.cuh: sample_emitter_direction)
+    const bool ext = sc.env_type >= 0 || sc.em_cdf != nullptr;
+    if (cfg.adjoint) k_shade<TYPE, true, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else if (ext) k_shade<TYPE, false, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    else k_shade<TYPE, false, false><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
 }
 
 void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
@@ -1121,14 +1124,18 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
 } // namespace pt

@@ -572,9 +572,25 @@ PT_DEV void shape_sample_position(const DevScene &sc, const DevShape &sh, float 
 #include "pt_env.cuh"
 namespace pt {
 
+// m_emitter_distr->sample_reuse_pmf (scene.cpp:257-260, core/distr_1d.h:137-216): (index, pmf, reused
+// sample). Out of line: scenes with uniform emitter selection keep their register budget.
+static __device__ __noinline__ float3 sample_emitter_weighted(const float *cdf, const float *pmf_w, float sum, float norm, uint32_t n, float sx) {
+    if (n < 2) return V(__uint_as_float(0u), __ldg(&pmf_w[0]) * norm, sx);
+    float value = sx * sum;
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) { uint32_t mid = (lo + hi) / 2; float c = __ldg(&cdf[mid]); if (((c < value) || c == 0.f) && c != sum) lo = mid + 1; else hi = mid; }
+    float cdf_n = lo ? __ldg(&cdf[lo - 1]) * norm : 0.f;
+    float pmf = __ldg(&pmf_w[lo]) * norm;
+    return V(__uint_as_float(lo), pmf, fdiv(sx - cdf_n, pmf));
+}
+
 // Scene::sample_emitter_direction (scene.cpp:316-366) -> AreaLight::sample_direction
 // (area.cpp:118-168) -> Shape::sample_direction (shape.cpp:94-111); visibility is
 // resolved by the trace kernel. Returns em_weight.
+// EXT = false: scenes with area lights only and uniform emitter selection (the common case, e.g. the
+// Cornell box): the environment / weighted-selection code is compiled out so that the shading kernels
+// keep their register budget (the mere presence of the out-of-line calls costs ~8 % of k_shade).
+template <bool EXT>
 PT_DEV float3 sample_emitter_direction(const DevScene &sc, float3 ref_p, float sx, float sy, DirectionSample &ds) {
     uint32_t n = sc.n_emitters;
     ds.pdf = 0.f; ds.emitter = -1;
@@ -584,21 +600,12 @@ PT_DEV float3 sample_emitter_direction(const DevScene &sc, float3 ref_p, float s
     float sx_re = n < 2 ? sx : scaled - (float) index;
     float emitter_weight = n < 2 ? 1.f : nf;
     float pmf = fdiv(1.f, nf);
-    if (sc.em_cdf) {
-        // m_emitter_distr->sample_reuse_pmf (scene.cpp:257-260, core/distr_1d.h:137-216)
-        pmf = 1.f; index = 0; sx_re = sx; emitter_weight = 1.f;
-        if (n >= 2) {
-            float value = sx * sc.em_sum;
-            uint32_t lo = 0, hi = n - 1;
-            while (lo < hi) { uint32_t mid = (lo + hi) / 2; float c = __ldg(&sc.em_cdf[mid]); if (((c < value) || c == 0.f) && c != sc.em_sum) lo = mid + 1; else hi = mid; }
-            index = lo;
-            float cdf_n = index ? __ldg(&sc.em_cdf[index - 1]) * sc.em_norm : 0.f;
-            pmf = __ldg(&sc.em_pmf[index]) * sc.em_norm;
-            sx_re = fdiv(sx - cdf_n, pmf); emitter_weight = rcp_(pmf);
-        } else pmf = __ldg(&sc.em_pmf[0]) * sc.em_norm;
+    if (EXT && sc.em_cdf) {
+        float3 r = sample_emitter_weighted(sc.em_cdf, sc.em_pmf, sc.em_sum, sc.em_norm, n, sx);
+        index = __float_as_uint(r.x); pmf = r.y; sx_re = r.z; emitter_weight = n >= 2 ? rcp_(pmf) : 1.f;
     }
     const DevEmitter &em = sc.emitters[index];
-    if (em.type != B200PT_EMITTER_AREA) {
+    if (EXT && em.type != B200PT_EMITTER_AREA) {
         float3 crad = em.type == B200PT_EMITTER_CONSTANT ? tex_eval3(sc, em.radiance_tex, make_float2(0.f, 0.f)) : V(0.f, 0.f, 0.f);
         float3 spec_env = env_sample_direction(sc.env, crad, ref_p, sx_re, sy, ds);
         ds.emitter = (int32_t) index;
