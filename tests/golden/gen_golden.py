@@ -313,6 +313,10 @@ def gen_multi_emitter():
     for (res, spp, md, seed) in [(32, 16, 6, 0), (32, 8, 3, 2)]:
         out[f"multi_{res}_box_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter="box", spp=spp, max_depth=md, extra=multi_emitter), seed, spp)
     out["weighted_32_box_spp16_d6_seed1"] = render(cbox_dict(res=32, rfilter="box", spp=16, max_depth=6, extra=weighted_emitters), 1, 16)
+    # hide_emitters: directly visible area lights are skipped (skip_area_emitters, integrator.cpp:96-123, path.cpp:177-191)
+    def hide(d):
+        multi_emitter(d); d["integrator"]["hide_emitters"] = True
+    out["multi_hide_32_box_spp8_d4_seed6"] = render(cbox_dict(res=32, rfilter="box", spp=8, max_depth=4, extra=hide), 6, 8)
     save("multi_emitter_renders.npz", **out)
 
 
