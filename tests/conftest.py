@@ -171,3 +171,19 @@ def rough_cbox(res=32, rfilter="box", spp=16, max_depth=8):
     d["pl"] = copy.deepcopy(ROUGH_SPECS["plastic_tinted_nonlinear"])
     d["floor"]["bsdf"] = {"type": "ref", "id": "pl"}
     return d
+
+
+def textured_cbox(res=32, rfilter="box", spp=16, max_depth=6):
+    """Cornell box with a bitmap back wall, a checkerboard floor and a principled box with checkerboard
+    roughness (gen_golden.py:textured; the bitmap comes from tests/golden/textured_renders.npz)."""
+    d = cbox(res, rfilter, spp, max_depth)
+    tex = golden("textured_renders.npz")["tex"]
+    d["tex-wall"] = {"type": "diffuse", "reflectance": {"type": "bitmap", "data": tex, "raw": True, "filter_type": "bilinear", "wrap_mode": "clamp"}}
+    d["checker-floor"] = {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                                             "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]}, "to_uv": [[4, 0, 0], [0, 6, 0], [0, 0, 1]]}}
+    d["pr-checker"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.6, 0.6, 0.6]}, "metallic": 0.5,
+                       "roughness": {"type": "checkerboard", "color0": 0.15, "color1": 0.7, "to_uv": [[3, 0, 0], [0, 3, 0], [0, 0, 1]]}}
+    d["back"]["bsdf"] = {"type": "ref", "id": "tex-wall"}
+    d["floor"]["bsdf"] = {"type": "ref", "id": "checker-floor"}
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "pr-checker"}
+    return d

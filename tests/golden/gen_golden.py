@@ -367,6 +367,31 @@ def gen_rough():
     save("rough.npz", **out)
 
 
+# --------------------------------------------------------------------------- textured surfaces in a render
+def textured(d, tex, bitmap, to_uv3):
+    """uv interpolation of rectangles / cubes (mesh.cpp:2380-2392) feeding bitmap and checkerboard
+    textures on diffuse and principled slots."""
+    d["tex-wall"] = {"type": "diffuse", "reflectance": {"type": "bitmap", "bitmap": bitmap(tex), "raw": True,
+                                                        "filter_type": "bilinear", "wrap_mode": "clamp"}}
+    d["checker-floor"] = {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                                             "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]}, "to_uv": to_uv3(4, 6)}}
+    d["pr-checker"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.6, 0.6, 0.6]}, "metallic": 0.5,
+                       "roughness": {"type": "checkerboard", "color0": 0.15, "color1": 0.7, "to_uv": to_uv3(3, 3)}}
+    d["back"]["bsdf"] = {"type": "ref", "id": "tex-wall"}
+    d["floor"]["bsdf"] = {"type": "ref", "id": "checker-floor"}
+    d["large-box"]["bsdf"] = {"type": "ref", "id": "pr-checker"}
+    return d
+
+
+def gen_textured():
+    tex = (0.1 + 0.8 * np.random.default_rng(5).random((6, 9, 3))).astype(np.float32)
+    out = {"tex": tex}
+    ext = lambda d: textured(d, tex, mi.Bitmap, lambda a, b: mi.ScalarTransform3f().scale([a, b]))
+    for (spp, md, seed) in [(16, 6, 0), (8, 3, 5)]:
+        out[f"textured_32_box_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=32, rfilter="box", spp=spp, max_depth=md, extra=ext), seed, spp)
+    save("textured_renders.npz", **out)
+
+
 # --------------------------------------------------------------------------- environment emitters
 def env_image(w=16, h=8):
     """Small synthetic lat-long sky: gradient + a bright 'sun' blob + a dim ground (float32, linear RGB)."""
@@ -462,7 +487,7 @@ def block_one(d, res):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env", "rough"]
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env", "rough", "textured"]
     if "rng" in what:
         gen_rng()
     scene = None
@@ -482,3 +507,5 @@ if __name__ == "__main__":
         gen_env()
     if "rough" in what:
         gen_rough()
+    if "textured" in what:
+        gen_textured()

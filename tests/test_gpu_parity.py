@@ -348,3 +348,10 @@ def test_edge_cases(oracle_mod):
     # environment at max_depth 1: primary rays only, sky + black objects
     sce = mb.load_dict(env_scene(res=24, spp=4, max_depth=1))
     compare_images(mb.render(sce, spp=4, seed=0), oracle_mod.OracleScene(sce).render(spp=4, seed=0, mode=0))
+
+
+def test_textured_scene_matches_oracle(oracle_mod):
+    from conftest import textured_cbox
+    sc = mb.load_dict(textured_cbox(res=48, spp=16, max_depth=6))
+    img = mb.render(sc, spp=16, seed=1)
+    compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=1, mode=0), max_bad_frac=0.01)
