@@ -187,3 +187,17 @@ def textured_cbox(res=32, rfilter="box", spp=16, max_depth=6):
     d["floor"]["bsdf"] = {"type": "ref", "id": "checker-floor"}
     d["large-box"]["bsdf"] = {"type": "ref", "id": "pr-checker"}
     return d
+
+
+def smooth_mesh_scene(res=32, spp=16, max_depth=5):
+    """env_scene floor + envmap + area light with a smooth-shaded UV sphere (vertex normals and texture
+    coordinates from tests/golden/smooth_mesh.npz; gen_golden.py:gen_smooth)."""
+    g = golden("smooth_mesh.npz")
+    d = env_scene(res=res, spp=spp, max_depth=max_depth, area_light=True)
+    del d["cube-a"], d["cube-b"]
+    d["ball-mat"] = {"type": "principled", "roughness": 0.3, "metallic": 0.3, "clearcoat": 0.5,
+                     "base_color": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                    "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]}, "to_uv": [[8, 0, 0], [0, 4, 0], [0, 0, 1]]}}
+    d["ball"] = {"type": "mesh", "positions": g["positions"], "normals": g["normals"], "texcoords": g["texcoords"], "faces": g["faces"],
+                 "bsdf": {"type": "ref", "id": "ball-mat"}}
+    return d

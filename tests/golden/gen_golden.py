@@ -480,6 +480,53 @@ def gen_env():
     save("env.npz", **out)
 
 
+# --------------------------------------------------------------------------- smooth-shaded mesh (vertex normals + texcoords)
+def write_ply(path, pos, nrm, uv, faces):
+    with open(path, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "property float nx\nproperty float ny\nproperty float nz\nproperty float u\nproperty float v\n"
+                "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(pos), len(faces)))
+        for p, n, t in zip(pos, nrm, uv):
+            f.write("%.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n" % (*p, *n, *t))
+        for tri in faces:
+            f.write("3 %d %d %d\n" % tuple(tri))
+
+
+def gen_smooth():
+    """UV sphere with interpolated shading normals and texture coordinates (mesh.cpp:2300-2392), principled
+    with a checkerboard base colour, on the env_scene floor under the envmap (+ area light)."""
+    import tempfile
+    n_theta, n_phi, radius, center = 12, 24, 0.6, np.array([0.0, 0.6, 0.0])
+    th = (np.arange(n_theta + 1, dtype=np.float64) / n_theta) * np.pi
+    ph = (np.arange(n_phi + 1, dtype=np.float64) / n_phi) * 2 * np.pi
+    T_, P_ = np.meshgrid(th, ph, indexing="ij")
+    nrm = np.stack([np.sin(T_) * np.cos(P_), np.cos(T_), np.sin(T_) * np.sin(P_)], -1).reshape(-1, 3)
+    pos = (nrm * radius + center).astype(np.float32); nrm = nrm.astype(np.float32)
+    uv = np.stack([P_ / (2 * np.pi), T_ / np.pi], -1).reshape(-1, 2).astype(np.float32)
+    idx = lambda i, j: i * (n_phi + 1) + j
+    faces = []
+    for i in range(n_theta):
+        j = np.arange(n_phi)
+        a, b, c, d_ = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+        if i > 0: faces.append(np.stack([a, d_, c], -1))
+        if i < n_theta - 1: faces.append(np.stack([a, c, b], -1))
+    faces = np.concatenate(faces, 0).astype(np.uint32)
+    ply = os.path.join(tempfile.gettempdir(), "b200pt_sphere.ply")
+    write_ply(ply, pos, nrm, uv, faces)
+    img = env_image()
+    T = mi.ScalarTransform4f
+    out = {"positions": pos, "normals": nrm, "texcoords": uv, "faces": faces}
+    for (key, spp, md, seed) in [("smooth_32_spp16_d5_seed0", 16, 5, 0), ("smooth_32_spp8_d3_seed4", 8, 3, 4)]:
+        d = env_scene(T, img, mi.Bitmap, spp=spp, max_depth=md, area_light=True)
+        del d["cube-a"], d["cube-b"]
+        d["ball-mat"] = {"type": "principled", "roughness": 0.3, "metallic": 0.3, "clearcoat": 0.5,
+                         "base_color": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.8, 0.2, 0.1]},
+                                        "color1": {"type": "rgb", "value": [0.1, 0.3, 0.9]}, "to_uv": mi.ScalarTransform3f().scale([8, 4])}}
+        d["ball"] = {"type": "ply", "filename": ply, "bsdf": {"type": "ref", "id": "ball-mat"}}
+        out[key] = render(block_one(d, 32), seed, spp)
+    save("smooth_mesh.npz", **out)
+
+
 def block_one(d, res):
     """Single-block render (so that the per-pixel sampler streams follow integrator.cpp:209-222 for one block)."""
     d["integrator"]["block_size"] = res
@@ -487,7 +534,7 @@ def block_one(d, res):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env", "rough", "textured"]
+    what = sys.argv[1:] or ["rng", "scene", "rays", "bsdfs", "renders", "materials", "multi", "env", "rough", "textured", "smooth"]
     if "rng" in what:
         gen_rng()
     scene = None
@@ -509,3 +556,5 @@ if __name__ == "__main__":
         gen_rough()
     if "textured" in what:
         gen_textured()
+    if "smooth" in what:
+        gen_smooth()

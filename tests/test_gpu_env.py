@@ -119,3 +119,10 @@ def test_envmap_data_gradient_and_update(oracle_mod):
     sc2 = mb.load_dict(env_scene(res=32, spp=8, area_light=True, integrator="prb", max_depth=4, img=new))
     assert np.array_equal(img, mb.render(sc2, spp=8, seed=2))
     compare_images(img, oracle_mod.OracleScene(sc2).render(spp=8, seed=2, mode=0), max_bad_frac=0.01)
+
+
+def test_smooth_mesh_scene_matches_oracle(oracle_mod):
+    from conftest import smooth_mesh_scene
+    sc = mb.load_dict(smooth_mesh_scene(res=48, spp=16, max_depth=5))
+    img = mb.render(sc, spp=16, seed=2)
+    compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=2, mode=0), max_bad_frac=0.01)
