@@ -201,3 +201,17 @@ def smooth_mesh_scene(res=32, spp=16, max_depth=5):
     d["ball"] = {"type": "mesh", "positions": g["positions"], "normals": g["normals"], "texcoords": g["texcoords"], "faces": g["faces"],
                  "bsdf": {"type": "ref", "id": "ball-mat"}}
     return d
+
+
+def principled_glass_cbox(res=32, rfilter="box", spp=16, max_depth=8):
+    """Cornell box with a transmissive principled box and a sheen / flatness wall (gen_golden.py:principled_glass)."""
+    import mitsuba3_b200 as mb
+    d = cbox(res, rfilter, spp, max_depth)
+    d["pglass"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.95, 1.0]}, "roughness": 0.1,
+                   "spec_trans": 0.9, "eta": 1.45}
+    d["cloth"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.3, 0.5, 0.2]}, "roughness": 0.8, "sheen": 0.8,
+                  "sheen_tint": 0.5, "flatness": 0.4, "spec_tint": 0.3, "specular": 0.3}
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "pglass"}
+    d["small-box"]["to_world"] = mb.Transform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
+    d["green-wall"]["bsdf"] = {"type": "ref", "id": "cloth"}
+    return d

@@ -277,8 +277,21 @@ def materials(d):
     d["floor"]["bsdf"] = {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.5, 0.5, 0.5]}}}
 
 
+def principled_glass(d):
+    """Transmissive principled small box (spec_trans lobe, eta 1.45) + sheen / flatness on a wall."""
+    d["pglass"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.95, 1.0]}, "roughness": 0.1,
+                   "spec_trans": 0.9, "eta": 1.45}
+    d["cloth"] = {"type": "principled", "base_color": {"type": "rgb", "value": [0.3, 0.5, 0.2]}, "roughness": 0.8, "sheen": 0.8,
+                  "sheen_tint": 0.5, "flatness": 0.4, "spec_tint": 0.3, "specular": 0.3}
+    d["small-box"]["bsdf"] = {"type": "ref", "id": "pglass"}
+    d["small-box"]["to_world"] = mi.ScalarTransform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
+    d["green-wall"]["bsdf"] = {"type": "ref", "id": "cloth"}
+
+
 def gen_material_renders():
     out = {}
+    for (res, rf, spp, md, seed) in [(32, "box", 16, 8, 1)]:
+        out[f"pglass_{res}_{rf}_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter=rf, spp=spp, max_depth=md, extra=principled_glass), seed, spp)
     for (res, rf, spp, md, seed) in [(32, "box", 16, 8, 0), (32, "box", 8, 12, 4)]:
         out[f"mat_{res}_{rf}_spp{spp}_d{md}_seed{seed}"] = render(cbox_dict(res=res, rfilter=rf, spp=spp, max_depth=md, extra=materials), seed, spp)
     d = cbox_dict(res=64, rfilter="box", spp=2048, max_depth=8, block=False, extra=materials)

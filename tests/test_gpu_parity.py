@@ -355,3 +355,10 @@ def test_textured_scene_matches_oracle(oracle_mod):
     sc = mb.load_dict(textured_cbox(res=48, spp=16, max_depth=6))
     img = mb.render(sc, spp=16, seed=1)
     compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=1, mode=0), max_bad_frac=0.01)
+
+
+def test_principled_transmission_scene_matches_oracle(oracle_mod):
+    from conftest import principled_glass_cbox
+    sc = mb.load_dict(principled_glass_cbox(res=48, spp=16, max_depth=8))
+    img = mb.render(sc, spp=16, seed=3)
+    compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=3, mode=0), max_bad_frac=0.01)
