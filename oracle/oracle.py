@@ -54,6 +54,8 @@ def load():
         lib.orc_bsdf_eval_pdf_sample.argtypes = [vp, C.c_uint32, C.c_uint32, f32p, f32p]
         lib.orc_camera_rays.argtypes = [vp, C.c_uint32, f32p, f32p]
         lib.orc_env_query.argtypes = [vp, C.c_uint32, f32p, f32p]
+        lib.orc_microfacet_query.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint32, f32p, f32p, f32p]
+        lib.orc_microfacet_query.restype = None
         lib.orc_rfilter_eval.argtypes = [vp, C.c_float]; lib.orc_rfilter_eval.restype = C.c_float
         lib.orc_tea32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
         lib.orc_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, f32p]
@@ -186,6 +188,14 @@ class OracleScene:
         out = np.zeros((pos.shape[0], 7), np.float32)
         self.lib.orc_camera_rays(self.h, pos.shape[0], _fp(pos), _fp(out))
         return out
+
+
+def microfacet_query(is_ggx, alpha_u, alpha_v, v, m=(0.0, 0.0, 1.0)):
+    """(D(v), smith_g1(v, m)) of MicrofacetDistribution(type, alpha_u, alpha_v) for directions v (n, 3)."""
+    v = np.ascontiguousarray(v, np.float32).reshape(-1, 3); mm = np.asarray(m, np.float32)
+    out = np.zeros((v.shape[0], 2), np.float32)
+    load().orc_microfacet_query(int(is_ggx), float(alpha_u), float(alpha_v), v.shape[0], _fp(v), _fp(mm), _fp(out))
+    return out[:, 0], out[:, 1]
 
 
 def tea32(v0, v1, rounds=4):
