@@ -56,6 +56,8 @@ def load():
         lib.orc_env_query.argtypes = [vp, C.c_uint32, f32p, f32p]
         lib.orc_microfacet_query.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint32, f32p, f32p, f32p]
         lib.orc_microfacet_query.restype = None
+        lib.orc_h2d_query.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, f32p]
+        lib.orc_h2d_query.restype = None
         lib.orc_rfilter_eval.argtypes = [vp, C.c_float]; lib.orc_rfilter_eval.restype = C.c_float
         lib.orc_tea32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
         lib.orc_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_int, f32p]
@@ -196,6 +198,14 @@ def microfacet_query(is_ggx, alpha_u, alpha_v, v, m=(0.0, 0.0, 1.0)):
     out = np.zeros((v.shape[0], 2), np.float32)
     load().orc_microfacet_query(int(is_ggx), float(alpha_u), float(alpha_v), v.shape[0], _fp(v), _fp(mm), _fp(out))
     return out[:, 0], out[:, 1]
+
+
+def h2d_query(data, samples):
+    """Hierarchical2D(data): rows = (sampled x, sampled y, pdf, eval at the input position)."""
+    d = np.ascontiguousarray(data, np.float32); q = np.ascontiguousarray(samples, np.float32).reshape(-1, 2)
+    out = np.zeros((q.shape[0], 4), np.float32)
+    load().orc_h2d_query(_fp(d), d.shape[1], d.shape[0], q.shape[0], _fp(q), _fp(out))
+    return out
 
 
 def tea32(v0, v1, rounds=4):
