@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
 
 
 def world():
