@@ -41,7 +41,7 @@ DEFAULT_WORKLOAD = "cornell_box_512x512_256spp_8bounce"
 METRIC = "Msamples/sec (fwd path, Cornell box)"
 
 
-def build_scene(workload):
+def build_scene(workload, textured_wall=False):
     import mitsuba3_b200 as mb
     w, h, spp, md, rf = WORKLOADS[workload]
     if workload.startswith("heightfield"):
@@ -50,6 +50,12 @@ def build_scene(workload):
         d = mb.matpreview_like()
     else:
         d = mb.cornell_box()
+    if textured_wall and "back" in d:
+        # BASELINE.json configs[2] / SURVEY 8(d): the back wall's albedo is a 64x64x3 bitmap texture (initial 0.5,
+        # bilinear, clamp, raw) -- the parameter the PRB gradient step differentiates
+        d["wall-tex"] = {"type": "diffuse", "reflectance": {"type": "bitmap", "data": np.full((64, 64, 3), 0.5, np.float32), "raw": True,
+                                                            "filter_type": "bilinear", "wrap_mode": "clamp"}}
+        d["back"]["bsdf"] = {"type": "ref", "id": "wall-tex"}
     d["sensor"]["film"].update(width=w, height=h, rfilter={"type": rf})
     d["sensor"]["sampler"]["sample_count"] = spp
     d["integrator"] = {"type": "path", "max_depth": md}
@@ -269,6 +275,8 @@ def main():
     prb = None
     if not args.no_prb:
         pint = PRBIntegrator(max_depth=md)
+        scene_main = scene
+        scene, _ = build_scene(args.workload, textured_wall=True)      # configs[2]: wall albedo texture is the parameter
         gi = torch.full((h, w, 3), 1.0 / (h * w * 3), device=f"cuda:{local}")
         spp_g = 64 * n_gpus if args.scaling == "weak" else 64
         n_grad = max(3, args.steps // 2)
@@ -286,8 +294,10 @@ def main():
         tp = torch.tensor([pe0.elapsed_time(pe1)], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        prb = {"ms_per_grad_step": float(tp.item()) / n_grad, "spp": spp_g, "grad_steps": n_grad,
-               "what": "primal render + render_backward (PRB adjoint, atomicAdd gradient scatter%s), CUDA events, "
+        n_params = int(sum(t.size for t in scene.textures if t.differentiable))
+        scene = scene_main
+        prb = {"ms_per_grad_step": float(tp.item()) / n_grad, "spp": spp_g, "grad_steps": n_grad, "differentiated_floats": n_params,
+               "what": "wall albedo = 64x64x3 bitmap texture; primal render + render_backward (PRB adjoint, atomicAdd gradient scatter%s), CUDA events, "
                        "max over ranks, max_depth %d" % (" + gradient all-reduce" if world > 1 else "", md),
                "reference": "unmeasurable here: prb needs an AD variant (llvm_ad_rgb) and the image has no libLLVM"}
 
