@@ -552,6 +552,18 @@ static b200pt_status end_stats(b200pt_scene *s, cudaStream_t st, uint64_t sample
     return B200PT_OK;
 }
 
+// Scratch device allocations of the query entry points below; released on every exit
+// path (CU_TRY returns early on a failed copy or launch).
+struct DevScratch {
+    std::vector<void *> ptrs;
+    template <typename T> cudaError_t alloc(T **p, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **) p, bytes);
+        if (e == cudaSuccess) ptrs.push_back((void *) *p);
+        return e;
+    }
+    ~DevScratch() { for (void *p : ptrs) cudaFree(p); }
+};
+
 extern "C" {
 
 b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_params *p, float *film_device, void *cuda_stream) {
@@ -741,9 +753,9 @@ b200pt_status b200pt_ray_intersect(b200pt_scene *s, uint32_t n, const float *ray
     if (!s || (n && (!rays_host || !t_out || !uv_out || !prim_out || !shape_out))) return fail(B200PT_ERR_INVALID, "null argument");
     if (n == 0) return B200PT_OK;   // empty batch
     CU_TRY(cudaSetDevice(s->device));
-    float *dr, *dt, *duv; uint32_t *dp; int32_t *ds;
-    CU_TRY(cudaMalloc(&dr, (size_t) n * 28)); CU_TRY(cudaMalloc(&dt, (size_t) n * 4)); CU_TRY(cudaMalloc(&duv, (size_t) n * 8));
-    CU_TRY(cudaMalloc(&dp, (size_t) n * 4)); CU_TRY(cudaMalloc(&ds, (size_t) n * 4));
+    float *dr, *dt, *duv; uint32_t *dp; int32_t *ds; DevScratch tmp;
+    CU_TRY(tmp.alloc(&dr, (size_t) n * 28)); CU_TRY(tmp.alloc(&dt, (size_t) n * 4)); CU_TRY(tmp.alloc(&duv, (size_t) n * 8));
+    CU_TRY(tmp.alloc(&dp, (size_t) n * 4)); CU_TRY(tmp.alloc(&ds, (size_t) n * 4));
     CU_TRY(cudaMemcpyAsync(dr, rays_host, (size_t) n * 28, cudaMemcpyHostToDevice, s->stream));
     Launch L = s->launch; L.grid = grid_for(s, n);
     launch_ray_intersect(s->dev, n, dr, dt, duv, dp, ds, L, s->stream);
@@ -751,9 +763,7 @@ b200pt_status b200pt_ray_intersect(b200pt_scene *s, uint32_t n, const float *ray
     CU_TRY(cudaMemcpyAsync(uv_out, duv, (size_t) n * 8, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaMemcpyAsync(prim_out, dp, (size_t) n * 4, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaMemcpyAsync(shape_out, ds, (size_t) n * 4, cudaMemcpyDeviceToHost, s->stream));
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(dr); cudaFree(dt); cudaFree(duv); cudaFree(dp); cudaFree(ds);
-    CU_TRY(e);
+    CU_TRY(cudaStreamSynchronize(s->stream));
     return B200PT_OK;
 }
 
@@ -761,15 +771,13 @@ b200pt_status b200pt_ray_test(b200pt_scene *s, uint32_t n, const float *rays_hos
     if (!s || (n && (!rays_host || !hit_out))) return fail(B200PT_ERR_INVALID, "null argument");
     if (n == 0) return B200PT_OK;
     CU_TRY(cudaSetDevice(s->device));
-    float *dr; uint8_t *dh;
-    CU_TRY(cudaMalloc(&dr, (size_t) n * 28)); CU_TRY(cudaMalloc(&dh, n));
+    float *dr; uint8_t *dh; DevScratch tmp;
+    CU_TRY(tmp.alloc(&dr, (size_t) n * 28)); CU_TRY(tmp.alloc(&dh, n));
     CU_TRY(cudaMemcpyAsync(dr, rays_host, (size_t) n * 28, cudaMemcpyHostToDevice, s->stream));
     Launch L = s->launch; L.grid = grid_for(s, n);
     launch_ray_test(s->dev, n, dr, dh, L, s->stream);
     CU_TRY(cudaMemcpyAsync(hit_out, dh, n, cudaMemcpyDeviceToHost, s->stream));
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(dr); cudaFree(dh);
-    CU_TRY(e);
+    CU_TRY(cudaStreamSynchronize(s->stream));
     return B200PT_OK;
 }
 
@@ -778,15 +786,13 @@ b200pt_status b200pt_bsdf_eval_pdf_sample(b200pt_scene *s, uint32_t bsdf, uint32
     if (bsdf >= s->dev.n_bsdfs) return fail(B200PT_ERR_INVALID, "BSDF index out of range");
     if (n == 0) return B200PT_OK;
     CU_TRY(cudaSetDevice(s->device));
-    float *di, *dout;
-    CU_TRY(cudaMalloc(&di, (size_t) n * 44)); CU_TRY(cudaMalloc(&dout, (size_t) n * 56));
+    float *di, *dout; DevScratch tmp;
+    CU_TRY(tmp.alloc(&di, (size_t) n * 44)); CU_TRY(tmp.alloc(&dout, (size_t) n * 56));
     CU_TRY(cudaMemcpyAsync(di, in_host, (size_t) n * 44, cudaMemcpyHostToDevice, s->stream));
     DevBsdf hb; CU_TRY(cudaMemcpy(&hb, s->dev.bsdfs + bsdf, sizeof(hb), cudaMemcpyDeviceToHost));
     launch_bsdf_eval(s->dev, bsdf, hb.type, n, di, dout, s->stream);
     CU_TRY(cudaMemcpyAsync(out_host, dout, (size_t) n * 56, cudaMemcpyDeviceToHost, s->stream));
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(di); cudaFree(dout);
-    CU_TRY(e);
+    CU_TRY(cudaStreamSynchronize(s->stream));
     return B200PT_OK;
 }
 
@@ -795,14 +801,12 @@ b200pt_status b200pt_env_query(b200pt_scene *s, uint32_t n, const float *in_host
     if (s->dev.env_type < 0) return fail(B200PT_ERR_INVALID, "the scene has no environment emitter");
     if (n == 0) return B200PT_OK;
     CU_TRY(cudaSetDevice(s->device));
-    float *di, *dout;
-    CU_TRY(cudaMalloc(&di, (size_t) n * 32)); CU_TRY(cudaMalloc(&dout, (size_t) n * 80));
+    float *di, *dout; DevScratch tmp;
+    CU_TRY(tmp.alloc(&di, (size_t) n * 32)); CU_TRY(tmp.alloc(&dout, (size_t) n * 80));
     CU_TRY(cudaMemcpyAsync(di, in_host, (size_t) n * 32, cudaMemcpyHostToDevice, s->stream));
     launch_env_query(s->dev, n, di, dout, s->stream);
     CU_TRY(cudaMemcpyAsync(out_host, dout, (size_t) n * 80, cudaMemcpyDeviceToHost, s->stream));
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(di); cudaFree(dout);
-    CU_TRY(e);
+    CU_TRY(cudaStreamSynchronize(s->stream));
     return B200PT_OK;
 }
 
