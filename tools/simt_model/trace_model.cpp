@@ -51,6 +51,8 @@ struct Options {
     int wide = 2;
     int warps = 148 * 5 * 8;
     int tri_reject = 0;       // > 0: cost of a triangle iteration that the sign prefilter rejects
+    bool leaf_once = false;   // one round of triangle tests per pass of the outer loop (lanes holding a second leaf keep it for the next round)
+    bool split_inplace = false; // same launch, work counter over [0, n) = shadow jobs, [n, 2n) = path jobs (slots without one idle)
     bool split_phases = false; // shadow rays of a wave in their own launch (no shadow/path mix inside a warp)
     int sort_bits = 0;        // > 0: sort the slots of each wave by a Morton key of (origin cell, direction octant)
     bool verbose = false;
@@ -249,13 +251,13 @@ static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
     const Costs &C = *w.cost; const Options &O = *w.opt;
     const int node_cost = O.wide <= 2 ? C.node : C.node_wide(O.wide);
     bool in_outer[32]; int n_outer = 0;
-    for (int i = 0; i < 32; ++i) { in_outer[i] = wp.ln[i].kind != 0 && wp.ln[i].node != SENT; n_outer += in_outer[i]; }
+    for (int i = 0; i < 32; ++i) { in_outer[i] = wp.ln[i].kind != 0 && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
     while (n_outer > 0) {
         // ---- inner-node loop ----
         bool in_node[32]; int n_node = 0;
         for (int i = 0; i < 32; ++i) {
             Lane &l = wp.ln[i];
-            if (in_outer[i]) l.searching = true;
+            if (in_outer[i]) l.searching = O.leaf_once ? l.leaf >= 0 : true;
             in_node[i] = in_outer[i] && l.node >= 0 && l.node != SENT; n_node += in_node[i];
         }
         while (n_node > 0) {
@@ -303,15 +305,26 @@ static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
                 if (l.node < 0) l.node = l.stack[l.sp--];
                 if (l.occluded) { l.node = SENT; l.leaf = 0; }
             }
+            if (O.leaf_once) break;
         }
         w.cnt.add(R_OUTER, C.outer, n_outer);
         if (dyn_break && !wp.exhausted && n_outer < 32 - O.idle) break;
         n_outer = 0;
-        for (int i = 0; i < 32; ++i) { in_outer[i] = in_outer[i] && wp.ln[i].node != SENT; n_outer += in_outer[i]; }
+        for (int i = 0; i < 32; ++i) { in_outer[i] = in_outer[i] && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
     }
 }
 
 static void begin_job(Wave &w, Lane &l, uint32_t slot, int &n_sh, int &n_pa) {
+    if (w.opt->split_inplace && !w.first) {
+        const uint32_t n = (uint32_t) w.slots->size();
+        bool shadow = slot < n; if (!shadow) slot -= n;
+        const Slot &s = (*w.slots)[slot];
+        l.slot = slot;
+        if (shadow) { if (!s.has_shadow) return; l.kind = 1; start_ray(l, s.sh); n_sh++; }
+        else { if (!s.alive) return; l.kind = 2; start_ray(l, s.path); n_pa++; }
+        w.cnt.rays++;
+        return;
+    }
     const Slot &s = (*w.slots)[slot];
     l.slot = slot;
     if (!w.first && s.has_shadow) { l.kind = 1; start_ray(l, s.sh); n_sh++; }
@@ -325,11 +338,12 @@ static void retire_section(Wave &w, Warp &wp) {
     int n_add = 0, n_restart = 0, n_finish = 0, n_hit = 0, n_miss = 0; bool any_bucket = false;
     for (int i = 0; i < 32; ++i) {
         Lane &l = wp.ln[i];
-        if (l.kind == 0 || l.node != SENT) continue;
+        if (l.kind == 0 || l.node != SENT || l.leaf < 0) continue;
         const Slot &s = (*w.slots)[l.slot];
         if (l.kind == 1) {
             if (!l.occluded) n_add++;
-            if (s.alive) { n_restart++; l.kind = 2; start_ray(l, s.path); w.cnt.rays++; }
+            if (s.alive && w.opt->split_inplace) l.kind = 0;
+            else if (s.alive) { n_restart++; l.kind = 2; start_ray(l, s.path); w.cnt.rays++; }
             else { n_finish++; l.kind = 0; (*w.hits)[l.slot] = { INFINITY, 0xffffffffu }; }
         } else {
             (*w.hits)[l.slot] = { l.hit_t, l.hit_prim };
@@ -348,7 +362,7 @@ static void retire_section(Wave &w, Warp &wp) {
 // one pass of the job loop of k_trace_dyn; false when the warp is done
 static bool dyn_pass(Wave &w, Warp &wp) {
     const Costs &C = *w.cost; const Options &O = *w.opt;
-    const uint32_t n = (uint32_t) w.slots->size();
+    const uint32_t n = (uint32_t) w.slots->size() * ((w.opt->split_inplace && !w.first) ? 2u : 1u);
     double before = w.cnt.total_warp();
     int idle = 0; for (int i = 0; i < 32; ++i) idle += wp.ln[i].kind == 0;
     w.cnt.add(R_HEAD, C.head, 32);
@@ -362,7 +376,7 @@ static bool dyn_pass(Wave &w, Warp &wp) {
         if (n_pa) w.cnt.add(R_REFILL, C.refill_start, n_pa);
     }
     bool any = false; for (int i = 0; i < 32; ++i) any |= wp.ln[i].kind != 0;
-    if (!any) { wp.clock += w.cnt.total_warp() - before; return false; }
+    if (!any) { wp.clock += w.cnt.total_warp() - before; return !wp.exhausted; }   // empty jobs (split ranges): fetch again
     traverse_section(w, wp, true);
     retire_section(w, wp);
     wp.clock += w.cnt.total_warp() - before;
@@ -443,7 +457,7 @@ int main(int argc, char **argv) {
         auto val = [&]() { return atoi(argv[++i]); };
         if (a == "--res") opt.res = val(); else if (a == "--spp") opt.spp = val(); else if (a == "--idle") opt.idle = val();
         else if (a == "--static") opt.dynamic = false; else if (a == "--wide") opt.wide = val(); else if (a == "--warps") opt.warps = val();
-        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true;
+        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true;
         else if (a == "--sort") opt.sort_bits = val(); else if (a == "--node-cost") cost.node = val(); else if (a == "--tri-cost") cost.tri = val();
         else if (a == "--retire-scale") { int p = val(); cost.ret_restart = cost.ret_restart * p / 100; cost.ret_hit = cost.ret_hit * p / 100; cost.refill_start = cost.refill_start * p / 100; }
         else if (a == "-v") opt.verbose = true;
