@@ -42,7 +42,15 @@ def harness():
     lib.bvh_h_order.argtypes = [ctypes.c_void_p]
     lib.bvh_h_validate.restype = ctypes.c_int
     lib.bvh_h_validate.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
-    lib.bvh_h_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bvh_h_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    for f in (lib.bvh_h_n_nodes4, lib.bvh_h_depth4):
+        f.restype = ctypes.c_uint32
+        f.argtypes = [ctypes.c_void_p]
+    lib.bvh_h_nodes4.restype = ctypes.c_void_p
+    lib.bvh_h_nodes4.argtypes = [ctypes.c_void_p]
+    lib.bvh_h_validate4.restype = ctypes.c_int
+    lib.bvh_h_validate4.argtypes = [ctypes.c_void_p]
+    lib.bvh_h_trace4.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
@@ -74,8 +82,31 @@ class Tree:
         t = np.empty(len(rays), np.float32)
         prim = np.empty(len(rays), np.uint32)
         n = ctypes.c_uint64(0)
-        self.lib.bvh_h_trace(self.h, len(rays), rays.ctypes.data, int(brute), t.ctypes.data, prim.ctypes.data, ctypes.byref(n))
+        steps = ctypes.c_uint64(0)
+        self.lib.bvh_h_trace(self.h, len(rays), rays.ctypes.data, int(brute), t.ctypes.data, prim.ctypes.data, ctypes.byref(n), ctypes.byref(steps))
+        self.last_steps = steps.value
         return t, prim, n.value
+
+    # ---- 4-wide tree ----
+    @property
+    def n_nodes4(self):
+        return self.lib.bvh_h_n_nodes4(self.h)
+
+    def nodes4(self):
+        raw = (ctypes.c_uint8 * (128 * self.n_nodes4)).from_address(self.lib.bvh_h_nodes4(self.h))
+        return np.frombuffer(raw, np.float32).reshape(-1, 32).copy()
+
+    def validate4(self):
+        return self.lib.bvh_h_validate4(self.h)
+
+    def trace4(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        t = np.empty(len(rays), np.float32)
+        prim = np.empty(len(rays), np.uint32)
+        n = ctypes.c_uint64(0)
+        steps = ctypes.c_uint64(0)
+        self.lib.bvh_h_trace4(self.h, len(rays), rays.ctypes.data, t.ctypes.data, prim.ctypes.data, ctypes.byref(n), ctypes.byref(steps))
+        return t, prim, n.value, steps.value
 
 
 def random_rays(rng, n, lo, hi, tri):
@@ -142,6 +173,15 @@ def test_invariants_and_walk_equals_brute_force(harness, name):
     assert (p_ref != 0xFFFFFFFF).sum() >= 20                      # the rays do hit something
     if len(tri) >= 1000:
         assert n_tree < n_ref // 10                               # and the tree actually culls
+    # the 4-wide collapse of the same tree: same leaves, same answers, fewer node visits
+    assert tree.validate4() == 0
+    t_w, p_w, n_w, steps4 = tree.trace4(rays)
+    assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
+    tree.trace(rays, brute=False)
+    steps2 = tree.last_steps
+    assert steps4 <= steps2
+    if len(tri) >= 300:
+        assert steps4 < 0.62 * steps2
 
 
 def test_empty_scene_has_a_root_that_is_never_entered(harness):
@@ -151,6 +191,31 @@ def test_empty_scene_has_a_root_that_is_never_entered(harness):
     assert nodes.view(np.int32)[0, 12] == 0x7FFFFFFF and nodes.view(np.int32)[0, 13] == 0x7FFFFFFF
     t, p, _ = tree.trace(np.array([[0, 0, 0, 0, 0, 1, np.inf]], np.float32), brute=False)
     assert np.isinf(t[0]) and p[0] == 0xFFFFFFFF
+
+
+def test_wide_layout(harness):
+    rng = np.random.default_rng(6)
+    tri = soup(rng, 777)
+    tree = Tree(harness, tri)
+    n4 = tree.nodes4()
+    ints = n4.view(np.int32)
+    child = ints[:, 24:28]
+    assert not ints[:, 28:32].any()
+    inner = child[(child >= 0) & (child != 0x7FFFFFFF)]
+    assert np.array_equal(inner, np.arange(1, tree.n_nodes4))      # breadth-first, root = 0
+    lo, hi = n4[:, 0:12].reshape(-1, 3, 4), n4[:, 12:24].reshape(-1, 3, 4)
+    empty = child == 0x7FFFFFFF
+    assert (lo[:, 0][empty] > hi[:, 0][empty]).all() and (lo[:, 0][~empty] <= hi[:, 0][~empty]).all()
+    leaves = ~child[child < 0]
+    assert ((leaves & 7) + 1).sum() == len(tri)
+    # the collapse fills the nodes wherever an inner child was left to open: the top of the tree is full,
+    # only nodes whose children are all leaves stay narrower
+    occupied = (~empty).sum(1)
+    assert occupied[: tree.n_nodes4 // 4].mean() > 3.9 and occupied.mean() > 2.8
+    has_inner = ((child >= 0) & ~empty).any(1)
+    assert (occupied[has_inner] == 4).all()
+    assert tree.n_nodes4 < 0.55 * tree.n_nodes
+    assert tree.lib.bvh_h_depth4(tree.h) <= (tree.lib.bvh_h_depth(tree.h) + 1) // 2 + 3
 
 
 def test_layout_breadth_first_and_leaf_encoding(harness):
@@ -189,3 +254,5 @@ def test_boxes_are_conservative_for_grazing_hits(harness):
     t_tree, p_tree, _ = tree.trace(rays, brute=False)
     t_ref, p_ref, _ = tree.trace(rays, brute=True)
     assert np.array_equal(p_tree, p_ref) and np.array_equal(t_tree, t_ref)
+    t_w, p_w, _, _ = tree.trace4(rays)
+    assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
