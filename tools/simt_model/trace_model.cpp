@@ -443,9 +443,10 @@ static uint32_t morton_key(const Ray &r, int bits) {
     auto q = [&](float v) { int x = (int) ((v * 0.5f + 0.5f) * (1 << bits)); return (uint32_t) std::min(std::max(x, 0), (1 << bits) - 1); };
     uint32_t oct = (r.d.x < 0) | ((r.d.y < 0) << 1) | ((r.d.z < 0) << 2);
     if (bits >= 100) return oct;                       // direction octant only
+    bool cell_only = bits >= 10; if (cell_only) bits -= 10;   // 11, 12, 13: origin cell only
     uint32_t x = q(r.o.x), y = q(r.o.y), z = q(r.o.z), key = 0;
     for (int b = bits - 1; b >= 0; --b) key = (key << 3) | (((x >> b) & 1) << 2) | (((y >> b) & 1) << 1) | ((z >> b) & 1);
-    return (key << 3) | oct;
+    return cell_only ? key : (key << 3) | oct;
 }
 
 int main(int argc, char **argv) {
