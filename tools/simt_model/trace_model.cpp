@@ -55,6 +55,9 @@ struct Options {
     bool split_inplace = false; // same launch, work counter over [0, n) = shadow jobs, [n, 2n) = path jobs (slots without one idle)
     bool split_phases = false; // shadow rays of a wave in their own launch (no shadow/path mix inside a warp)
     int sort_bits = 0;        // > 0: sort the slots of each wave by a Morton key of (origin cell, direction octant)
+    int window = 0;           // > 0: after ordering, shuffle the slots inside consecutive windows of this many entries
+                              //      (the shading kernels compact survivors in atomic order: order is only kept at the
+                              //      granularity of one grid-stride iteration)
     bool verbose = false;
 };
 
@@ -458,7 +461,7 @@ int main(int argc, char **argv) {
         auto val = [&]() { return atoi(argv[++i]); };
         if (a == "--res") opt.res = val(); else if (a == "--spp") opt.spp = val(); else if (a == "--idle") opt.idle = val();
         else if (a == "--static") opt.dynamic = false; else if (a == "--wide") opt.wide = val(); else if (a == "--warps") opt.warps = val();
-        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true;
+        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true; else if (a == "--window") opt.window = val();
         else if (a == "--sort") opt.sort_bits = val(); else if (a == "--node-cost") cost.node = val(); else if (a == "--tri-cost") cost.tri = val();
         else if (a == "--retire-scale") { int p = val(); cost.ret_restart = cost.ret_restart * p / 100; cost.ret_hit = cost.ret_hit * p / 100; cost.refill_start = cost.refill_start * p / 100; }
         else if (a == "-v") opt.verbose = true;
@@ -534,6 +537,11 @@ int main(int argc, char **argv) {
             if (ns.alive || ns.has_shadow) next.push_back(ns);
         }
         if (opt.sort_bits > 0) std::stable_sort(next.begin(), next.end(), [&](const Slot &a, const Slot &b) { return morton_key(a.path, opt.sort_bits) < morton_key(b.path, opt.sort_bits); });
+        if (opt.window > 1)
+            for (size_t b = 0; b < next.size(); b += (size_t) opt.window) {
+                size_t e = std::min(next.size(), b + (size_t) opt.window);
+                for (size_t i = e - 1; i > b; --i) { size_t j = b + (size_t) (rng.next() * (float) (i - b + 1)); if (j > i) j = i; std::swap(next[i], next[j]); }
+            }
         slots.swap(next);
     }
     double W = total.total_warp(), T = total.total_thread();
