@@ -41,6 +41,8 @@ struct Costs {
     int n_queues = 5;
     // wide-node variants: cost of one node iteration with W children
     int node_wide(int w) const { return 40 + 28 * w; }   // loads + W slab tests + ordered push
+    int node_coop = 62;   // cooperative node step: own child box (2 loads, 1 slab test), rank by shuffles, ordered push
+    int leaf_coop = 92;   // cooperative leaf: one triangle per lane + shuffle reduction of (t, prim), incl. leaf overhead
 };
 
 struct Options {
@@ -51,6 +53,7 @@ struct Options {
     int wide = 2;
     int warps = 148 * 5 * 8;
     int tri_reject = 0;       // > 0: cost of a triangle iteration that the sign prefilter rejects
+    int coop = 0;             // > 0: `coop` lanes share one ray of a `coop`-wide tree: one child box / one leaf triangle per lane
     bool leaf_once = false;   // one round of triangle tests per pass of the outer loop (lanes holding a second leaf keep it for the next round)
     bool split_inplace = false; // same launch, work counter over [0, n) = shadow jobs, [n, 2n) = path jobs (slots without one idle)
     bool split_phases = false; // shadow rays of a wave in their own launch (no shadow/path mix inside a warp)
@@ -83,6 +86,8 @@ struct Scene {
 };
 
 static const int32_t SENT = 0x76543210;
+static int WS = 32;   // rays per warp
+static int TH = 1;    // threads cooperating on one ray (--coop: TH = tree width, WS = 32 / TH)
 
 static void load_scene(const Options &opt, Scene &sc) {
     FILE *f = fopen(opt.scene.c_str(), "rb");
@@ -204,7 +209,7 @@ static const char *region_name[R_COUNT] = { "node loop", "triangle tests", "leaf
 struct Counters {
     double warp_instr[R_COUNT] = {}, thread_instr[R_COUNT] = {};
     double rays = 0, node_steps = 0, tri_tests = 0;
-    void add(Region r, int cost, int active) { warp_instr[r] += cost; thread_instr[r] += (double) cost * active; }
+    void add(Region r, int cost, int active) { warp_instr[r] += cost; thread_instr[r] += (double) cost * active * TH; }
     double total_warp() const { double s = 0; for (double v : warp_instr) s += v; return s; }
     double total_thread() const { double s = 0; for (double v : thread_instr) s += v; return s; }
 };
@@ -252,13 +257,13 @@ static void node_step(Wave &w, Lane &l) {
 // traversal section of one pass of the job loop; `dyn_break` = leave when too few lanes still walk
 static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
     const Costs &C = *w.cost; const Options &O = *w.opt;
-    const int node_cost = O.wide <= 2 ? C.node : C.node_wide(O.wide);
+    const int node_cost = O.coop ? C.node_coop : O.wide <= 2 ? C.node : C.node_wide(O.wide);
     bool in_outer[32]; int n_outer = 0;
-    for (int i = 0; i < 32; ++i) { in_outer[i] = wp.ln[i].kind != 0 && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
+    for (int i = 0; i < WS; ++i) { in_outer[i] = wp.ln[i].kind != 0 && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
     while (n_outer > 0) {
         // ---- inner-node loop ----
         bool in_node[32]; int n_node = 0;
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < WS; ++i) {
             Lane &l = wp.ln[i];
             if (in_outer[i]) l.searching = O.leaf_once ? l.leaf >= 0 : true;
             in_node[i] = in_outer[i] && l.node >= 0 && l.node != SENT; n_node += in_node[i];
@@ -266,22 +271,23 @@ static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
         while (n_node > 0) {
             w.cnt.add(R_NODE, node_cost, n_node);
             bool any_searching = false;
-            for (int i = 0; i < 32; ++i) if (in_node[i]) { node_step(w, wp.ln[i]); any_searching |= wp.ln[i].searching; }
+            for (int i = 0; i < WS; ++i) if (in_node[i]) { node_step(w, wp.ln[i]); any_searching |= wp.ln[i].searching; }
             if (!any_searching) break;
             n_node = 0;
-            for (int i = 0; i < 32; ++i) { in_node[i] = in_node[i] && wp.ln[i].node >= 0 && wp.ln[i].node != SENT; n_node += in_node[i]; }
+            for (int i = 0; i < WS; ++i) { in_node[i] = in_node[i] && wp.ln[i].node >= 0 && wp.ln[i].node != SENT; n_node += in_node[i]; }
         }
         // ---- leaf loop ----
         while (true) {
             int n_leaf = 0, maxcount = 0; int cnts[32];
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < WS; ++i) {
                 cnts[i] = 0;
                 if (in_outer[i] && wp.ln[i].leaf < 0) { uint32_t enc = (uint32_t) ~wp.ln[i].leaf; cnts[i] = (int) (enc & 7u) + 1; n_leaf++; maxcount = std::max(maxcount, cnts[i]); }
             }
             if (!n_leaf) break;
             for (int k = 0; k < maxcount; ++k) {
+                const bool charge = !O.coop || k == 0;     // cooperative leaf: all its triangles in one iteration
                 int act = 0, act_full = 0;
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < WS; ++i) {
                     if (cnts[i] <= k) continue;
                     Lane &l = wp.ln[i]; act++;
                     uint32_t first = ((uint32_t) ~l.leaf) >> 3, ti = first + (uint32_t) k;
@@ -294,14 +300,16 @@ static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
                     }
                     w.cnt.tri_tests++;
                 }
+                if (!charge) continue;
+                if (O.coop) { w.cnt.add(R_TRI, C.leaf_coop, n_leaf); continue; }
                 if (O.tri_reject > 0) {
                     // prefilter executed by all, the exact tail only by the lanes that pass it
                     w.cnt.add(R_TRI, O.tri_reject, act);
                     if (act_full) w.cnt.add(R_TRI, C.tri - O.tri_reject + 8, act_full);
                 } else w.cnt.add(R_TRI, C.tri, act);
             }
-            w.cnt.add(R_LEAF, C.leaf_ovh, n_leaf);
-            for (int i = 0; i < 32; ++i) {
+            if (!O.coop) w.cnt.add(R_LEAF, C.leaf_ovh, n_leaf);
+            for (int i = 0; i < WS; ++i) {
                 if (!cnts[i]) continue;
                 Lane &l = wp.ln[i];
                 l.leaf = l.node;
@@ -311,9 +319,9 @@ static void traverse_section(Wave &w, Warp &wp, bool dyn_break) {
             if (O.leaf_once) break;
         }
         w.cnt.add(R_OUTER, C.outer, n_outer);
-        if (dyn_break && !wp.exhausted && n_outer < 32 - O.idle) break;
+        if (dyn_break && !wp.exhausted && n_outer < WS - std::max(1, O.idle * WS / 32)) break;
         n_outer = 0;
-        for (int i = 0; i < 32; ++i) { in_outer[i] = in_outer[i] && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
+        for (int i = 0; i < WS; ++i) { in_outer[i] = in_outer[i] && (wp.ln[i].node != SENT || wp.ln[i].leaf < 0); n_outer += in_outer[i]; }
     }
 }
 
@@ -339,7 +347,7 @@ static void begin_job(Wave &w, Lane &l, uint32_t slot, int &n_sh, int &n_pa) {
 static void retire_section(Wave &w, Warp &wp) {
     const Costs &C = *w.cost;
     int n_add = 0, n_restart = 0, n_finish = 0, n_hit = 0, n_miss = 0; bool any_bucket = false;
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < WS; ++i) {
         Lane &l = wp.ln[i];
         if (l.kind == 0 || l.node != SENT || l.leaf < 0) continue;
         const Slot &s = (*w.slots)[l.slot];
@@ -359,7 +367,7 @@ static void retire_section(Wave &w, Warp &wp) {
     if (n_finish) w.cnt.add(R_RETIRE, C.ret_finish, n_finish);
     if (n_hit) w.cnt.add(R_RETIRE, C.ret_hit, n_hit);
     if (n_miss) w.cnt.add(R_RETIRE, C.ret_miss, n_miss);
-    w.cnt.add(R_BUCKET, C.bucket_empty * C.n_queues + (any_bucket ? C.bucket_hit : 0), 32);
+    w.cnt.add(R_BUCKET, C.bucket_empty * C.n_queues + (any_bucket ? C.bucket_hit : 0), WS);
 }
 
 // one pass of the job loop of k_trace_dyn; false when the warp is done
@@ -367,18 +375,18 @@ static bool dyn_pass(Wave &w, Warp &wp) {
     const Costs &C = *w.cost; const Options &O = *w.opt;
     const uint32_t n = (uint32_t) w.slots->size() * ((w.opt->split_inplace && !w.first) ? 2u : 1u);
     double before = w.cnt.total_warp();
-    int idle = 0; for (int i = 0; i < 32; ++i) idle += wp.ln[i].kind == 0;
-    w.cnt.add(R_HEAD, C.head, 32);
-    if (!wp.exhausted && idle >= O.idle) {
+    int idle = 0; for (int i = 0; i < WS; ++i) idle += wp.ln[i].kind == 0;
+    w.cnt.add(R_HEAD, C.head, WS);
+    if (!wp.exhausted && idle >= std::max(1, O.idle * WS / 32)) {
         uint32_t base = w.work_counter; w.work_counter += (uint32_t) idle;
         if (base + idle >= n) wp.exhausted = true;
-        w.cnt.add(R_REFILL, C.refill_common, 32);
+        w.cnt.add(R_REFILL, C.refill_common, WS);
         int n_sh = 0, n_pa = 0; uint32_t k = 0;
-        for (int i = 0; i < 32; ++i) if (wp.ln[i].kind == 0) { uint32_t s = base + k++; if (s < n) begin_job(w, wp.ln[i], s, n_sh, n_pa); }
+        for (int i = 0; i < WS; ++i) if (wp.ln[i].kind == 0) { uint32_t s = base + k++; if (s < n) begin_job(w, wp.ln[i], s, n_sh, n_pa); }
         if (n_sh) w.cnt.add(R_REFILL, C.refill_start, n_sh);
         if (n_pa) w.cnt.add(R_REFILL, C.refill_start, n_pa);
     }
-    bool any = false; for (int i = 0; i < 32; ++i) any |= wp.ln[i].kind != 0;
+    bool any = false; for (int i = 0; i < WS; ++i) any |= wp.ln[i].kind != 0;
     if (!any) { wp.clock += w.cnt.total_warp() - before; return !wp.exhausted; }   // empty jobs (split ranges): fetch again
     traverse_section(w, wp, true);
     retire_section(w, wp);
@@ -391,26 +399,26 @@ static bool static_pass(Wave &w, Warp &wp, uint32_t n_warps) {
     const Costs &C = *w.cost;
     const uint32_t n = (uint32_t) w.slots->size();
     double before = w.cnt.total_warp();
-    if (!wp.static_loaded) { wp.static_loaded = true; } else wp.static_base += n_warps * 32u;
+    if (!wp.static_loaded) { wp.static_loaded = true; } else wp.static_base += n_warps * (uint32_t) WS;
     if (wp.static_base >= n) return false;
     int n_sh = 0, n_pa = 0;
     wp.exhausted = true;
     // phase 1: shadow rays
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < WS; ++i) {
         Lane &l = wp.ln[i]; l.kind = 0; uint32_t s = wp.static_base + i;
         if (s < n && !w.first && (*w.slots)[s].has_shadow) { l.slot = s; l.kind = 1; start_ray(l, (*w.slots)[s].sh); n_sh++; w.cnt.rays++; }
     }
     if (n_sh) { w.cnt.add(R_REFILL, C.refill_start, n_sh); traverse_section(w, wp, false); }
-    int n_add = 0; for (int i = 0; i < 32; ++i) if (wp.ln[i].kind == 1 && !wp.ln[i].occluded) n_add++;
+    int n_add = 0; for (int i = 0; i < WS; ++i) if (wp.ln[i].kind == 1 && !wp.ln[i].occluded) n_add++;
     if (n_add) w.cnt.add(R_RETIRE, C.ret_shadow_add, n_add);
     // phase 2: path rays
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < WS; ++i) {
         Lane &l = wp.ln[i]; l.kind = 0; uint32_t s = wp.static_base + i;
         if (s < n) { (*w.hits)[s] = { INFINITY, 0xffffffffu }; if (w.first || (*w.slots)[s].alive) { l.slot = s; l.kind = 2; start_ray(l, (*w.slots)[s].path); n_pa++; w.cnt.rays++; } }
     }
     if (n_pa) { w.cnt.add(R_REFILL, C.refill_start, n_pa); traverse_section(w, wp, false); }
     retire_section(w, wp);
-    w.cnt.add(R_HEAD, C.head, 32);
+    w.cnt.add(R_HEAD, C.head, WS);
     wp.clock += w.cnt.total_warp() - before;
     return true;
 }
@@ -419,9 +427,9 @@ static Counters run_wave(const Scene &sc, const Options &opt, const Costs &cost,
                          std::vector<uint32_t> &retire_order, bool first) {
     Wave w; w.sc = &sc; w.opt = &opt; w.cost = &cost; w.slots = &slots; w.hits = &hits; w.retire_order = &retire_order; w.first = first;
     hits.assign(slots.size(), { INFINITY, 0xffffffffu }); retire_order.clear();
-    uint32_t n_warps = (uint32_t) std::min<size_t>((size_t) opt.warps, (slots.size() + 255) / 256 * 8);
+    uint32_t n_warps = (uint32_t) std::min<size_t>((size_t) opt.warps, (slots.size() * TH + 255) / 256 * 8);
     std::vector<Warp> warps(n_warps);
-    for (uint32_t i = 0; i < n_warps; ++i) warps[i].static_base = i * 32u;
+    for (uint32_t i = 0; i < n_warps; ++i) warps[i].static_base = i * (uint32_t) WS;
     using QE = std::pair<double, uint32_t>;
     std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
     for (uint32_t i = 0; i < n_warps; ++i) pq.push({ 0.0, i });
@@ -461,7 +469,8 @@ int main(int argc, char **argv) {
         auto val = [&]() { return atoi(argv[++i]); };
         if (a == "--res") opt.res = val(); else if (a == "--spp") opt.spp = val(); else if (a == "--idle") opt.idle = val();
         else if (a == "--static") opt.dynamic = false; else if (a == "--wide") opt.wide = val(); else if (a == "--warps") opt.warps = val();
-        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true; else if (a == "--window") opt.window = val();
+        else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true; else if (a == "--window") opt.window = val(); else if (a == "--coop") { opt.coop = val(); opt.wide = opt.coop; TH = opt.coop; WS = 32 / TH; }
+        else if (a == "--node-coop") cost.node_coop = val();
         else if (a == "--sort") opt.sort_bits = val(); else if (a == "--node-cost") cost.node = val(); else if (a == "--tri-cost") cost.tri = val();
         else if (a == "--retire-scale") { int p = val(); cost.ret_restart = cost.ret_restart * p / 100; cost.ret_hit = cost.ret_hit * p / 100; cost.refill_start = cost.refill_start * p / 100; }
         else if (a == "-v") opt.verbose = true;
