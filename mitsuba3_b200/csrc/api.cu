@@ -342,6 +342,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
+    { const char *e = getenv("B200PT_TRACE_PHASES"); s->launch.split_phases = e ? atoi(e) != 0 : false; }   // experimental, see k_trace_dyn
     set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
@@ -474,6 +475,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
         launch_trace(d, cfg, w.buf[bufi], w.hit, n_in, w.q, qcounts, w.lane_result, s->stats_dev, first, L, st);
         if (s->profile) cudaEventRecord(e1, st);
         s->stats.kernel_launches++; s->stats.trace_launches++;
+        if (!first && L.dynamic_fetch && L.split_phases) { s->stats.kernel_launches++; s->stats.trace_launches++; }
     };
     int cur = 0;
     trace(cur, nullptr, w.counts + 0, true);

@@ -323,12 +323,18 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 // ray of the batch. The traversal itself is the same speculative while-while walk,
 // resumable across refills (node / leaf / stack live in registers + local memory).
 // Semantics per slot are identical to k_trace.
+//
+// PHASE (experimental, off by default: B200PT_TRACE_PHASES=1; profiles/r01_simt_model.md, "separate job
+// ranges"): 0 = a job is the shadow ray of a slot followed by its path ray (above); 1 = shadow rays only,
+// 2 = path rays only, as two launches over the same slots -- any-hit and closest-hit walks no longer share
+// warps. A slot without the ray of the phase is an empty job. Launch 1 completes before launch 2 starts
+// (same stream), so a path that ends in launch 2 reads `result` with its shadow contribution already added.
 // ---------------------------------------------------------------------------
 
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 5
 #endif
-template <bool FIRST, bool SMEM_ALL>
+template <bool FIRST, bool SMEM_ALL, int PHASE = 0>
 __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
@@ -377,7 +383,19 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 if (i < n) {
                     slot = i;
                     flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w);
-                    if (!FIRST && (flags & PF_HAS_SHADOW)) {
+                    if (PHASE == 1) {          // shadow rays only; a slot without one is an empty job
+                        if (flags & PF_HAS_SHADOW) {
+                            float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                            kind = 1; n_shadow++;
+                            start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
+                        }
+                    } else if (PHASE == 2) {   // path rays only
+                        if (flags & PF_ALIVE) {
+                            float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                            kind = 2; n_closest++;
+                            start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
+                        }
+                    } else if (!FIRST && (flags & PF_HAS_SHADOW)) {
                         float4 so = cur.sh_o[i], sd = cur.sh_d[i];
                         kind = 1; n_shadow++;
                         start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
@@ -389,7 +407,10 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, kind != 0)) break;
+        if (!__any_sync(0xffffffffu, kind != 0)) {
+            if (PHASE != 0 && !exhausted) continue;     // only empty jobs came back: fetch again
+            break;
+        }
 
         // ---- traverse until this lane's ray is done or the warp wants to refill -----------
         if (kind != 0) {
@@ -443,7 +464,10 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                     res.x += sd.w; res.y += cc.x; res.z += cc.y;
                     cur.result[slot] = res;
                 }
-                if (flags & PF_ALIVE) {
+                if (PHASE == 1) {          // the path ray of the slot belongs to the second launch
+                    if (!(flags & PF_ALIVE)) lane_result[cur.rng[slot].w] = cur.result[slot];
+                    kind = 0;
+                } else if (flags & PF_ALIVE) {
                     float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
                     kind = 2; n_closest++;
                     start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
@@ -1027,8 +1051,14 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
     if (L.dynamic_fetch) {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
+#define LAUNCH_DYN_PHASE(A, P, CTR) k_trace_dyn<false, A, P><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
         if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
+        else if (L.split_phases) {      // experimental: shadow rays, then path rays (work counters 5 and 7 of the bounce's block)
+            if (all) { LAUNCH_DYN_PHASE(true, 1, 5); LAUNCH_DYN_PHASE(true, 2, 7); }
+            else { LAUNCH_DYN_PHASE(false, 1, 5); LAUNCH_DYN_PHASE(false, 2, 7); }
+        }
         else { if (all) LAUNCH_DYN(false, true); else LAUNCH_DYN(false, false); }
+#undef LAUNCH_DYN_PHASE
 #undef LAUNCH_DYN
         return;
     }
@@ -1118,6 +1148,10 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

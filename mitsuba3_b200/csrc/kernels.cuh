@@ -55,7 +55,9 @@ struct RenderCfg {
 constexpr int BLOCK = 256;
 constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 registers -> 4 blocks / SM
 
-struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle; };
+struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
+                bool split_phases;   // experimental (B200PT_TRACE_PHASES=1): shadow rays and path rays of a wave as two launches
+};
 
 // counters in the stats buffer
 enum { ST_BOUNCES = 0, ST_SHADOW = 1, ST_CLOSEST = 2, ST_COUNT = 8 };

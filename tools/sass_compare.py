@@ -1,0 +1,29 @@
+"""Compare two `cuobjdump -sass` dumps kernel by kernel (instruction text + encodings, whitespace-insensitive).
+
+    cuobjdump -sass old/libb200pt.so > old.sass; cuobjdump -sass mitsuba3_b200/lib/libb200pt.so > new.sass
+    python tools/sass_compare.py old.sass new.sass
+
+Used to show that staging an experimental, default-off variant (a new template instantiation) leaves the
+device code of every shipped kernel untouched when no GPU is at hand to re-measure.
+"""
+import re,hashlib,sys
+def funcs(path):
+    out={}; cur=None; buf=[]
+    for line in open(path):
+        m=re.match(r'\s*Function : (\S+)',line)
+        if m:
+            if cur: out[cur]=hashlib.md5(''.join(buf).encode()).hexdigest()
+            cur=m.group(1); buf=[]
+        elif cur:
+            t=re.sub(r'\s+',' ',line).strip()
+            if t: buf.append(t+'\n')
+    if cur: out[cur]=hashlib.md5(''.join(buf).encode()).hexdigest()
+    return out
+base=funcs(sys.argv[1]); new=funcs(sys.argv[2])
+def norm(k): return k.replace('ELi0EEEvNS_8DevSceneENS_9RenderCfgENS_7PathBufEP6float4PKjNS_6Queues','EEEvNS_8DevSceneENS_9RenderCfgENS_7PathBufEP6float4PKjNS_6Queues') if 'k_trace_dyn' in k else k
+newn={norm(k):v for k,v in new.items()}
+bad=0
+for k in base:
+    if k not in newn: print('MISSING',k[:80]); bad+=1
+    elif base[k]!=newn[k]: print('DIFF',k[:80]); bad+=1
+print(len(base),'kernels compared,',bad,'differ;', len(new)-len(base),'new kernels')
