@@ -43,6 +43,8 @@ struct Wavefront {
     float4 *hit = nullptr, *lane_result = nullptr, *lane_dL = nullptr;
     Queues q;
     uint32_t *counts = nullptr; size_t n_counts = 0;
+    // experimental cell ordering of the material queues (B200PT_CELL_ORDER=1), see kernels.cu: k_cell_keys
+    uint2 *cell_keyrank = nullptr; uint32_t *cell_hist = nullptr, *cell_offsets = nullptr, *cell_sorted = nullptr;
     std::vector<void *> allocs;
 };
 
@@ -55,6 +57,7 @@ struct b200pt_scene {
     size_t grad_floats = 0;
     uint32_t n_sm = 148;
     Launch launch;
+    bool cell_order = false; CellGrid cell_grid;     // experimental, off by default
     Wavefront wf;
     // shard pixel list cache
     uint32_t *pix_ids = nullptr; uint32_t n_pix_ids = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
@@ -285,6 +288,15 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         }
         vo += sh.n_vertices; po += sh.n_faces;
     }
+    if (const char *e = getenv("B200PT_CELL_ORDER")) s->cell_order = atoi(e) != 0;
+    if (s->cell_order) {      // grid of the experimental cell ordering: the bounding box of the vertices
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (size_t v = 0; v < n_verts; ++v)
+            for (int k = 0; k < 3; ++k) { float x = verts[v * 8 + k]; lo[k] = std::fmin(lo[k], x); hi[k] = std::fmax(hi[k], x); }
+        float sc3[3];
+        for (int k = 0; k < 3; ++k) { if (!(hi[k] > lo[k])) { lo[k] = 0.f; hi[k] = 1.f; } sc3[k] = (float) CELL_AXIS / std::fmax(hi[k] - lo[k], 1e-20f); }
+        s->cell_grid.lo = make_float3(lo[0], lo[1], lo[2]); s->cell_grid.scale = make_float3(sc3[0], sc3[1], sc3[2]);
+    }
     if (env_index >= 0) {
         scene_bounding_sphere(verts.data(), n_verts, henv.center, henv.radius);
         DevEnv *de = nullptr; S_TRY(dev_upload(s, &henv, 1, &de)); d.env = de;
@@ -412,6 +424,11 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
     if (s->dev.env_type >= 0) CU_TRY(A(slack * 4, (void **) &w.q.slots[Q_ENV])); else w.q.slots[Q_ENV] = nullptr;
     w.n_counts = (size_t) (MAX_BOUNCE_SLOTS + 2) * 8;
     CU_TRY(A(w.n_counts * 4, (void **) &w.counts));
+    w.cell_keyrank = nullptr; w.cell_hist = w.cell_offsets = w.cell_sorted = nullptr;
+    if (s->cell_order) {
+        CU_TRY(A(slack * 8, (void **) &w.cell_keyrank)); CU_TRY(A(slack * 4, (void **) &w.cell_sorted));
+        CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_hist)); CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_offsets));
+    }
     w.q.counts = w.counts;
     w.cap = cap;
     return B200PT_OK;
@@ -463,6 +480,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     uint32_t lanes = cfg.chunk_lanes;
     cfg.adjoint = mode >= 1; cfg.forward = mode == 2;
     CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
+    if (s->cell_order) CU_TRY(cudaMemsetAsync(w.cell_hist, 0, CELL_BINS * 4, st));
     int g_all = grid_for(s, lanes);
     launch_generate(d, cfg, s->pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
     s->stats.kernel_launches++;
@@ -488,7 +506,12 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
         }
         for (int t = 0; t < N_BSDF_TYPES; ++t) {
             if (!s->type_present[t]) continue;
-            launch_shade(t, d, cfg, w.buf[cur], w.hit, w.q.slots[t], cnt + t, w.buf[cur ^ 1], cnt + 4, w.lane_result, s->stats_dev, Ls, st);
+            const uint32_t *queue = w.q.slots[t];
+            if (s->cell_order) {      // experimental: shade the queue cell by cell of the hit points
+                launch_cell_order(w.buf[cur], w.hit, w.q.slots[t], cnt + t, s->cell_grid, w.cell_keyrank, w.cell_hist, w.cell_offsets, w.cell_sorted, g_all, st);
+                queue = w.cell_sorted; s->stats.kernel_launches += 3;
+            }
+            launch_shade(t, d, cfg, w.buf[cur], w.hit, queue, cnt + t, w.buf[cur ^ 1], cnt + 4, w.lane_result, s->stats_dev, Ls, st);
             s->stats.kernel_launches++;
         }
         cur ^= 1;

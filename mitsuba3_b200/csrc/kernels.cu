@@ -1039,8 +1039,78 @@ __global__ void k_bsdf_eval(DevScene sc, uint32_t bsdf, uint32_t n, const float 
 }
 
 // ---------------------------------------------------------------------------
+// Experimental, off by default (B200PT_CELL_ORDER=1; profiles/r01_simt_model.md section 3.1, not yet run on a
+// GPU): reorder a material queue by the 8 x 8 x 8 cell of the hit point before it is shaded. The shading
+// kernels compact their survivors in processing order, so the next wave's slots end up grouped by ray
+// origin and the traversal warps see more coherent rays. Counting sort in three small launches:
+//   k_cell_keys     per queue entry: cell id of o + t d, rank inside the cell (warp-aggregated atomicAdd)
+//   k_cell_scan     exclusive scan of the 512 counters (and resets them for the next queue)
+//   k_cell_scatter  sorted[offset[cell] + rank] = slot
+// Per-lane results do not depend on the slot order (every lane carries its own RNG and film position).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_cell_keys(PathBuf cur, const float4 *__restrict__ hit, const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount,
+                                                     CellGrid g, uint2 *__restrict__ keyrank, uint32_t *__restrict__ hist) {
+    const uint32_t n = *qcount;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
+        uint32_t qi = base + lane_id;
+        bool valid = qi < n;
+        uint32_t key = 0xffffffffu;
+        if (valid) {
+            uint32_t slot = queue[qi];
+            float4 o = cur.ray_o[slot], d = cur.ray_d[slot];
+            float t = hit[slot].x;
+            int cx = (int) ((__fmaf_rn(t, d.x, o.x) - g.lo.x) * g.scale.x);
+            int cy = (int) ((__fmaf_rn(t, d.y, o.y) - g.lo.y) * g.scale.y);
+            int cz = (int) ((__fmaf_rn(t, d.z, o.z) - g.lo.z) * g.scale.z);
+            cx = min(CELL_AXIS - 1, max(0, cx)); cy = min(CELL_AXIS - 1, max(0, cy)); cz = min(CELL_AXIS - 1, max(0, cz));
+            key = (uint32_t) ((cz * CELL_AXIS + cy) * CELL_AXIS + cx);
+        }
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t leader = __ffs(peers) - 1, first = 0;
+        if (valid && lane_id == leader) first = atomicAdd(&hist[key], (uint32_t) __popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) keyrank[qi] = make_uint2(key, first + __popc(peers & ((1u << lane_id) - 1u)));
+    }
+}
+
+__global__ void __launch_bounds__(CELL_BINS) k_cell_scan(uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets) {
+    __shared__ uint32_t sh[CELL_BINS];
+    const uint32_t t = threadIdx.x;
+    const uint32_t v = hist[t];
+    hist[t] = 0;                      // ready for the next queue
+    sh[t] = v;
+    __syncthreads();
+    for (uint32_t of = 1; of < CELL_BINS; of <<= 1) {
+        uint32_t add = t >= of ? sh[t - of] : 0u;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    offsets[t] = sh[t] - v;           // exclusive
+}
+
+__global__ void __launch_bounds__(BLOCK) k_cell_scatter(const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, const uint2 *__restrict__ keyrank,
+                                                        const uint32_t *__restrict__ offsets, uint32_t *__restrict__ sorted) {
+    const uint32_t n = *qcount;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += stride) {
+        uint2 kr = keyrank[qi];
+        sorted[offsets[kr.x] + kr.y] = queue[qi];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
+void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount, const CellGrid &g, uint2 *keyrank,
+                       uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st) {
+    k_cell_keys<<<grid, BLOCK, 0, st>>>(cur, hit, queue, qcount, g, keyrank, hist);
+    k_cell_scan<<<1, CELL_BINS, 0, st>>>(hist, offsets);
+    k_cell_scatter<<<grid, BLOCK, 0, st>>>(queue, qcount, keyrank, offsets, sorted);
+}
+
 void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, PathBuf buf, const float4 *adj_dL_lane,
                      const float4 *adj_L_lane, int grid, cudaStream_t st) {
     k_generate<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, buf, adj_dL_lane, adj_L_lane);

@@ -59,6 +59,10 @@ struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes,
                 bool split_phases;   // experimental (B200PT_TRACE_PHASES=1): shadow rays and path rays of a wave as two launches
 };
 
+// experimental cell ordering of the material queues (kernels.cu: k_cell_keys), off by default
+constexpr int CELL_AXIS = 8, CELL_BINS = CELL_AXIS * CELL_AXIS * CELL_AXIS;
+struct CellGrid { float3 lo, scale; };     // cell = clamp(int((p - lo) * scale), 0, CELL_AXIS - 1) per axis
+
 // counters in the stats buffer
 enum { ST_BOUNCES = 0, ST_SHADOW = 1, ST_CLOSEST = 2, ST_COUNT = 8 };
 
@@ -70,6 +74,8 @@ void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cu
                   const uint32_t *qcount, PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st);
 void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
                       float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st);
+void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount, const CellGrid &g, uint2 *keyrank,
+                       uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,
