@@ -355,7 +355,18 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
     { const char *e = getenv("B200PT_TRACE_PHASES"); s->launch.split_phases = e ? atoi(e) != 0 : false; }   // experimental, see k_trace_dyn
-    set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
+    s->launch.wide = false; s->launch.nodes4 = nullptr; s->launch.n_nodes4_units = 0; s->launch.n_smem_nodes_w = 0; s->launch.smem_trace_w = 0;
+    if (const char *e = getenv("B200PT_BVH_WIDE")) if (atoi(e) != 0) {      // experimental 4-wide walk, see k_trace_dyn
+        Bvh4 wide = collapse_bvh4(bvh);
+        if (3 * ((size_t) wide.depth + 1) + 2 <= 128) {                      // fits the stack of the wide walk
+            Bvh4Node *p; S_TRY(dev_upload(s, wide.nodes.data(), wide.nodes.size(), &p));
+            s->launch.wide = true; s->launch.nodes4 = (const float4 *) p;
+            s->launch.n_nodes4_units = (uint32_t) (2 * wide.nodes.size());                      // in 64-byte units
+            s->launch.n_smem_nodes_w = std::min<uint32_t>(s->launch.n_nodes4_units, 512);       // 32 KiB = 256 wide nodes
+            s->launch.smem_trace_w = ((size_t) s->launch.n_smem_nodes_w * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
+        }
+    }
+    set_trace_smem_attr(std::max(s->launch.smem_trace, s->launch.smem_trace_w) + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
     S_TRY(cudaMalloc(&s->film_own, npix * 4 * sizeof(float))); s->allocs.push_back(s->film_own);

@@ -122,6 +122,14 @@ PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
     return tri < c.n_smem_tris ? c.s_tris[3 * tri + k] : __ldg(&c.g_tris[3 * (size_t) tri + k]);
 }
 
+// 4-wide nodes (bvh.h: Bvh4Node, 8 x float4) of the experimental wide walk; the shared-memory window is
+// counted in 64-byte units like the binary nodes (a wide node = two units)
+template <bool SMEM_ALL>
+PT_DEV float4 ld_node4(const TraceCtx &c, uint32_t node, int k) {
+    if (SMEM_ALL) return c.s_nodes[8 * node + k];
+    return 2 * node + 1 < c.n_smem_nodes ? c.s_nodes[8 * node + k] : __ldg(&c.g_nodes[8 * (size_t) node + k]);
+}
+
 PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
 
 // slab test, subtraction first (no cancellation against o * inv)
@@ -329,12 +337,17 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 // 2 = path rays only, as two launches over the same slots -- any-hit and closest-hit walks no longer share
 // warps. A slot without the ray of the phase is an empty job. Launch 1 completes before launch 2 starts
 // (same stream), so a path that ends in launch 2 reads `result` with its shadow contribution already added.
+//
+// WIDE (experimental, off by default: B200PT_BVH_WIDE=1, section 3.3 of the same note): the inner-node loop
+// walks the 4-wide tree of pt::collapse_bvh4 -- `sc.nodes` then points to the Bvh4Node array, four slab tests
+// per step, children ordered near to far by a 5-exchange sorting network, up to three pushes. Leaves, the
+// triangle test and the tie-break are the binary walk's, so the hits are the same.
 // ---------------------------------------------------------------------------
 
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 5
 #endif
-template <bool FIRST, bool SMEM_ALL, int PHASE = 0>
+template <bool FIRST, bool SMEM_ALL, int PHASE = 0, bool WIDE = false>
 __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
     float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
     float maxt = 0.f;
     Hit hit; hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
-    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
+    int32_t stack[WIDE ? 128 : 64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
     bool occluded = false;
     bool exhausted = false;           // the global pool is empty
 
@@ -417,6 +430,27 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
             while (node != TRAV_SENTINEL) {
                 bool searching = true;
                 while (node >= 0 && node != TRAV_SENTINEL) {
+                    if (WIDE) {
+                        float4 lox = ld_node4<SMEM_ALL>(c, node, 0), loy = ld_node4<SMEM_ALL>(c, node, 1), loz = ld_node4<SMEM_ALL>(c, node, 2);
+                        float4 hix = ld_node4<SMEM_ALL>(c, node, 3), hiy = ld_node4<SMEM_ALL>(c, node, 4), hiz = ld_node4<SMEM_ALL>(c, node, 5);
+                        float4 chf = ld_node4<SMEM_ALL>(c, node, 6);
+                        int32_t c0 = __float_as_int(chf.x), c1 = __float_as_int(chf.y), c2 = __float_as_int(chf.z), c3 = __float_as_int(chf.w);
+                        float t0, t1, t2, t3;
+                        bool h0 = box_hit(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, o, inv, maxt, t0) & (c0 != 0x7fffffff);
+                        bool h1 = box_hit(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, o, inv, maxt, t1) & (c1 != 0x7fffffff);
+                        bool h2 = box_hit(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, o, inv, maxt, t2) & (c2 != 0x7fffffff);
+                        bool h3 = box_hit(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, o, inv, maxt, t3) & (c3 != 0x7fffffff);
+                        // children that are missed sort last
+                        t0 = h0 ? t0 : PT_INF; t1 = h1 ? t1 : PT_INF; t2 = h2 ? t2 : PT_INF; t3 = h3 ? t3 : PT_INF;
+#define PT_CSWAP(ta, ca, tb, cb) { bool sw = tb < ta; float tlo = sw ? tb : ta, thi = sw ? ta : tb; int32_t clo = sw ? cb : ca, chi = sw ? ca : cb; ta = tlo; tb = thi; ca = clo; cb = chi; }
+                        PT_CSWAP(t0, c0, t1, c1) PT_CSWAP(t2, c2, t3, c3) PT_CSWAP(t0, c0, t2, c2) PT_CSWAP(t1, c1, t3, c3) PT_CSWAP(t1, c1, t2, c2)
+#undef PT_CSWAP
+                        // the far children go onto the stack farthest first, the walk continues in the nearest
+                        if (t3 < PT_INF) stack[++sp] = c3;
+                        if (t2 < PT_INF) stack[++sp] = c2;
+                        if (t1 < PT_INF) stack[++sp] = c1;
+                        node = t0 < PT_INF ? c0 : stack[sp--];
+                    } else {
                     float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
                     int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                     float tl, tr;
@@ -430,6 +464,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                             if (tr < tl) { far = cl; node = cr; }
                             stack[++sp] = far;
                         }
+                    }
                     }
                     if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }
                     if (!__any_sync(__activemask(), searching)) break;
@@ -1119,6 +1154,20 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
+    if (L.dynamic_fetch && L.wide) {
+        // experimental 4-wide walk: the kernel's scene copy points to the Bvh4Node array (counted in 64-byte units)
+        DevScene scw = sc; scw.nodes = L.nodes4; scw.n_nodes = L.n_nodes4_units;
+        const bool allw = L.n_smem_nodes_w == scw.n_nodes && L.n_smem_tris == sc.n_tris;
+#define LAUNCH_WIDE(F, A, P, CTR) k_trace_dyn<F, A, P, true><<<L.grid, BLOCK, L.smem_trace_w + L.smem_tables, st>>>(scw, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, L.n_smem_nodes_w, L.n_smem_tris, L.refill_idle)
+        if (first) { if (allw) LAUNCH_WIDE(true, true, 0, 5); else LAUNCH_WIDE(true, false, 0, 5); }
+        else if (L.split_phases) {
+            if (allw) { LAUNCH_WIDE(false, true, 1, 5); LAUNCH_WIDE(false, true, 2, 7); }
+            else { LAUNCH_WIDE(false, false, 1, 5); LAUNCH_WIDE(false, false, 2, 7); }
+        }
+        else { if (allw) LAUNCH_WIDE(false, true, 0, 5); else LAUNCH_WIDE(false, false, 0, 5); }
+#undef LAUNCH_WIDE
+        return;
+    }
     if (L.dynamic_fetch) {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
 #define LAUNCH_DYN_PHASE(A, P, CTR) k_trace_dyn<false, A, P><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
@@ -1222,6 +1271,14 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<true, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_dyn<false, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

@@ -57,6 +57,8 @@ constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 regis
 
 struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
                 bool split_phases;   // experimental (B200PT_TRACE_PHASES=1): shadow rays and path rays of a wave as two launches
+                // experimental (B200PT_BVH_WIDE=1): 4-wide walk over the Bvh4Node array, sizes in 64-byte units
+                bool wide; const float4 *nodes4; uint32_t n_nodes4_units, n_smem_nodes_w; size_t smem_trace_w;
 };
 
 // experimental cell ordering of the material queues (kernels.cu: k_cell_keys), off by default

@@ -243,4 +243,63 @@ void bvh_h_trace4(void *p, uint32_t n_rays, const float *rays, float *t_out, uin
     if (n_steps) *n_steps = steps;
 }
 
+// The node step of the wide walk exactly as the traversal kernel does it (kernels.cu, k_trace_dyn<.., WIDE>):
+// four slab tests with the near distance, misses sorted last by the 5-exchange network, far children pushed
+// farthest first, descent into the nearest; a fixed-size stack whose high-water mark is reported.
+static bool slab_near(const float *lo, const float *hi, const float *o, const float *inv, float tmax, float &tnear) {
+    float t0x = (lo[0] - o[0]) * inv[0], t1x = (hi[0] - o[0]) * inv[0];
+    float t0y = (lo[1] - o[1]) * inv[1], t1y = (hi[1] - o[1]) * inv[1];
+    float t0z = (lo[2] - o[2]) * inv[2], t1z = (hi[2] - o[2]) * inv[2];
+    float tmin = std::fmax(std::fmax(std::fmin(t0x, t1x), std::fmin(t0y, t1y)), std::fmax(std::fmin(t0z, t1z), 0.f));
+    float tmx = std::fmin(std::fmin(std::fmax(t0x, t1x), std::fmax(t0y, t1y)), std::fmin(std::fmax(t0z, t1z), tmax));
+    tnear = tmin;
+    return tmin <= tmx * 1.0000004f;
+}
+
+void bvh_h_trace4_ordered(void *p, uint32_t n_rays, const float *rays, int any_hit, float *t_out, uint32_t *prim_out, uint32_t *max_sp_out) {
+    Handle *h = (Handle *) p; const pt::Bvh &b = h->bvh; const pt::Bvh4 &w = h->wide;
+    const int32_t SENT = 0x76543210;
+    int max_sp = 0;
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        const float *o = rays + 7 * (size_t) r, *d = o + 3; float maxt = o[6];
+        float best = INFINITY; uint32_t prim = 0xffffffffu; bool occluded = false;
+        float inv[3]; for (int a = 0; a < 3; ++a) inv[a] = std::fabs(d[a]) > 1e-30f ? 1.f / d[a] : std::copysign(1e30f, d[a]);
+        int32_t stack[128]; int sp = 0; stack[0] = SENT; int32_t node = 0;
+        while (node != SENT && !occluded) {
+            if (node < 0) {
+                uint32_t enc = (uint32_t) ~node, first = enc >> 3, count = (enc & 7u) + 1u;
+                for (uint32_t i = first; i < first + count; ++i) {
+                    float t; uint32_t g = b.order[i];
+                    if (tri_test(&h->tri[9 * (size_t) g], o, d, maxt, t)) {
+                        if (any_hit) occluded = true;
+                        else if (t < best || (t == best && g < prim)) { best = t; prim = g; maxt = t; }
+                    }
+                }
+                node = stack[sp--];
+                continue;
+            }
+            const pt::Bvh4Node &nd = w.nodes[node];
+            float t[4]; int32_t c[4];
+            for (int k = 0; k < 4; ++k) {
+                float lo[3] = { nd.lo[0][k], nd.lo[1][k], nd.lo[2][k] }, hi[3] = { nd.hi[0][k], nd.hi[1][k], nd.hi[2][k] };
+                c[k] = nd.child[k];
+                bool hit = slab_near(lo, hi, o, inv, maxt, t[k]) & (c[k] != pt::BVH_EMPTY);
+                t[k] = hit ? t[k] : INFINITY;
+            }
+#define CSWAP(i, j) { bool sw = t[j] < t[i]; float tlo = sw ? t[j] : t[i], thi = sw ? t[i] : t[j]; int32_t clo = sw ? c[j] : c[i], chi = sw ? c[i] : c[j]; t[i] = tlo; t[j] = thi; c[i] = clo; c[j] = chi; }
+            CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+#undef CSWAP
+            if (!(t[0] <= t[1] && t[1] <= t[2] && t[2] <= t[3])) { t_out[r] = -1.f; prim_out[r] = 0xfffffffeu; goto next_ray; }   // network failed to sort
+            if (t[3] < INFINITY) stack[++sp] = c[3];
+            if (t[2] < INFINITY) stack[++sp] = c[2];
+            if (t[1] < INFINITY) stack[++sp] = c[1];
+            if (sp > max_sp) max_sp = sp;
+            node = t[0] < INFINITY ? c[0] : stack[sp--];
+        }
+        t_out[r] = any_hit ? (occluded ? 1.f : 0.f) : best; prim_out[r] = prim;
+    next_ray:;
+    }
+    if (max_sp_out) *max_sp_out = (uint32_t) max_sp;
+}
+
 } // extern "C"

@@ -50,6 +50,7 @@ def harness():
     lib.bvh_h_nodes4.argtypes = [ctypes.c_void_p]
     lib.bvh_h_validate4.restype = ctypes.c_int
     lib.bvh_h_validate4.argtypes = [ctypes.c_void_p]
+    lib.bvh_h_trace4_ordered.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.bvh_h_trace4.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
@@ -98,6 +99,15 @@ class Tree:
 
     def validate4(self):
         return self.lib.bvh_h_validate4(self.h)
+
+    def trace4_ordered(self, rays, any_hit=False):
+        """The wide walk with the traversal kernel's node step (near-to-far network, push order, fixed stack)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        t = np.empty(len(rays), np.float32)
+        prim = np.empty(len(rays), np.uint32)
+        max_sp = ctypes.c_uint32(0)
+        self.lib.bvh_h_trace4_ordered(self.h, len(rays), rays.ctypes.data, int(any_hit), t.ctypes.data, prim.ctypes.data, ctypes.byref(max_sp))
+        return t, prim, max_sp.value
 
     def trace4(self, rays):
         rays = np.ascontiguousarray(rays, np.float32)
@@ -177,6 +187,13 @@ def test_invariants_and_walk_equals_brute_force(harness, name):
     assert tree.validate4() == 0
     t_w, p_w, n_w, steps4 = tree.trace4(rays)
     assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
+    # the node step of the traversal kernel (sorting network, push order, fixed stack): same hits, the same
+    # occlusion answers, and the stack stays within the bound api.cu checks before enabling the wide walk
+    t_o, p_o, max_sp = tree.trace4_ordered(rays)
+    assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
+    occl, _, _ = tree.trace4_ordered(rays, any_hit=True)
+    assert np.array_equal(occl > 0, p_ref != 0xFFFFFFFF)
+    assert max_sp <= 3 * (tree.lib.bvh_h_depth4(tree.h) + 1) + 1 <= 127
     tree.trace(rays, brute=False)
     steps2 = tree.last_steps
     assert steps4 <= steps2

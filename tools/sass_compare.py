@@ -20,7 +20,14 @@ def funcs(path):
     if cur: out[cur]=hashlib.md5(''.join(buf).encode()).hexdigest()
     return out
 base=funcs(sys.argv[1]); new=funcs(sys.argv[2])
-def norm(k): return k.replace('ELi0EEEvNS_8DevSceneENS_9RenderCfgENS_7PathBufEP6float4PKjNS_6Queues','EEEvNS_8DevSceneENS_9RenderCfgENS_7PathBufEP6float4PKjNS_6Queues') if 'k_trace_dyn' in k else k
+def norm(k):
+    """Template parameters added later with a default value (k_trace_dyn<FIRST, SMEM_ALL[, PHASE = 0[, WIDE = false]]>)
+    change the mangled name of the unchanged instantiation; fold them away."""
+    if 'k_trace_dyn' in k:
+        for tail in ('ELi0ELb0EEEv', 'ELi0EEEv'):
+            k = k.replace(tail, 'EEEv', 1) if tail in k else k
+    return k
+base={norm(k):v for k,v in base.items()}
 newn={norm(k):v for k,v in new.items()}
 bad=0
 for k in base:
