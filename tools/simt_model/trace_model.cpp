@@ -40,7 +40,8 @@ struct Costs {
     int bucket_empty = 6, bucket_hit = 35;       // per queue of the bucket pass
     int n_queues = 5;
     // wide-node variants: cost of one node iteration with W children
-    int node_wide(int w) const { return 40 + 28 * w; }   // loads + W slab tests + ordered push
+    int wide_override = 0;
+    int node_wide(int w) const { return wide_override ? wide_override : 40 + 28 * w; }   // loads + W slab tests + ordered push
     int node_coop = 62;   // cooperative node step: own child box (2 loads, 1 slab test), rank by shuffles, ordered push
     int leaf_coop = 92;   // cooperative leaf: one triangle per lane + shuffle reduction of (t, prim), incl. leaf overhead
 };
@@ -470,7 +471,7 @@ int main(int argc, char **argv) {
         if (a == "--res") opt.res = val(); else if (a == "--spp") opt.spp = val(); else if (a == "--idle") opt.idle = val();
         else if (a == "--static") opt.dynamic = false; else if (a == "--wide") opt.wide = val(); else if (a == "--warps") opt.warps = val();
         else if (a == "--tri-reject") opt.tri_reject = val(); else if (a == "--split") opt.split_phases = true; else if (a == "--split2") opt.split_inplace = true; else if (a == "--leaf-once") opt.leaf_once = true; else if (a == "--window") opt.window = val(); else if (a == "--coop") { opt.coop = val(); opt.wide = opt.coop; TH = opt.coop; WS = 32 / TH; }
-        else if (a == "--node-coop") cost.node_coop = val();
+        else if (a == "--node-coop") cost.node_coop = val(); else if (a == "--wide-cost") cost.wide_override = val();
         else if (a == "--sort") opt.sort_bits = val(); else if (a == "--node-cost") cost.node = val(); else if (a == "--tri-cost") cost.tri = val();
         else if (a == "--retire-scale") { int p = val(); cost.ret_restart = cost.ret_restart * p / 100; cost.ret_hit = cost.ret_hit * p / 100; cost.refill_start = cost.refill_start * p / 100; }
         else if (a == "-v") opt.verbose = true;
