@@ -125,9 +125,9 @@ PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
 // 4-wide nodes (bvh.h: Bvh4Node, 8 x float4) of the experimental wide walk; the shared-memory window is
 // counted in 64-byte units like the binary nodes (a wide node = two units)
 template <bool SMEM_ALL>
-PT_DEV float4 ld_node4(const TraceCtx &c, uint32_t node, int k) {
-    if (SMEM_ALL) return c.s_nodes[8 * node + k];
-    return 2 * node + 1 < c.n_smem_nodes ? c.s_nodes[8 * node + k] : __ldg(&c.g_nodes[8 * (size_t) node + k]);
+PT_DEV float4 ld_node4(const TraceCtx &c, uint32_t node, int byte_off) {     // byte offset of the row inside the 128-byte node
+    if (SMEM_ALL || 2 * node + 1 < c.n_smem_nodes) return *(const float4 *) ((const char *) (c.s_nodes + 8 * node) + byte_off);
+    return __ldg((const float4 *) ((const char *) (c.g_nodes + 8 * (size_t) node) + byte_off));
 }
 
 PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
@@ -139,6 +139,20 @@ PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float
     float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
     float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
     float tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+    tnear = tmin;
+    return tmin <= tmx * 1.0000004f;
+}
+
+// slab test with the near / far plane of every axis already chosen by the sign of the ray direction
+// (wide walk: the planes are separate float4 rows, so the choice is an address, not a min/max per axis).
+// For lo <= hi and the finite non-zero `inv` of safe_inv this yields bit for bit the values of box_hit:
+// rounded subtraction and multiplication are monotonic, so min((lo-o)*inv, (hi-o)*inv) IS the near product.
+PT_DEV bool box_hit_nf(float nx, float ny, float nz, float fx, float fy, float fz, float3 o, float3 inv, float tmax, float &tnear) {
+    float t0x = (nx - o.x) * inv.x, t1x = (fx - o.x) * inv.x;
+    float t0y = (ny - o.y) * inv.y, t1y = (fy - o.y) * inv.y;
+    float t0z = (nz - o.z) * inv.z, t1z = (fz - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.f));
+    float tmx = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
     tnear = tmin;
     return tmin <= tmx * 1.0000004f;
 }
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 //
 // WIDE (experimental, off by default: B200PT_BVH_WIDE=1, section 3.3 of the same note): the inner-node loop
 // walks the 4-wide tree of pt::collapse_bvh4 -- `sc.nodes` then points to the Bvh4Node array, four slab tests
-// per step, children ordered near to far by a 5-exchange sorting network, up to three pushes. Leaves, the
+// per step, the nearest child first, up to three pushes. Leaves, the
 // triangle test and the tie-break are the binary walk's, so the hits are the same.
 // ---------------------------------------------------------------------------
 
@@ -431,21 +445,29 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 bool searching = true;
                 while (node >= 0 && node != TRAV_SENTINEL) {
                     if (WIDE) {
-                        float4 lox = ld_node4<SMEM_ALL>(c, node, 0), loy = ld_node4<SMEM_ALL>(c, node, 1), loz = ld_node4<SMEM_ALL>(c, node, 2);
-                        float4 hix = ld_node4<SMEM_ALL>(c, node, 3), hiy = ld_node4<SMEM_ALL>(c, node, 4), hiz = ld_node4<SMEM_ALL>(c, node, 5);
-                        float4 chf = ld_node4<SMEM_ALL>(c, node, 6);
+                        // rows 0..2 = lo.xyz, 3..5 = hi.xyz of the four children: the near plane of an axis is the lo row
+                        // for a positive direction component, the hi row for a negative one
+                        // (byte offsets: lo rows at 0 / 16 / 32, hi rows 48 further; x ^ 48 flips between the two)
+                        const int kx = inv.x < 0.f ? 48 : 0, ky = inv.y < 0.f ? 48 : 0, kz = inv.z < 0.f ? 48 : 0;
+                        float4 nx = ld_node4<SMEM_ALL>(c, node, kx), ny = ld_node4<SMEM_ALL>(c, node, 16 + ky), nz = ld_node4<SMEM_ALL>(c, node, 32 + kz);
+                        float4 fx = ld_node4<SMEM_ALL>(c, node, kx ^ 48), fy = ld_node4<SMEM_ALL>(c, node, 16 + (ky ^ 48)), fz = ld_node4<SMEM_ALL>(c, node, 32 + (kz ^ 48));
+                        float4 chf = ld_node4<SMEM_ALL>(c, node, 96);
                         int32_t c0 = __float_as_int(chf.x), c1 = __float_as_int(chf.y), c2 = __float_as_int(chf.z), c3 = __float_as_int(chf.w);
                         float t0, t1, t2, t3;
-                        bool h0 = box_hit(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, o, inv, maxt, t0) & (c0 != 0x7fffffff);
-                        bool h1 = box_hit(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, o, inv, maxt, t1) & (c1 != 0x7fffffff);
-                        bool h2 = box_hit(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, o, inv, maxt, t2) & (c2 != 0x7fffffff);
-                        bool h3 = box_hit(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, o, inv, maxt, t3) & (c3 != 0x7fffffff);
+                        // an empty child carries the inverted box (+inf, -inf): with the planes picked by sign its near
+                        // product is +inf and its far product -inf for every finite non-zero `inv`, so it always misses
+                        bool h0 = box_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, o, inv, maxt, t0);
+                        bool h1 = box_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, o, inv, maxt, t1);
+                        bool h2 = box_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, o, inv, maxt, t2);
+                        bool h3 = box_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, o, inv, maxt, t3);
                         // children that are missed sort last
                         t0 = h0 ? t0 : PT_INF; t1 = h1 ? t1 : PT_INF; t2 = h2 ? t2 : PT_INF; t3 = h3 ? t3 : PT_INF;
 #define PT_CSWAP(ta, ca, tb, cb) { bool sw = tb < ta; float tlo = sw ? tb : ta, thi = sw ? ta : tb; int32_t clo = sw ? cb : ca, chi = sw ? ca : cb; ta = tlo; tb = thi; ca = clo; cb = chi; }
-                        PT_CSWAP(t0, c0, t1, c1) PT_CSWAP(t2, c2, t3, c3) PT_CSWAP(t0, c0, t2, c2) PT_CSWAP(t1, c1, t3, c3) PT_CSWAP(t1, c1, t2, c2)
+                        // nearest child to the front; the others keep their order (a full sort costs 16 more instructions
+                        // per step and saves only ~1 % of the node visits: tests/test_bvh_host.py, bvh_h_trace4_ordered)
+                        PT_CSWAP(t0, c0, t1, c1) PT_CSWAP(t0, c0, t2, c2) PT_CSWAP(t0, c0, t3, c3)
 #undef PT_CSWAP
-                        // the far children go onto the stack farthest first, the walk continues in the nearest
+                        // the other children that were hit go onto the stack, the walk continues in the nearest
                         if (t3 < PT_INF) stack[++sp] = c3;
                         if (t2 < PT_INF) stack[++sp] = c2;
                         if (t1 < PT_INF) stack[++sp] = c1;

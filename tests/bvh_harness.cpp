@@ -256,7 +256,9 @@ static bool slab_near(const float *lo, const float *hi, const float *o, const fl
     return tmin <= tmx * 1.0000004f;
 }
 
-void bvh_h_trace4_ordered(void *p, uint32_t n_rays, const float *rays, int any_hit, float *t_out, uint32_t *prim_out, uint32_t *max_sp_out) {
+void bvh_h_trace4_ordered(void *p, uint32_t n_rays, const float *rays, int mode, float *t_out, uint32_t *prim_out, uint32_t *max_sp_out, uint64_t *n_steps) {
+    const int any_hit = mode & 1; const bool nearest_only = (mode & 2) != 0;   // nearest_only: descend into the nearest child, push the others unsorted
+    uint64_t steps = 0;
     Handle *h = (Handle *) p; const pt::Bvh &b = h->bvh; const pt::Bvh4 &w = h->wide;
     const int32_t SENT = 0x76543210;
     int max_sp = 0;
@@ -278,18 +280,39 @@ void bvh_h_trace4_ordered(void *p, uint32_t n_rays, const float *rays, int any_h
                 node = stack[sp--];
                 continue;
             }
-            const pt::Bvh4Node &nd = w.nodes[node];
+            const pt::Bvh4Node &nd = w.nodes[node]; steps++;
             float t[4]; int32_t c[4];
             for (int k = 0; k < 4; ++k) {
                 float lo[3] = { nd.lo[0][k], nd.lo[1][k], nd.lo[2][k] }, hi[3] = { nd.hi[0][k], nd.hi[1][k], nd.hi[2][k] };
                 c[k] = nd.child[k];
                 bool hit = slab_near(lo, hi, o, inv, maxt, t[k]) & (c[k] != pt::BVH_EMPTY);
+                if (c[k] == pt::BVH_EMPTY) {
+                    // the kernel does not look at the child id: the inverted box of an empty child must miss by itself
+                    float nr[3], fr[3];
+                    for (int a = 0; a < 3; ++a) { bool neg = inv[a] < 0.f; nr[a] = neg ? hi[a] : lo[a]; fr[a] = neg ? lo[a] : hi[a]; }
+                    float tn = std::fmax(std::fmax((nr[0] - o[0]) * inv[0], (nr[1] - o[1]) * inv[1]), std::fmax((nr[2] - o[2]) * inv[2], 0.f));
+                    float tf = std::fmin(std::fmin((fr[0] - o[0]) * inv[0], (fr[1] - o[1]) * inv[1]), std::fmin((fr[2] - o[2]) * inv[2], maxt));
+                    if (tn <= tf * 1.0000004f) { t_out[r] = -3.f; prim_out[r] = 0xfffffffcu; goto next_ray; }
+                }
+                if (c[k] != pt::BVH_EMPTY) {
+                    // the kernel picks the near / far plane by the sign of the direction instead of min/max per axis
+                    // (box_hit_nf): must be the same numbers
+                    float nr[3], fr[3];
+                    for (int a = 0; a < 3; ++a) { bool neg = inv[a] < 0.f; nr[a] = neg ? hi[a] : lo[a]; fr[a] = neg ? lo[a] : hi[a]; }
+                    float tn = std::fmax(std::fmax((nr[0] - o[0]) * inv[0], (nr[1] - o[1]) * inv[1]), std::fmax((nr[2] - o[2]) * inv[2], 0.f));
+                    float tf = std::fmin(std::fmin((fr[0] - o[0]) * inv[0], (fr[1] - o[1]) * inv[1]), std::fmin((fr[2] - o[2]) * inv[2], maxt));
+                    bool hit_nf = tn <= tf * 1.0000004f;
+                    if (hit_nf != hit || (hit && tn != t[k])) { t_out[r] = -2.f; prim_out[r] = 0xfffffffdu; goto next_ray; }
+                }
                 t[k] = hit ? t[k] : INFINITY;
             }
 #define CSWAP(i, j) { bool sw = t[j] < t[i]; float tlo = sw ? t[j] : t[i], thi = sw ? t[i] : t[j]; int32_t clo = sw ? c[j] : c[i], chi = sw ? c[i] : c[j]; t[i] = tlo; t[j] = thi; c[i] = clo; c[j] = chi; }
-            CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+            if (nearest_only) { CSWAP(0, 1) CSWAP(0, 2) CSWAP(0, 3) }      // minimum to the front, the rest as they come
+            else {
+                CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+                if (!(t[0] <= t[1] && t[1] <= t[2] && t[2] <= t[3])) { t_out[r] = -1.f; prim_out[r] = 0xfffffffeu; goto next_ray; }   // network failed to sort
+            }
 #undef CSWAP
-            if (!(t[0] <= t[1] && t[1] <= t[2] && t[2] <= t[3])) { t_out[r] = -1.f; prim_out[r] = 0xfffffffeu; goto next_ray; }   // network failed to sort
             if (t[3] < INFINITY) stack[++sp] = c[3];
             if (t[2] < INFINITY) stack[++sp] = c[2];
             if (t[1] < INFINITY) stack[++sp] = c[1];
@@ -300,6 +323,7 @@ void bvh_h_trace4_ordered(void *p, uint32_t n_rays, const float *rays, int any_h
     next_ray:;
     }
     if (max_sp_out) *max_sp_out = (uint32_t) max_sp;
+    if (n_steps) *n_steps = steps;
 }
 
 } // extern "C"

@@ -20,8 +20,7 @@ CSRC = os.path.join(ROOT, "mitsuba3_b200", "csrc")
 MAX_LEAF = 2          # bvh.h: BVH_MAX_LEAF
 
 
-@pytest.fixture(scope="module")
-def harness():
+def load_harness():
     out_dir = os.path.join(HERE, "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libbvh_harness.so")
@@ -50,9 +49,14 @@ def harness():
     lib.bvh_h_nodes4.argtypes = [ctypes.c_void_p]
     lib.bvh_h_validate4.restype = ctypes.c_int
     lib.bvh_h_validate4.argtypes = [ctypes.c_void_p]
-    lib.bvh_h_trace4_ordered.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.bvh_h_trace4_ordered.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.bvh_h_trace4.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def harness():
+    return load_harness()
 
 
 class Tree:
@@ -100,13 +104,16 @@ class Tree:
     def validate4(self):
         return self.lib.bvh_h_validate4(self.h)
 
-    def trace4_ordered(self, rays, any_hit=False):
+    def trace4_ordered(self, rays, any_hit=False, nearest_only=False):
         """The wide walk with the traversal kernel's node step (near-to-far network, push order, fixed stack)."""
         rays = np.ascontiguousarray(rays, np.float32)
         t = np.empty(len(rays), np.float32)
         prim = np.empty(len(rays), np.uint32)
         max_sp = ctypes.c_uint32(0)
-        self.lib.bvh_h_trace4_ordered(self.h, len(rays), rays.ctypes.data, int(any_hit), t.ctypes.data, prim.ctypes.data, ctypes.byref(max_sp))
+        steps = ctypes.c_uint64(0)
+        self.lib.bvh_h_trace4_ordered(self.h, len(rays), rays.ctypes.data, int(any_hit) | (2 if nearest_only else 0), t.ctypes.data, prim.ctypes.data,
+                                      ctypes.byref(max_sp), ctypes.byref(steps))
+        self.last_steps4 = steps.value
         return t, prim, max_sp.value
 
     def trace4(self, rays):
@@ -191,7 +198,11 @@ def test_invariants_and_walk_equals_brute_force(harness, name):
     # occlusion answers, and the stack stays within the bound api.cu checks before enabling the wide walk
     t_o, p_o, max_sp = tree.trace4_ordered(rays)
     assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
-    occl, _, _ = tree.trace4_ordered(rays, any_hit=True)
+    full_sort_steps = tree.last_steps4
+    t_o, p_o, max_sp = tree.trace4_ordered(rays, nearest_only=True)      # what the kernel does
+    assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
+    assert tree.last_steps4 <= 1.10 * full_sort_steps                    # nearest-first costs a few % of visits (worst: overlapping soup)
+    occl, _, _ = tree.trace4_ordered(rays, any_hit=True, nearest_only=True)
     assert np.array_equal(occl > 0, p_ref != 0xFFFFFFFF)
     assert max_sp <= 3 * (tree.lib.bvh_h_depth4(tree.h) + 1) + 1 <= 127
     tree.trace(rays, brute=False)
@@ -273,3 +284,20 @@ def test_boxes_are_conservative_for_grazing_hits(harness):
     assert np.array_equal(p_tree, p_ref) and np.array_equal(t_tree, t_ref)
     t_w, p_w, _, _ = tree.trace4(rays)
     assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
+    # axis-parallel rays (direction components exactly +0 / -0: the reciprocal is the signed 1e30 of safe_inv),
+    # through the kernel's node step incl. its sign-selected slab test
+    n = 1500
+    o = rng.uniform(-1.2, 1.2, (n, 3))
+    axis = rng.integers(0, 3, n)
+    sign = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    d = np.zeros((n, 3))
+    d[np.arange(n), axis] = sign
+    d[rng.random((n, 3)) < 0.3] *= -1.0          # sprinkle negative zeros
+    o[np.arange(n), axis] = -2.0 * sign
+    o[axis == 1, 1] = 2.0 * sign[axis == 1]
+    d[axis == 1, 1] = -sign[axis == 1]
+    rays = np.concatenate([o, d, np.full((n, 1), np.inf)], 1).astype(np.float32)
+    t_ref, p_ref, _ = tree.trace(rays, brute=True)
+    t_o, p_o, _ = tree.trace4_ordered(rays, nearest_only=True)
+    assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
+    assert (p_ref != 0xFFFFFFFF).sum() > 200
