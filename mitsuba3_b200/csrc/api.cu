@@ -45,6 +45,7 @@ struct Wavefront {
     uint32_t *counts = nullptr; size_t n_counts = 0;
     // experimental cell ordering of the material queues (B200PT_CELL_ORDER=1), see kernels.cu: k_cell_keys
     uint2 *cell_keyrank = nullptr; uint32_t *cell_hist = nullptr, *cell_offsets = nullptr, *cell_sorted = nullptr;
+    uint32_t *wave_order = nullptr;     // experimental ordered traversal (B200PT_WAVE_ORDER=1): [0] = count, [4 ..] = slots
     std::vector<void *> allocs;
 };
 
@@ -57,7 +58,7 @@ struct b200pt_scene {
     size_t grad_floats = 0;
     uint32_t n_sm = 148;
     Launch launch;
-    bool cell_order = false; CellGrid cell_grid;     // experimental, off by default
+    bool cell_order = false, order_waves = false; CellGrid cell_grid;     // experimental, off by default
     Wavefront wf;
     // shard pixel list cache
     uint32_t *pix_ids = nullptr; uint32_t n_pix_ids = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
@@ -289,7 +290,8 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         vo += sh.n_vertices; po += sh.n_faces;
     }
     if (const char *e = getenv("B200PT_CELL_ORDER")) s->cell_order = atoi(e) != 0;
-    if (s->cell_order) {      // grid of the experimental cell ordering: the bounding box of the vertices
+    if (const char *e = getenv("B200PT_WAVE_ORDER")) s->order_waves = atoi(e) != 0;
+    if (s->cell_order || s->order_waves) {      // grid of the experimental orderings: the bounding box of the vertices
         float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
         for (size_t v = 0; v < n_verts; ++v)
             for (int k = 0; k < 3; ++k) { float x = verts[v * 8 + k]; lo[k] = std::fmin(lo[k], x); hi[k] = std::fmax(hi[k], x); }
@@ -355,6 +357,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
     { const char *e = getenv("B200PT_TRACE_PHASES"); s->launch.split_phases = e ? atoi(e) != 0 : false; }   // experimental, see k_trace_dyn
+    s->launch.ordered = false;
     s->launch.wide = false; s->launch.nodes4 = nullptr; s->launch.n_nodes4_units = 0; s->launch.n_smem_nodes_w = 0; s->launch.smem_trace_w = 0;
     if (const char *e = getenv("B200PT_BVH_WIDE")) if (atoi(e) != 0) {      // experimental 4-wide walk, see k_trace_dyn
         Bvh4 wide = collapse_bvh4(bvh);
@@ -435,11 +438,13 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
     if (s->dev.env_type >= 0) CU_TRY(A(slack * 4, (void **) &w.q.slots[Q_ENV])); else w.q.slots[Q_ENV] = nullptr;
     w.n_counts = (size_t) (MAX_BOUNCE_SLOTS + 2) * 8;
     CU_TRY(A(w.n_counts * 4, (void **) &w.counts));
-    w.cell_keyrank = nullptr; w.cell_hist = w.cell_offsets = w.cell_sorted = nullptr;
-    if (s->cell_order) {
-        CU_TRY(A(slack * 8, (void **) &w.cell_keyrank)); CU_TRY(A(slack * 4, (void **) &w.cell_sorted));
+    w.cell_keyrank = nullptr; w.cell_hist = w.cell_offsets = w.cell_sorted = w.wave_order = nullptr;
+    if (s->cell_order || s->order_waves) {
+        CU_TRY(A(slack * 8, (void **) &w.cell_keyrank));
         CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_hist)); CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_offsets));
     }
+    if (s->cell_order) CU_TRY(A(slack * 4, (void **) &w.cell_sorted));
+    if (s->order_waves) CU_TRY(A((slack + 4) * 4, (void **) &w.wave_order));
     w.q.counts = w.counts;
     w.cap = cap;
     return B200PT_OK;
@@ -491,7 +496,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     uint32_t lanes = cfg.chunk_lanes;
     cfg.adjoint = mode >= 1; cfg.forward = mode == 2;
     CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
-    if (s->cell_order) CU_TRY(cudaMemsetAsync(w.cell_hist, 0, CELL_BINS * 4, st));
+    if (s->cell_order || s->order_waves) CU_TRY(cudaMemsetAsync(w.cell_hist, 0, CELL_BINS * 4, st));
     int g_all = grid_for(s, lanes);
     launch_generate(d, cfg, s->pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
     s->stats.kernel_launches++;
@@ -501,6 +506,13 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     auto trace = [&](int bufi, const uint32_t *n_in, uint32_t *qcounts, bool first) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (s->profile) { e0 = next_trace_event(s); e1 = next_trace_event(s); cudaEventRecord(e0, st); }
+        if (!first && s->order_waves && L.dynamic_fetch) {
+            // experimental: walk the wave in (origin cell, direction octant) order
+            launch_wave_order(w.buf[bufi], n_in, s->cell_grid, w.cell_keyrank, w.cell_hist, w.cell_offsets, w.wave_order, g_all, st);
+            Launch Lo = L; Lo.ordered = true;
+            launch_trace(d, cfg, w.buf[bufi], w.hit, w.wave_order, w.q, qcounts, w.lane_result, s->stats_dev, first, Lo, st);
+            s->stats.kernel_launches += 3;
+        } else
         launch_trace(d, cfg, w.buf[bufi], w.hit, n_in, w.q, qcounts, w.lane_result, s->stats_dev, first, L, st);
         if (s->profile) cudaEventRecord(e1, st);
         s->stats.kernel_launches++; s->stats.trace_launches++;

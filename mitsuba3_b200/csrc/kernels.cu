@@ -356,12 +356,17 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 // walks the 4-wide tree of pt::collapse_bvh4 -- `sc.nodes` then points to the Bvh4Node array, four slab tests
 // per step, the nearest child first, up to three pushes. Leaves, the
 // triangle test and the tie-break are the binary walk's, so the hits are the same.
+//
+// ORDERED (experimental, off by default: B200PT_WAVE_ORDER=1, section 3.1): job i is slot order[i] instead of
+// slot i, `order` being the wave's slots sorted by (4x4x4 cell of the ray origin, direction octant) by the
+// k_wave_keys / k_cell_scan / k_cell_scatter pass. `n_in` then points to that list's header: n_in[0] = number
+// of slots, entries from n_in[4] on (no extra kernel parameter: the shipped instantiations keep their layout).
 // ---------------------------------------------------------------------------
 
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 5
 #endif
-template <bool FIRST, bool SMEM_ALL, int PHASE = 0, bool WIDE = false>
+template <bool FIRST, bool SMEM_ALL, int PHASE = 0, bool WIDE = false, bool ORDERED = false>
 __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
@@ -408,26 +413,27 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
             if (kind == 0) {
                 uint32_t i = base + __popc(idle_mask & ((1u << lane_id) - 1u));
                 if (i < n) {
-                    slot = i;
-                    flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w);
+                    const uint32_t si = ORDERED ? __ldg(&n_in[4 + i]) : i;      // the slot of job i
+                    slot = si;
+                    flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[si].w);
                     if (PHASE == 1) {          // shadow rays only; a slot without one is an empty job
                         if (flags & PF_HAS_SHADOW) {
-                            float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                            float4 so = cur.sh_o[si], sd = cur.sh_d[si];
                             kind = 1; n_shadow++;
                             start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
                         }
                     } else if (PHASE == 2) {   // path rays only
                         if (flags & PF_ALIVE) {
-                            float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                            float4 ro = cur.ray_o[si], rd = cur.ray_d[si];
                             kind = 2; n_closest++;
                             start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
                         }
                     } else if (!FIRST && (flags & PF_HAS_SHADOW)) {
-                        float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                        float4 so = cur.sh_o[si], sd = cur.sh_d[si];
                         kind = 1; n_shadow++;
                         start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
                     } else {       // every queued slot is alive or has a shadow ray
-                        float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                        float4 ro = cur.ray_o[si], rd = cur.ray_d[si];
                         kind = 2; n_closest++;
                         start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
                     }
@@ -1148,13 +1154,41 @@ __global__ void __launch_bounds__(CELL_BINS) k_cell_scan(uint32_t *__restrict__ 
     offsets[t] = sh[t] - v;           // exclusive
 }
 
+// queue == nullptr: the entries are the slots 0 .. n-1 themselves (ordering of a whole wave);
+// header != nullptr: header[0] receives n (the ordered traversal kernel reads count and list from one pointer)
 __global__ void __launch_bounds__(BLOCK) k_cell_scatter(const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, const uint2 *__restrict__ keyrank,
-                                                        const uint32_t *__restrict__ offsets, uint32_t *__restrict__ sorted) {
+                                                        const uint32_t *__restrict__ offsets, uint32_t *__restrict__ sorted, uint32_t *__restrict__ header) {
     const uint32_t n = *qcount;
     const uint32_t stride = gridDim.x * blockDim.x;
+    if (header && blockIdx.x == 0 && threadIdx.x == 0) header[0] = n;
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += stride) {
         uint2 kr = keyrank[qi];
-        sorted[offsets[kr.x] + kr.y] = queue[qi];
+        sorted[offsets[kr.x] + kr.y] = queue ? queue[qi] : qi;
+    }
+}
+
+// Key of a wave's slot for the ordered traversal (B200PT_WAVE_ORDER=1): 4 x 4 x 4 cell of the ray origin and the
+// octant of the ray direction, 512 bins like the hit-point cells above.
+__global__ void __launch_bounds__(BLOCK) k_wave_keys(PathBuf cur, const uint32_t *__restrict__ n_in, CellGrid g, uint2 *__restrict__ keyrank, uint32_t *__restrict__ hist) {
+    const uint32_t n = *n_in;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
+        uint32_t i = base + lane_id;
+        bool valid = i < n;
+        uint32_t key = 0xffffffffu;
+        if (valid) {
+            float4 o = cur.ray_o[i], d = cur.ray_d[i];
+            int cx = (int) ((o.x - g.lo.x) * (0.5f * g.scale.x)), cy = (int) ((o.y - g.lo.y) * (0.5f * g.scale.y)), cz = (int) ((o.z - g.lo.z) * (0.5f * g.scale.z));
+            cx = min(CELL_AXIS / 2 - 1, max(0, cx)); cy = min(CELL_AXIS / 2 - 1, max(0, cy)); cz = min(CELL_AXIS / 2 - 1, max(0, cz));
+            uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+            key = (uint32_t) (((cz * (CELL_AXIS / 2) + cy) * (CELL_AXIS / 2) + cx) * 8) + oct;
+        }
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t leader = __ffs(peers) - 1, first = 0;
+        if (valid && lane_id == leader) first = atomicAdd(&hist[key], (uint32_t) __popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) keyrank[i] = make_uint2(key, first + __popc(peers & ((1u << lane_id) - 1u)));
     }
 }
 
@@ -1165,7 +1199,15 @@ void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, co
                        uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st) {
     k_cell_keys<<<grid, BLOCK, 0, st>>>(cur, hit, queue, qcount, g, keyrank, hist);
     k_cell_scan<<<1, CELL_BINS, 0, st>>>(hist, offsets);
-    k_cell_scatter<<<grid, BLOCK, 0, st>>>(queue, qcount, keyrank, offsets, sorted);
+    k_cell_scatter<<<grid, BLOCK, 0, st>>>(queue, qcount, keyrank, offsets, sorted, nullptr);
+}
+
+// order_buf[0] = number of slots of the wave, order_buf[4 ..] = the slots sorted by (origin cell, direction octant)
+void launch_wave_order(PathBuf cur, const uint32_t *n_in, const CellGrid &g, uint2 *keyrank, uint32_t *hist, uint32_t *offsets, uint32_t *order_buf,
+                       int grid, cudaStream_t st) {
+    k_wave_keys<<<grid, BLOCK, 0, st>>>(cur, n_in, g, keyrank, hist);
+    k_cell_scan<<<1, CELL_BINS, 0, st>>>(hist, offsets);
+    k_cell_scatter<<<grid, BLOCK, 0, st>>>(nullptr, n_in, keyrank, offsets, order_buf + 4, order_buf);
 }
 
 void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, PathBuf buf, const float4 *adj_dL_lane,
@@ -1176,18 +1218,22 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
-    if (L.dynamic_fetch && L.wide) {
-        // experimental 4-wide walk: the kernel's scene copy points to the Bvh4Node array (counted in 64-byte units)
-        DevScene scw = sc; scw.nodes = L.nodes4; scw.n_nodes = L.n_nodes4_units;
-        const bool allw = L.n_smem_nodes_w == scw.n_nodes && L.n_smem_tris == sc.n_tris;
-#define LAUNCH_WIDE(F, A, P, CTR) k_trace_dyn<F, A, P, true><<<L.grid, BLOCK, L.smem_trace_w + L.smem_tables, st>>>(scw, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, L.n_smem_nodes_w, L.n_smem_tris, L.refill_idle)
-        if (first) { if (allw) LAUNCH_WIDE(true, true, 0, 5); else LAUNCH_WIDE(true, false, 0, 5); }
-        else if (L.split_phases) {
-            if (allw) { LAUNCH_WIDE(false, true, 1, 5); LAUNCH_WIDE(false, true, 2, 7); }
-            else { LAUNCH_WIDE(false, false, 1, 5); LAUNCH_WIDE(false, false, 2, 7); }
-        }
-        else { if (allw) LAUNCH_WIDE(false, true, 0, 5); else LAUNCH_WIDE(false, false, 0, 5); }
-#undef LAUNCH_WIDE
+    if (L.dynamic_fetch && (L.wide || (L.ordered && !first))) {
+        // experimental variants. Wide walk: the kernel's scene copy points to the Bvh4Node array (counted in 64-byte
+        // units). Ordered: n_in is the header of the wave's order list (launch_wave_order).
+        DevScene scw = sc; uint32_t nsm = L.n_smem_nodes; size_t smem = L.smem_trace;
+        if (L.wide) { scw.nodes = L.nodes4; scw.n_nodes = L.n_nodes4_units; nsm = L.n_smem_nodes_w; smem = L.smem_trace_w; }
+        const bool allw = nsm == scw.n_nodes && L.n_smem_tris == sc.n_tris;
+#define LAUNCH_X(F, A, P, W, O, CTR) k_trace_dyn<F, A, P, W, O><<<L.grid, BLOCK, smem + L.smem_tables, st>>>(scw, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, nsm, L.n_smem_tris, L.refill_idle)
+#define LAUNCH_XA(F, P, W, O, CTR) { if (allw) LAUNCH_X(F, true, P, W, O, CTR); else LAUNCH_X(F, false, P, W, O, CTR); }
+#define LAUNCH_XP(W, O) { if (L.split_phases) { LAUNCH_XA(false, 1, W, O, 5) LAUNCH_XA(false, 2, W, O, 7) } else LAUNCH_XA(false, 0, W, O, 5) }
+        if (first) LAUNCH_XA(true, 0, true, false, 5)          // only reached with L.wide
+        else if (L.wide && L.ordered) LAUNCH_XP(true, true)
+        else if (L.wide) LAUNCH_XP(true, false)
+        else LAUNCH_XP(false, true)
+#undef LAUNCH_XP
+#undef LAUNCH_XA
+#undef LAUNCH_X
         return;
     }
     if (L.dynamic_fetch) {
@@ -1301,6 +1347,10 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+#define PT_ATTR_ORD(A, P, W) cudaFuncSetAttribute(k_trace_dyn<false, A, P, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    PT_ATTR_ORD(true, 0, false) PT_ATTR_ORD(false, 0, false) PT_ATTR_ORD(true, 1, false) PT_ATTR_ORD(false, 1, false) PT_ATTR_ORD(true, 2, false) PT_ATTR_ORD(false, 2, false)
+    PT_ATTR_ORD(true, 0, true) PT_ATTR_ORD(false, 0, true) PT_ATTR_ORD(true, 1, true) PT_ATTR_ORD(false, 1, true) PT_ATTR_ORD(true, 2, true) PT_ATTR_ORD(false, 2, true)
+#undef PT_ATTR_ORD
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

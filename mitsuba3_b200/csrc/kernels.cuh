@@ -59,6 +59,7 @@ struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes,
                 bool split_phases;   // experimental (B200PT_TRACE_PHASES=1): shadow rays and path rays of a wave as two launches
                 // experimental (B200PT_BVH_WIDE=1): 4-wide walk over the Bvh4Node array, sizes in 64-byte units
                 bool wide; const float4 *nodes4; uint32_t n_nodes4_units, n_smem_nodes_w; size_t smem_trace_w;
+                bool ordered;        // experimental (B200PT_WAVE_ORDER=1): the traversal walks the wave's order list (n_in = its header)
 };
 
 // experimental cell ordering of the material queues (kernels.cu: k_cell_keys), off by default
@@ -78,6 +79,8 @@ void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, con
                       float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st);
 void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount, const CellGrid &g, uint2 *keyrank,
                        uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st);
+void launch_wave_order(PathBuf cur, const uint32_t *n_in, const CellGrid &g, uint2 *keyrank, uint32_t *hist, uint32_t *offsets, uint32_t *order_buf,
+                       int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,

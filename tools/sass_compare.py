@@ -21,10 +21,10 @@ def funcs(path):
     return out
 base=funcs(sys.argv[1]); new=funcs(sys.argv[2])
 def norm(k):
-    """Template parameters added later with a default value (k_trace_dyn<FIRST, SMEM_ALL[, PHASE = 0[, WIDE = false]]>)
+    """Template parameters added later with a default value (k_trace_dyn<FIRST, SMEM_ALL[, PHASE = 0[, WIDE = false[, ORDERED = false]]]>)
     change the mangled name of the unchanged instantiation; fold them away."""
     if 'k_trace_dyn' in k:
-        for tail in ('ELi0ELb0EEEv', 'ELi0EEEv'):
+        for tail in ('ELi0ELb0ELb0EEEv', 'ELi0ELb0EEEv', 'ELi0EEEv'):
             k = k.replace(tail, 'EEEv', 1) if tail in k else k
     return k
 base={norm(k):v for k,v in base.items()}
