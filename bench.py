@@ -346,7 +346,7 @@ def main():
                          "share_of_step": trace_ms / max(dev_ms, 1e-9),
                          "step": {"bytes_per_sample": 144.0 + 304.0 * b_bar, "achieved": step_gbs, "frac": step_gbs / hbm_peak}},
         }
-        switches = sorted(k for k in ("B200PT_WAVE_ORDER", "B200PT_CELL_ORDER", "B200PT_TRACE_PHASES", "B200PT_BVH_WIDE") if os.environ.get(k, "0") not in ("", "0"))
+        switches = sorted(k for k in ("B200PT_WAVE_ORDER", "B200PT_CELL_ORDER", "B200PT_TRACE_PHASES", "B200PT_BVH_WIDE", "B200PT_SPLAT_FOLD") if os.environ.get(k, "0") not in ("", "0"))
         if switches:     # staged traversal variants (off by default): a line measured with one of them says so
             out["config"]["switches"] = switches
         if prb:

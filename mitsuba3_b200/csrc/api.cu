@@ -357,6 +357,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
     { const char *e = getenv("B200PT_TRACE_PHASES"); s->launch.split_phases = e ? atoi(e) != 0 : false; }   // experimental, see k_trace_dyn
+    if (const char *e = getenv("B200PT_SPLAT_FOLD")) set_splat_fold(atoi(e) != 0);      // experimental, see k_splat_gauss
     s->launch.ordered = false;
     s->launch.wide = false; s->launch.nodes4 = nullptr; s->launch.n_nodes4_units = 0; s->launch.n_smem_nodes_w = 0; s->launch.smem_trace_w = 0;
     if (const char *e = getenv("B200PT_BVH_WIDE")) if (atoi(e) != 0) {      // experimental 4-wide walk, see k_trace_dyn

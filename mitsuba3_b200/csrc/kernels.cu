@@ -957,7 +957,14 @@ PT_DEV void sample_film_pos(const DevScene &sc, const RenderCfg &cfg, uint32_t p
 // (floor(pos) +- 2, imageblock.cpp:452-466): the warp reduces the 25 x 4 weighted values
 // with shuffles and issues one fp32 atomicAdd per (tap, channel) instead of 32.
 // WEIGHTS_ONLY accumulates only the weight channel (first pass of the adjoint).
-template <bool WEIGHTS_ONLY>
+//
+// FOLD (experimental, off by default: B200PT_SPLAT_FOLD=1, not yet run on a GPU): SHFL issues at a quarter of the
+// ALU rate, and the 100 butterfly reductions (500 shuffles per warp and pass) are what bounds this kernel
+// (67 M samples / 32 x 500 shuffles / 148 SMs at 1 per clock = 3.6 of its 4.1 ms). A folding reduction sums
+// 32 values per lane with 16 + 8 + 4 + 2 + 1 = 31 shuffles: at offset o the lane keeps the half of its values
+// selected by its bit o and hands the other half to its partner. Lane L ends up with the warp total of value L,
+// added in the same pairwise order as the butterfly, i.e. bit-identical (emulation in profiles/r01_simt_model.md).
+template <bool WEIGHTS_ONLY, bool FOLD = false>
 __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
                                                        const float4 *__restrict__ lane_result, float *__restrict__ film) {
     const uint32_t lane_id = threadIdx.x & 31u;
@@ -988,6 +995,34 @@ __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cf
                 int x = px - 2 + k, y = py - 2 + k;
                 wx[k] = (x >= x0 && x <= x1) ? rfilter_eval(sc, (float) x - pfx) : 0.f;
                 wy[k] = (y >= y0 && y <= y1) ? rfilter_eval(sc, (float) y - pfy) : 0.f;
+            }
+            if (FOLD && !WEIGHTS_ONLY) {
+                // value m = tap * 4 + channel (tap = ky * 5 + kx; channels r, g, b, weight), 100 values in 4 batches of 32
+                const bool b16 = (lane_id & 16u) != 0, b8 = (lane_id & 8u) != 0, b4 = (lane_id & 4u) != 0, b2 = (lane_id & 2u) != 0, b1 = (lane_id & 1u) != 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float a[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = 32 * b + j, tap = m >> 2, ch = m & 3;
+                        if (m < 100) { float w = wx[tap % 5] * wy[tap / 5]; a[j] = ch == 0 ? v.x * w : ch == 1 ? v.y * w : ch == 2 ? v.z * w : w; }
+                        else a[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { float keep = b16 ? a[j + 16] : a[j], send = b16 ? a[j] : a[j + 16]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { float keep = b8 ? a[j + 8] : a[j], send = b8 ? a[j] : a[j + 8]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { float keep = b4 ? a[j + 4] : a[j], send = b4 ? a[j] : a[j + 4]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { float keep = b2 ? a[j + 2] : a[j], send = b2 ? a[j] : a[j + 2]; a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+                    { float keep = b1 ? a[1] : a[0], send = b1 ? a[0] : a[1]; a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1); }
+                    // this lane now holds the warp total of value 32 b + lane_id; adding a zero total changes nothing
+                    const int m = 32 * b + (int) lane_id, tap = m >> 2;
+                    const int x = px - 2 + tap % 5, y = py - 2 + tap / 5;
+                    if (m < 100 && x >= 0 && y >= 0 && x < W && y < H && a[0] != 0.f) atomicAdd(film + 4 * ((size_t) y * W + x) + (m & 3), a[0]);
+                }
+                continue;
             }
             float mine0 = 0.f, mine1 = 0.f, mine2 = 0.f, mine3 = 0.f;
 #pragma unroll
@@ -1285,8 +1320,12 @@ void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *ou
     k_env_query<<<(int) ((n + 127) / 128), 128, 0, st>>>(sc, n, in, out);
 }
 
+static bool g_splat_fold = false;     // experimental folding reduction of the gaussian splat (B200PT_SPLAT_FOLD=1), process-wide
+void set_splat_fold(bool on) { g_splat_fold = on; }
+
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st) {
     if (sc.rfilter == B200PT_RFILTER_BOX) k_splat_box<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
+    else if (g_splat_fold) k_splat_gauss<false, true><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
     else k_splat_gauss<false><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
 }
 

@@ -90,6 +90,7 @@ void launch_develop(const DevScene &sc, const float *film, float *out, cudaStrea
 void launch_ray_intersect(const DevScene &sc, uint32_t n, const float *rays, float *t, float *uv, uint32_t *prim, int32_t *shape, const Launch &L, cudaStream_t st);
 void launch_ray_test(const DevScene &sc, uint32_t n, const float *rays, uint8_t *hit, const Launch &L, cudaStream_t st);
 void set_trace_smem_attr(size_t bytes);
+void set_splat_fold(bool on);     // experimental (B200PT_SPLAT_FOLD=1): folding reduction in k_splat_gauss
 void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, const float *in, float *out, cudaStream_t st);
 
 } // namespace pt

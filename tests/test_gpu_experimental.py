@@ -1,6 +1,6 @@
 """Opt-in GPU tests of the traversal variants staged behind environment switches (all off by default;
 profiles/r01_simt_model.md section 3): B200PT_WAVE_ORDER, B200PT_CELL_ORDER, B200PT_TRACE_PHASES,
-B200PT_BVH_WIDE.
+B200PT_BVH_WIDE, and of the folding reduction of the gaussian splat (B200PT_SPLAT_FOLD, section 5).
 
 They are skipped unless B200PT_TEST_EXPERIMENTAL=1:
 
@@ -25,7 +25,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B200PT_TEST_EXPERIMENTAL") != "1",
                                  reason="staged traversal variants: set B200PT_TEST_EXPERIMENTAL=1 to run")]
 
-SWITCHES = ["B200PT_WAVE_ORDER", "B200PT_CELL_ORDER", "B200PT_TRACE_PHASES", "B200PT_BVH_WIDE"]
+SWITCHES = ["B200PT_WAVE_ORDER", "B200PT_CELL_ORDER", "B200PT_TRACE_PHASES", "B200PT_BVH_WIDE", "B200PT_SPLAT_FOLD"]
 
 
 def _heightfield(res=48, spp=8):
@@ -45,12 +45,14 @@ SCENES = {
 
 
 def _render(desc, env):
-    """The switches are read when the device scene is created."""
+    """The switches are read when the device scene is created (B200PT_SPLAT_FOLD is process-wide: it is set or
+    cleared explicitly by every call here)."""
     old = {k: os.environ.get(k) for k in SWITCHES}
     try:
         for k in SWITCHES:
             os.environ.pop(k, None)
         os.environ.update(env)
+        os.environ.setdefault("B200PT_SPLAT_FOLD", "0")
         sc = mb.load_dict(desc)
         return mb.render(sc, seed=3), None
     finally:
@@ -97,6 +99,7 @@ def test_prb_gradient_with_switch(built, switch):
             for k in SWITCHES:
                 os.environ.pop(k, None)
             os.environ.update(env)
+            os.environ.setdefault("B200PT_SPLAT_FOLD", "0")
             sc = mb.load_dict(desc)
             from mitsuba3_b200.integrators import make_integrator
             integ = make_integrator(sc)

@@ -36,6 +36,7 @@ bench wave_order B200PT_WAVE_ORDER=1
 bench cell_order B200PT_CELL_ORDER=1
 bench phases B200PT_TRACE_PHASES=1
 bench wide B200PT_BVH_WIDE=1
+bench splat_fold B200PT_SPLAT_FOLD=1
 bench wave_order+phases B200PT_WAVE_ORDER=1 B200PT_TRACE_PHASES=1
 bench wave_order+phases+wide B200PT_WAVE_ORDER=1 B200PT_TRACE_PHASES=1 B200PT_BVH_WIDE=1
-bench all B200PT_WAVE_ORDER=1 B200PT_CELL_ORDER=1 B200PT_TRACE_PHASES=1 B200PT_BVH_WIDE=1
+bench all B200PT_WAVE_ORDER=1 B200PT_CELL_ORDER=1 B200PT_TRACE_PHASES=1 B200PT_BVH_WIDE=1 B200PT_SPLAT_FOLD=1

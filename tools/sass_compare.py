@@ -26,6 +26,8 @@ def norm(k):
     if 'k_trace_dyn' in k:
         for tail in ('ELi0ELb0ELb0EEEv', 'ELi0ELb0EEEv', 'ELi0EEEv'):
             k = k.replace(tail, 'EEEv', 1) if tail in k else k
+    if 'k_splat_gauss' in k:          # k_splat_gauss<WEIGHTS_ONLY[, FOLD = false]>
+        k = k.replace('ILb0ELb0EEEv', 'ILb0EEEv').replace('ILb1ELb0EEEv', 'ILb1EEEv')
     return k
 base={norm(k):v for k,v in base.items()}
 newn={norm(k):v for k,v in new.items()}
