@@ -123,6 +123,16 @@ class B200PTError(RuntimeError):
     pass
 
 
+def adjoint_covers_slot(bsdf_type: int, flags: int, slot: int) -> bool:
+    """BSDF slots whose parameter derivative the PRB adjoint implements (csrc/api.cu: adjoint_covers_slot).
+    Delta lobes have an exact-zero gradient in detached PRB (prb.py:296), so smooth conductor / dielectric count."""
+    if bsdf_type == BSDF_DIFFUSE:
+        return slot == SLOT_REFLECTANCE
+    if bsdf_type in (BSDF_CONDUCTOR, BSDF_DIELECTRIC):
+        return not (flags & M_ROUGH)
+    return False
+
+
 def load() -> C.CDLL:
     """Load ``libb200pt.so`` (built in-tree by ``__graft_entry__.build()``)."""
     global _lib

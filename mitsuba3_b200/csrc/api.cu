@@ -61,16 +61,22 @@ struct b200pt_scene {
     bool cell_order = false, order_waves = false; CellGrid cell_grid;     // experimental, off by default
     Wavefront wf;
     // shard pixel list cache
-    uint32_t *pix_ids = nullptr; uint32_t n_pix_ids = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
-    uint32_t *all_pix_ids = nullptr;   // identity list (weights pre-pass)
+    uint32_t *pix_ids = nullptr; uint32_t n_shard_pix = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
+    uint32_t *all_pix_ids = nullptr;   // identity list (whole frame; weights pre-pass of the gaussian adjoint)
+    uint32_t *cur_pix_ids = nullptr; uint32_t n_pix_ids = 0;   // the list selected by the last ensure_pix_ids
     unsigned long long *stats_dev = nullptr;
     float *film_own = nullptr, *out_dev = nullptr, *grad_in_dev = nullptr, *film_w = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stats = nullptr;
     std::vector<cudaEvent_t> trace_events; size_t trace_ev_used = 0;
     bool profile = false;
     b200pt_stats stats;
+    // statistics are read back lazily (b200pt_get_stats): a render call never waits for the device on their account
+    unsigned long long *stats_host = nullptr; bool stats_pending = false;
     // envmap emitter: its `data` texture and the device buffers rebuilt when that texture is updated
+    // first differentiable texture that sits in a BSDF slot whose derivative the adjoint does not implement (-1: none):
+    // the gradient entry points refuse such a scene instead of returning zeros for that parameter
+    int32_t unsupported_grad_tex = -1; std::string unsupported_grad_why;
     int32_t env_tex = -1; bool env_mis_compensation = false; float *env_dev_tex = nullptr, *env_dev_warp = nullptr;
     uint32_t env_w = 0, env_h = 0;
 };
@@ -84,6 +90,17 @@ static cudaError_t dev_upload(b200pt_scene *s, const T *host, size_t n, T **out)
     if (n) e = cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
     *out = (T *) p;
     return e;
+}
+
+// BSDF slots whose parameter derivative the PRB adjoint implements (kernels.cu: bsdf_backward). Delta lobes have
+// a zero gradient in detached PRB by construction (prb.py:296: bsdf.eval of a delta lobe is 0), so the smooth
+// conductor / dielectric slots are covered -- by an exact zero.
+static bool adjoint_covers_slot(int32_t type, uint32_t flags, int slot) {
+    switch (type) {
+        case B200PT_BSDF_DIFFUSE: return slot == B200PT_SLOT_REFLECTANCE;
+        case B200PT_BSDF_CONDUCTOR: case B200PT_BSDF_DIELECTRIC: return !(flags & B200PT_M_ROUGH);
+        default: return false;
+    }
 }
 
 extern "C" {
@@ -108,6 +125,8 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     for (cudaEvent_t e : s->trace_events) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_stats) cudaEventDestroy(s->ev_stats);
+    if (s->stats_host) cudaFreeHost(s->stats_host);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -147,7 +166,8 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     cudaDeviceProp prop; S_TRY(cudaGetDeviceProperties(&prop, device));
     s->n_sm = (uint32_t) prop.multiProcessorCount;
     S_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    S_TRY(cudaEventCreate(&s->ev0)); S_TRY(cudaEventCreate(&s->ev1));
+    S_TRY(cudaEventCreate(&s->ev0)); S_TRY(cudaEventCreate(&s->ev1)); S_TRY(cudaEventCreate(&s->ev_stats));
+    S_TRY(cudaMallocHost(&s->stats_host, ST_COUNT * sizeof(unsigned long long)));
     s->profile = getenv("B200PT_PROFILE") != nullptr;
 
     // ---- textures ----------------------------------------------------------
@@ -188,6 +208,17 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         if (b.type == B200PT_BSDF_PLASTIC) { hb[i].type = B200PT_BSDF_CONDUCTOR; hb[i].flags |= PT_M_PLASTIC; }   // shares the conductor queue / kernel
     }
     d.n_bsdfs = desc->n_bsdfs;
+    for (uint32_t i = 0; i < desc->n_bsdfs && s->unsupported_grad_tex < 0; ++i) {
+        const b200pt_bsdf &b = desc->bsdfs[i];
+        for (int k = 0; k < B200PT_MAX_SLOTS; ++k) {
+            int32_t t = b.tex[k];
+            if (t < 0 || !desc->textures[t].differentiable || adjoint_covers_slot(b.type, b.flags, k)) continue;
+            s->unsupported_grad_tex = t;
+            s->unsupported_grad_why = "texture " + std::to_string(t) + " (slot " + std::to_string(k) + " of BSDF " + std::to_string(i) + ", model " + std::to_string(b.type) +
+                                      ") is differentiable, but the PRB adjoint has no derivative for that slot; mark it non-differentiable";
+            break;
+        }
+    }
     std::vector<DevEmitter> he(desc->n_emitters);
     DevEnv henv; memset(&henv, 0, sizeof(henv)); henv.type = -1; henv.emitter_index = -1; henv.radiance_tex = -1;
     d.env = nullptr; d.env_type = -1; d.env_emitter = -1; d.env_radiance_tex = -1;
@@ -451,30 +482,51 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
     return B200PT_OK;
 }
 
+// Tile (tx, ty) belongs to rank (tx + ty * stride) % count with the smallest stride >= count/2 + 1 that is coprime
+// with count (count = 2: stride 1, a checkerboard) -- a diagonal deal: every rank meets every tile column and row, so
+// no rank owns whole columns of the image (a plain t % count does when count divides the tiles per row: 16 % load
+// imbalance on the Cornell box at 8 GPUs against 1.9 %). Same rule as mitsuba3_b200/dist.py: tile_owner.
+static uint32_t tile_stride(uint32_t count) {
+    if (count <= 2) return 1;
+    auto gcd = [](uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; };
+    uint32_t st = count / 2 + 1;
+    while (gcd(st, count) != 1) ++st;
+    return st;
+}
+
 static b200pt_status ensure_pix_ids(b200pt_scene *s, const b200pt_render_params *p) {
     uint32_t count = std::max(1u, p->shard_count), rank = p->shard_rank, ts = p->tile_size ? p->tile_size : 32;
     if (rank >= count) return fail(B200PT_ERR_INVALID, "shard_rank >= shard_count");
-    if (s->pix_ids && s->pix_key[0] == rank && s->pix_key[1] == count && s->pix_key[2] == ts) return B200PT_OK;
     uint32_t W = s->dev.crop_w, H = s->dev.crop_h;
-    std::vector<uint32_t> ids; ids.reserve((size_t) W * H / count + 1024);
-    uint32_t tiles_x = (W + ts - 1) / ts, tiles_y = (H + ts - 1) / ts;
-    // pixel-tile sharding: tile (tx, ty) belongs to rank (tx + ty * (count/2 + 1)) % count --
-    // a diagonal deal, so that no rank owns whole tile columns (a plain t % count does when count divides
-    // tiles_x: measured 16 % load imbalance on the Cornell box at 8 GPUs, 1.9 % with this rule). Within a
-    // rank the pixels are enumerated tile by tile in scanline order of the tiles, row-major inside a tile.
-    const uint32_t stride = count / 2 + 1;
-    for (uint32_t t = 0; t < tiles_x * tiles_y; ++t) {
-        uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
-        if ((tx + ty * stride) % count != rank) continue;
-        for (uint32_t y = ty * ts; y < std::min(H, (ty + 1) * ts); ++y)
-            for (uint32_t x = tx * ts; x < std::min(W, (tx + 1) * ts); ++x) ids.push_back(y * W + x);
+    if (count == 1) {
+        // whole frame in scanline order: its own cache slot (the gaussian adjoint uses it next to the shard's list)
+        if (!s->all_pix_ids) {
+            std::vector<uint32_t> ids((size_t) W * H);
+            for (uint32_t i = 0; i < W * H; ++i) ids[i] = i;
+            CU_TRY(cudaMalloc(&s->all_pix_ids, std::max<size_t>(ids.size(), 1) * 4));
+            CU_TRY(cudaMemcpy(s->all_pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+        }
+        s->cur_pix_ids = s->all_pix_ids; s->n_pix_ids = W * H;
+        return B200PT_OK;
     }
-    if (count == 1) { ids.resize((size_t) W * H); for (uint32_t i = 0; i < W * H; ++i) ids[i] = i; }   // whole frame: scanline order
-    if (s->pix_ids) { cudaFree(s->pix_ids); s->pix_ids = nullptr; }
-    CU_TRY(cudaMalloc(&s->pix_ids, std::max<size_t>(ids.size(), 1) * 4));
-    CU_TRY(cudaMemcpy(s->pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
-    s->n_pix_ids = (uint32_t) ids.size();
-    s->pix_key[0] = rank; s->pix_key[1] = count; s->pix_key[2] = ts;
+    if (!(s->pix_ids && s->pix_key[0] == rank && s->pix_key[1] == count && s->pix_key[2] == ts)) {
+        std::vector<uint32_t> ids; ids.reserve((size_t) W * H / count + 1024);
+        uint32_t tiles_x = (W + ts - 1) / ts, tiles_y = (H + ts - 1) / ts;
+        // within a rank the pixels are enumerated tile by tile in scanline order of the tiles, row-major inside a tile
+        const uint32_t stride = tile_stride(count);
+        for (uint32_t t = 0; t < tiles_x * tiles_y; ++t) {
+            uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
+            if ((tx + ty * stride) % count != rank) continue;
+            for (uint32_t y = ty * ts; y < std::min(H, (ty + 1) * ts); ++y)
+                for (uint32_t x = tx * ts; x < std::min(W, (tx + 1) * ts); ++x) ids.push_back(y * W + x);
+        }
+        if (s->pix_ids) { cudaFree(s->pix_ids); s->pix_ids = nullptr; }
+        CU_TRY(cudaMalloc(&s->pix_ids, std::max<size_t>(ids.size(), 1) * 4));
+        CU_TRY(cudaMemcpy(s->pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+        s->n_shard_pix = (uint32_t) ids.size();
+        s->pix_key[0] = rank; s->pix_key[1] = count; s->pix_key[2] = ts;
+    }
+    s->cur_pix_ids = s->pix_ids; s->n_pix_ids = s->n_shard_pix;
     return B200PT_OK;
 }
 
@@ -499,7 +551,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
     if (s->cell_order || s->order_waves) CU_TRY(cudaMemsetAsync(w.cell_hist, 0, CELL_BINS * 4, st));
     int g_all = grid_for(s, lanes);
-    launch_generate(d, cfg, s->pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
+    launch_generate(d, cfg, s->cur_pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
     s->stats.kernel_launches++;
     Launch L = s->launch;
     L.grid = std::min<int>(s->launch.grid, (int) ((lanes + BLOCK - 1) / BLOCK)); if (L.grid < 1) L.grid = 1;
@@ -548,6 +600,12 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
             if (alive[0] + alive[1] + alive[2] + alive[3] + alive[QCOUNT_ENV] == 0) break;
         }
     }
+    if (max_b < cfg.max_depth && !(cfg.adjoint && !cfg.forward)) {
+        // the bounce counters ran out before max_depth (unbounded paths only): the lanes still queued hand in the radiance
+        // they have gathered so far instead of leaving their lane_result entry unwritten
+        launch_flush(w.buf[cur], w.q, w.counts + (size_t) max_b * 8, w.lane_result, g_all, st);
+        s->stats.kernel_launches++;
+    }
     CU_TRY(cudaGetLastError());
     return B200PT_OK;
 }
@@ -562,11 +620,29 @@ static RenderCfg make_cfg(const b200pt_scene *s, const b200pt_render_params *p) 
     return c;
 }
 
-static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix) {
+// bytes of wavefront state per lane (ensure_wavefront)
+static size_t wavefront_bytes_per_lane(const b200pt_scene *s, bool adjoint) {
+    size_t per = 2 * (8 * 16 + 8 + (adjoint ? 32 : 0)) + 3 * 16;      // two path buffers + hit, lane_result, lane_dL
+    for (int t = 0; t < N_BSDF_TYPES; ++t) if (s->type_present[t]) per += 4;
+    if (s->dev.env_type >= 0) per += 4;
+    if (s->cell_order || s->order_waves) per += 8 + 4;
+    return per;
+}
+
+static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix, bool adjoint) {
     size_t lanes = p->chunk_lanes;
     if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 26); }   // 64 Mi lanes (~26 GB of wavefront state): fewest launches, measured best (profiles/r01_tuning.md)
+    // never ask for more state than the device can hold next to what other users of the GPU (torch, NCCL) have taken:
+    // the wavefront already allocated counts as available, 10 % of the free memory stays untouched
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        size_t per = wavefront_bytes_per_lane(s, adjoint);
+        bool have_adj = s->wf.cap && s->wf.buf[0].adj_L != nullptr;
+        size_t held = s->wf.cap * wavefront_bytes_per_lane(s, have_adj);
+        size_t fit = (size_t) ((double) (free_b + held) * 0.9) / per;
+        if (lanes > fit) lanes = std::max<size_t>(fit, 1024);
+    }
     size_t px = std::max<size_t>(1, lanes / std::max(1u, p->spp));
-    (void) s;
     return std::min<size_t>(px, std::max(1u, n_pix));
 }
 
@@ -582,22 +658,34 @@ static b200pt_status validate_params(const b200pt_scene *s, const b200pt_render_
 
 static void begin_stats(b200pt_scene *s, cudaStream_t st) {
     memset(&s->stats, 0, sizeof(s->stats));
+    s->stats_pending = false;
     s->trace_ev_used = 0;
     cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), st);
     cudaEventRecord(s->ev0, st);
 }
 
 static b200pt_status end_stats(b200pt_scene *s, cudaStream_t st, uint64_t samples) {
+    // no host synchronisation here: the counters travel to pinned host memory behind the kernels of this call and
+    // are resolved by b200pt_get_stats (a frame that is followed by an NCCL all-reduce must not stall the host first)
     CU_TRY(cudaEventRecord(s->ev1, st));
-    unsigned long long h[ST_COUNT];
-    CU_TRY(cudaMemcpyAsync(h, s->stats_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaMemcpyAsync(s->stats_host, s->stats_dev, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(s->ev_stats, st));
+    s->stats.samples = samples;
+    s->stats_pending = true;
+    return B200PT_OK;
+}
+
+static b200pt_status resolve_stats(b200pt_scene *s) {
+    if (!s->stats_pending) return B200PT_OK;
+    CU_TRY(cudaEventSynchronize(s->ev_stats));
+    const unsigned long long *h = s->stats_host;
     float ms = 0.f; CU_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->stats.device_ms = ms; s->stats.samples = samples; s->stats.bounces = h[ST_BOUNCES]; s->stats.shadow_rays = h[ST_SHADOW];
+    s->stats.device_ms = ms; s->stats.bounces = h[ST_BOUNCES]; s->stats.shadow_rays = h[ST_SHADOW];
     s->stats.trace_rays = h[ST_CLOSEST] + h[ST_SHADOW];
     double tms = 0;
     for (size_t i = 0; i + 1 < s->trace_ev_used; i += 2) { float m = 0.f; if (cudaEventElapsedTime(&m, s->trace_events[i], s->trace_events[i + 1]) == cudaSuccess) tms += m; }
     s->stats.trace_ms = tms;
+    s->stats_pending = false;
     return B200PT_OK;
 }
 
@@ -627,13 +715,13 @@ b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_para
         return end_stats(s, st, 0);
     }
     RenderCfg cfg = make_cfg(s, p);
-    size_t cpx = chunk_pixels(s, p, s->n_pix_ids);
+    size_t cpx = chunk_pixels(s, p, s->n_pix_ids, false);
     e = ensure_wavefront(s, cpx * p->spp, false); if (e) return e;
     for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
         size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
         cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p->spp);
         e = run_chunk(s, cfg, 0, st); if (e) return e;
-        launch_splat(s->dev, cfg, s->pix_ids, s->wf.lane_result, film_device, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+        launch_splat(s->dev, cfg, s->cur_pix_ids, s->wf.lane_result, film_device, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
         s->stats.kernel_launches++;
     }
     CU_TRY(cudaGetLastError());
@@ -664,6 +752,7 @@ b200pt_status b200pt_render(b200pt_scene *s, const b200pt_render_params *p, floa
 b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render_params *p_, const float *grad_in_device, void *cuda_stream) {
     b200pt_status vs = validate_params(s, p_); if (vs) return vs;
     if (!grad_in_device) return fail(B200PT_ERR_INVALID, "null grad_in");
+    if (s->unsupported_grad_tex >= 0) return fail(B200PT_ERR_UNSUPPORTED, s->unsupported_grad_why);
     b200pt_render_params p = *p_; p.prb = 1;
     CU_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t) cuda_stream;   // NULL = the CUDA default stream, as everywhere in CUDA
@@ -683,13 +772,13 @@ b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render
         for (size_t pix0 = 0; pix0 < npix; pix0 += cpx) {
             size_t npx = std::min(cpx, npix - pix0);
             wc.chunk_pix0 = (uint32_t) pix0; wc.chunk_lanes = (uint32_t) (npx * p.spp);
-            launch_weights(d, wc, s->pix_ids, s->film_w, grid_for(s, wc.chunk_lanes), st);
+            launch_weights(d, wc, s->cur_pix_ids, s->film_w, grid_for(s, wc.chunk_lanes), st);
             s->stats.kernel_launches++;
         }
     }
     b200pt_status e = ensure_pix_ids(s, &p); if (e) return e;
     if (s->n_pix_ids == 0) return end_stats(s, st, 0);
-    size_t cpx = chunk_pixels(s, &p, s->n_pix_ids);
+    size_t cpx = chunk_pixels(s, &p, s->n_pix_ids, true);
     e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
     for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
         size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
@@ -697,7 +786,7 @@ b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render
         // pass 1: primal with the same stream (sampler.clone(), common.py:752) -> L per lane
         e = run_chunk(s, cfg, 0, st); if (e) return e;
         // dL per lane: adjoint of splat + develop
-        launch_splat_adjoint(d, cfg, s->pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, cfg.chunk_lanes), st);
+        launch_splat_adjoint(d, cfg, s->cur_pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, cfg.chunk_lanes), st);
         s->stats.kernel_launches++;
         // pass 2: adjoint replay (common.py:765)
         e = run_chunk(s, cfg, 1, st); if (e) return e;
@@ -721,6 +810,7 @@ b200pt_status b200pt_render_backward(b200pt_scene *s, const b200pt_render_params
 b200pt_status b200pt_render_forward(b200pt_scene *s, const b200pt_render_params *p_, float *out_host) {
     b200pt_status vs = validate_params(s, p_); if (vs) return vs;
     if (!out_host) return fail(B200PT_ERR_INVALID, "null argument");
+    if (s->unsupported_grad_tex >= 0) return fail(B200PT_ERR_UNSUPPORTED, s->unsupported_grad_why);
     b200pt_render_params p = *p_; p.prb = 1;
     CU_TRY(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
@@ -730,14 +820,14 @@ b200pt_status b200pt_render_forward(b200pt_scene *s, const b200pt_render_params 
     begin_stats(s, st);
     if (p.max_depth != 0 && s->n_pix_ids != 0) {
         RenderCfg cfg = make_cfg(s, &p);
-        size_t cpx = chunk_pixels(s, &p, s->n_pix_ids);
+        size_t cpx = chunk_pixels(s, &p, s->n_pix_ids, true);
         e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
         for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
             size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
             cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
             e = run_chunk(s, cfg, 0, st); if (e) return e;      // primal: L per lane
             e = run_chunk(s, cfg, 2, st); if (e) return e;      // forward replay: dL per lane
-            launch_splat(s->dev, cfg, s->pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+            launch_splat(s->dev, cfg, s->cur_pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
             s->stats.kernel_launches++;
         }
     }
@@ -861,6 +951,8 @@ b200pt_status b200pt_env_query(b200pt_scene *s, uint32_t n, const float *in_host
 
 b200pt_status b200pt_get_stats(b200pt_scene *s, b200pt_stats *out) {
     if (!s || !out) return fail(B200PT_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    b200pt_status e = resolve_stats(s); if (e) return e;
     *out = s->stats;
     return B200PT_OK;
 }

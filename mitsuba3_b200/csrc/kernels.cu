@@ -1316,6 +1316,23 @@ void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, con
     else k_shade_env<false><<<grid, BLOCK, 0, st>>>(sc, cfg, cur, queue, qcount, lane_result, stats);
 }
 
+// Lanes still queued when the per-chunk bounce counters run out (api.cu: MAX_BOUNCE_SLOTS, unbounded paths only) hand in
+// the radiance gathered so far.
+__global__ void __launch_bounds__(BLOCK) k_flush(PathBuf cur, Queues q, const uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int t = 0; t < N_QUEUES; ++t) {
+        if (!q.slots[t]) continue;
+        const uint32_t n = qcounts[t == Q_ENV ? QCOUNT_ENV : t];
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            uint32_t slot = q.slots[t][i];
+            lane_result[cur.rng[slot].w] = cur.result[slot];
+        }
+    }
+}
+void launch_flush(PathBuf cur, Queues q, const uint32_t *qcounts, float4 *lane_result, int grid, cudaStream_t st) {
+    k_flush<<<grid, BLOCK, 0, st>>>(cur, q, qcounts, lane_result);
+}
+
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st) {
     k_env_query<<<(int) ((n + 127) / 128), 128, 0, st>>>(sc, n, in, out);
 }

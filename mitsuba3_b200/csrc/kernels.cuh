@@ -81,6 +81,7 @@ void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, co
                        uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st);
 void launch_wave_order(PathBuf cur, const uint32_t *n_in, const CellGrid &g, uint2 *keyrank, uint32_t *hist, uint32_t *offsets, uint32_t *order_buf,
                        int grid, cudaStream_t st);
+void launch_flush(PathBuf cur, Queues q, const uint32_t *qcounts, float4 *lane_result, int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,

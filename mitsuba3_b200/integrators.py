@@ -213,6 +213,11 @@ class PRBIntegrator(PathIntegrator):
         p = self.params(scene, seed, spp)
         abi.check(ds.lib.b200pt_render_backward(ds.h, C.byref(p), g.ctypes.data_as(C.POINTER(C.c_float))), ds.lib)
         names = scene.parameters() if params is None else {k: scene.parameters()[k] for k in params}
+        if params is not None:
+            bad = [k for k, i in names.items() if not scene.textures[i].differentiable]
+            if bad:      # never a silent zero: the adjoint has no derivative for these slots
+                raise RuntimeError(f"no gradient available for {bad}: the parameter is marked non-differentiable or sits in a "
+                                   f"BSDF slot whose derivative the PRB adjoint does not implement")
         return {k: ds.grad(i) for k, i in names.items() if scene.textures[i].differentiable}
 
 

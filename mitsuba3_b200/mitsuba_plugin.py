@@ -43,7 +43,7 @@ class _Extractor:
         self.sensor_mi = scene.sensors()[sensor] if isinstance(sensor, int) else sensor
 
     # ---- textures from a traversed parameter set ---------------------------------
-    def _texture(self, params, prefix, key, name, channels, default=None, differentiable=True):
+    def _texture(self, params, prefix, key, name, channels, default=None, differentiable=None):
         """`prefix.key.value` (constant) or `prefix.key.data` (bitmap tensor)."""
         k_val, k_data = f"{prefix}{key}.value", f"{prefix}{key}.data"
         t = TextureData(name=name, channels=channels, differentiable=differentiable)
@@ -339,6 +339,7 @@ def register(mi):
         def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
             host = self._host_scene(scene, sensor)
             self._sync_params(host, scene)
+            self._refuse_uncovered(host, params)
             grads = self._impl.render_backward(host, np.array(grad_in, np.float32), seed=int(seed), spp=int(spp))
             env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
             for name, g in grads.items():
@@ -347,10 +348,21 @@ def register(mi):
                 if name in params and dr.grad_enabled(params[name]):
                     dr.accum_grad(params[name], type(params[name])(g))     # opt.step() reads dr.grad (drjit/opt.py:451)
 
+        @staticmethod
+        def _refuse_uncovered(host, params):
+            # a parameter the caller tracks (dr.enable_grad) whose derivative the adjoint lacks: fail, never a silent zero
+            from .integrators import device_scene
+            device_scene(host)          # resolves TextureData.differentiable
+            names = host.parameters()
+            bad = [k for k in names if k in params and dr.grad_enabled(params[k]) and not host.textures[names[k]].differentiable]
+            if bad:
+                raise NotImplementedError(f"b200_prb: no derivative implemented for {bad}")
+
         def render_forward(self, scene, params, sensor=0, seed=0, spp=0):
             # tangents = the gradients the caller attached with dr.set_grad (common.py:536-539)
             host = self._host_scene(scene, sensor)
             self._sync_params(host, scene)
+            self._refuse_uncovered(host, params)
             names = host.parameters()
             env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
             tangents = {}

@@ -55,7 +55,10 @@ class TextureData:
     wrap: int = abi.WRAP_REPEAT
     filter: int = abi.FILTER_BILINEAR
     to_uv: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=f32))
-    differentiable: bool = True
+    # True / False, or None = "wherever the PRB adjoint has the derivative" (resolved by Scene.build_desc: a texture
+    # that sits in a BSDF slot without an implemented derivative is not a gradient target -- asking
+    # render_backward for it by name raises instead of returning zeros)
+    differentiable: bool | None = None
 
     @property
     def size(self) -> int:
@@ -158,6 +161,14 @@ class Scene:
         descriptor points to and must outlive the C call."""
         keep = []
         texs = (abi.Texture * max(1, len(self.textures)))()
+        uncovered = set()
+        for b in self.bsdfs:
+            for k, ti in enumerate(b.tex):
+                if ti >= 0 and not abi.adjoint_covers_slot(b.type, b.flags, k):
+                    uncovered.add(ti)
+        for i, t in enumerate(self.textures):
+            if t.differentiable is None:
+                t.differentiable = i not in uncovered
         for i, t in enumerate(self.textures):
             ct = texs[i]
             ct.kind, ct.channels = t.kind, t.channels

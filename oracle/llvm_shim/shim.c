@@ -13,6 +13,7 @@
 
 #include "shim_tab.inc"
 
+#define EXPORT __attribute__((visibility("default")))
 void *shim_slot[SHIM_N];
 static void *lite;
 
@@ -53,7 +54,20 @@ __attribute__((constructor)) static void shim_init(void) {
 #undef PY
 }
 
-#define EXPORT __attribute__((visibility("default")))
+/* Dr.Jit's MCJIT path needs position-independent code and, for lack of a C API, finds the relocation-model field of
+ * the TargetMachine by scanning for the three consecutive 32-bit fields {Reloc::Static = 0, CodeModel::Small = 1,
+ * CodeGenOpt::Aggressive = 3} and overwriting the first (llvm_mcjit.cpp:52-100).  Since LLVM 17 a 64-bit
+ * `LargeDataThreshold` sits between the code model and the optimisation level, so the key no longer matches.
+ * The threshold is only consulted for the medium / large code models; setting it to 3 under the small model is
+ * inert and restores the {0, 1, 3} pattern exactly at the relocation-model field, which Dr.Jit then sets to PIC. */
+EXPORT void *LLVMGetExecutionEngineTargetMachine(void *engine) {
+    void *(*real)(void *) = (void *(*)(void *)) shim_slot[SHIM_SLOT_LLVMGetExecutionEngineTargetMachine];
+    unsigned *tm = (unsigned *) real(engine);
+    if (tm)
+        for (int i = 96; i < 192; ++i)
+            if (tm[i] <= 1u && tm[i + 1] == 1u && tm[i + 2] == 0u && tm[i + 3] == 0u && tm[i + 4] == 3u) { tm[i + 2] = 3u; break; }
+    return tm;
+}
 
 /* ---- new pass manager (LLVM-C: llvm-c/Transforms/PassBuilder.h) on llvmlite's wrappers ---------- */
 EXPORT void *LLVMCreatePassBuilderOptions(void) { return PY_CreatePTO(); }

@@ -11,5 +11,8 @@ def reference_env(root=None):
             env = dict(os.environ)
             env["PYTHONPATH"] = os.pathsep.join([os.path.join(base, "python"), root, env.get("PYTHONPATH", "")])
             env["LD_LIBRARY_PATH"] = os.pathsep.join([base, os.path.join(base, "python", "mitsuba"), os.path.join(base, "python", "drjit"), env.get("LD_LIBRARY_PATH", "")])
+            shim = os.path.join(root, "oracle", "_ref", "llvm_shim", "libLLVM.so")     # oracle/llvm_shim: llvm_ad_rgb without a system libLLVM
+            if os.path.exists(shim) and "DRJIT_LIBLLVM_PATH" not in env:
+                env["DRJIT_LIBLLVM_PATH"] = shim
             return env
     return None
