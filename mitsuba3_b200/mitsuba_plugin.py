@@ -303,23 +303,34 @@ def register(mi):
             self._cache = {}
 
         def _host_scene(self, scene, sensor):
+            # keyed by the scene object itself (weak reference: an id() can be reused after the scene is collected)
+            import weakref
             key = (id(scene), sensor if isinstance(sensor, int) else id(sensor))
-            if key not in self._cache:
-                self._cache[key] = extract_scene(mi, scene, sensor)
-            return self._cache[key]
+            ent = self._cache.get(key)
+            if ent is None or ent[1]() is not scene:
+                host = extract_scene(mi, scene, sensor)
+                ent = (host, weakref.ref(scene), mi.traverse(scene))     # the parameter map is built once per scene
+                self._cache[key] = ent
+            self._params_of = ent[2]
+            return ent[0]
 
         def _sync_params(self, host, scene):
-            """Push the current values of the differentiable parameters (optimiser steps)."""
-            params = mi.traverse(scene)
+            """Push the parameter values that CHANGED since the last call (optimiser steps) to the device scene."""
+            params = self._params_of
+            names = host.parameters()
             vals = {}
             env_tex = {host.textures[e.radiance_tex].name for e in host.emitters if e.type == abi.EMITTER_ENVMAP}
-            for name in host.parameters():
+            for name, ti in names.items():
                 if name in params:
                     v = np.array(params[name], np.float32)
                     if name in env_tex:      # the plugin's `data` tensor carries two halo columns (envmap.cpp:155-192)
                         v = np.ascontiguousarray(v.reshape(tuple(int(n) for n in params[name].shape))[:, 1:-1, :])
+                    cur = host.textures[ti].array()
+                    if v.size == cur.size and np.array_equal(v.reshape(-1), np.asarray(cur, np.float32).reshape(-1)):
+                        continue             # unchanged: no upload, no envmap warp rebuild
                     vals[name] = v
-            update_params(host, vals)
+            if vals:
+                update_params(host, vals)
 
         def render(self, scene, sensor=0, seed=0, spp=0, develop=True, evaluate=True):
             host = self._host_scene(scene, sensor)
