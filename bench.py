@@ -156,10 +156,14 @@ def cpu_baseline_reference(workload, spp_sample, reps=1, prb_spp=0):
     w, h, spp, md, rf = WORKLOADS[workload]
     for variant in ("llvm_ad_rgb", "scalar_rgb"):
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), variant, workload, str(w), str(h), str(spp_sample), str(md), rf,
-                                str(reps), str(prb_spp)], env=env, capture_output=True, text=True, timeout=1500)
+            # the JIT variant renders the frame at its full sample count, three times (~10-20 s of CPU work on the
+            # 16-core lease); the scalar variant gets the bounded sample
+            vs, vr = (spp, max(reps, 3)) if variant == "llvm_ad_rgb" else (spp_sample, reps)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), variant, workload, str(w), str(h), str(vs), str(md), rf,
+                                str(vr), str(min(prb_spp, vs))], env=env, capture_output=True, text=True, timeout=1500)
             j = json.loads(r.stdout.strip().splitlines()[-1])
             if "error" not in j:
+                j["spp_sample"] = vs
                 return j
             print("reference arm:", j["error"], file=sys.stderr)
         except Exception as e:      # noqa: BLE001
@@ -178,7 +182,7 @@ def cpu_baseline(scene, workload, spp1, prb=False):
         out = {"value": ref["msamples_per_s"], "unit": "Msamples/s", "cores": cores, "cores_detail": detail, "threads": ref.get("threads"),
                "kind": "reference", "seconds": ref["seconds"], "variant": ref["variant"], "accel": ref["accel"],
                "sample": f"mitsuba {ref['version']} {ref['variant']}, {ref['accel']}, {cores} effective host cores ({ref.get('threads')} Dr.Jit threads), "
-                         f"same frame {w}x{h}, max_depth {md}, {spp_sample} of {spp1} spp ({ref['seconds']:.1f} s)"}
+                         f"same frame {w}x{h}, max_depth {md}, {ref['spp_sample']} of {spp1} spp ({ref['seconds']:.1f} s per render)"}
         if "prb_ms_per_grad_step" in ref:
             # scaled linearly in spp to the GPU arm's 64 spp gradient step when the sample used fewer
             out["prb"] = {"ms_per_grad_step": ref["prb_ms_per_grad_step"] * 64.0 / ref["prb_spp"], "measured_spp": ref["prb_spp"],

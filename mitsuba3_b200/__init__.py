@@ -7,7 +7,7 @@ the reference's Python interface (``load_dict`` / ``render`` / integrator
 ``render`` + ``render_backward`` / parameter map). There is no CPU fallback.
 """
 from .scene import (Scene, load_dict, cornell_box, cornell_box_heightfield, heightfield_mesh,  # noqa: F401
-                    matpreview_like, uv_sphere_mesh, synthetic_sky)
+                    matpreview_like, matpreview_scene, uv_sphere_mesh, synthetic_sky)
 from .transform import Transform4f  # noqa: F401
 
 ScalarTransform4f = Transform4f

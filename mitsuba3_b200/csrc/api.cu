@@ -43,9 +43,6 @@ struct Wavefront {
     float4 *hit = nullptr, *lane_result = nullptr, *lane_dL = nullptr;
     Queues q;
     uint32_t *counts = nullptr; size_t n_counts = 0;
-    // experimental cell ordering of the material queues (B200PT_CELL_ORDER=1), see kernels.cu: k_cell_keys
-    uint2 *cell_keyrank = nullptr; uint32_t *cell_hist = nullptr, *cell_offsets = nullptr, *cell_sorted = nullptr;
-    uint32_t *wave_order = nullptr;     // experimental ordered traversal (B200PT_WAVE_ORDER=1): [0] = count, [4 ..] = slots
     std::vector<void *> allocs;
 };
 
@@ -58,7 +55,6 @@ struct b200pt_scene {
     size_t grad_floats = 0;
     uint32_t n_sm = 148;
     Launch launch;
-    bool cell_order = false, order_waves = false; CellGrid cell_grid;     // experimental, off by default
     Wavefront wf;
     // shard pixel list cache
     uint32_t *pix_ids = nullptr; uint32_t n_shard_pix = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
@@ -279,7 +275,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     // ---- shapes: flatten to one vertex / primitive array ---------------------
     size_t n_verts = 0, n_prims = 0;
     for (uint32_t i = 0; i < desc->n_shapes; ++i) { n_verts += desc->shapes[i].n_vertices; n_prims += desc->shapes[i].n_faces; }
-    if (n_prims >= (1u << 28)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles");
+    if (n_prims >= (1u << 26)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles (the traversal queue addresses 2^26)");
     std::vector<float> verts(n_verts * 8); std::vector<uint32_t> pv(n_prims * 4); std::vector<float> tri9(n_prims * 9);
     std::vector<DevShape> hs(desc->n_shapes);
     size_t vo = 0, po = 0;
@@ -319,16 +315,6 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
             o.area_cdf = dc; o.area_pmf = dp; o.area_sum = cdf.empty() ? 0.f : cdf.back(); o.area_norm = 1.0f / o.area_sum;
         }
         vo += sh.n_vertices; po += sh.n_faces;
-    }
-    if (const char *e = getenv("B200PT_CELL_ORDER")) s->cell_order = atoi(e) != 0;
-    if (const char *e = getenv("B200PT_WAVE_ORDER")) s->order_waves = atoi(e) != 0;
-    if (s->cell_order || s->order_waves) {      // grid of the experimental orderings: the bounding box of the vertices
-        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-        for (size_t v = 0; v < n_verts; ++v)
-            for (int k = 0; k < 3; ++k) { float x = verts[v * 8 + k]; lo[k] = std::fmin(lo[k], x); hi[k] = std::fmax(hi[k], x); }
-        float sc3[3];
-        for (int k = 0; k < 3; ++k) { if (!(hi[k] > lo[k])) { lo[k] = 0.f; hi[k] = 1.f; } sc3[k] = (float) CELL_AXIS / std::fmax(hi[k] - lo[k], 1e-20f); }
-        s->cell_grid.lo = make_float3(lo[0], lo[1], lo[2]); s->cell_grid.scale = make_float3(sc3[0], sc3[1], sc3[2]);
     }
     if (env_index >= 0) {
         scene_bounding_sphere(verts.data(), n_verts, henv.center, henv.radius);
@@ -387,21 +373,14 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
-    { const char *e = getenv("B200PT_TRACE_PHASES"); s->launch.split_phases = e ? atoi(e) != 0 : false; }   // experimental, see k_trace_dyn
-    if (const char *e = getenv("B200PT_SPLAT_FOLD")) set_splat_fold(atoi(e) != 0);      // experimental, see k_splat_gauss
-    s->launch.ordered = false;
-    s->launch.wide = false; s->launch.nodes4 = nullptr; s->launch.n_nodes4_units = 0; s->launch.n_smem_nodes_w = 0; s->launch.smem_trace_w = 0;
-    if (const char *e = getenv("B200PT_BVH_WIDE")) if (atoi(e) != 0) {      // experimental 4-wide walk, see k_trace_dyn
-        Bvh4 wide = collapse_bvh4(bvh);
-        if (3 * ((size_t) wide.depth + 1) + 2 <= 128) {                      // fits the stack of the wide walk
-            Bvh4Node *p; S_TRY(dev_upload(s, wide.nodes.data(), wide.nodes.size(), &p));
-            s->launch.wide = true; s->launch.nodes4 = (const float4 *) p;
-            s->launch.n_nodes4_units = (uint32_t) (2 * wide.nodes.size());                      // in 64-byte units
-            s->launch.n_smem_nodes_w = std::min<uint32_t>(s->launch.n_nodes4_units, 512);       // 32 KiB = 256 wide nodes
-            s->launch.smem_trace_w = ((size_t) s->launch.n_smem_nodes_w * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
-        }
+    { const char *e = getenv("B200PT_TRACE_QUEUE"); s->launch.pair_queue = e ? atoi(e) != 0 : true; }
+    { const char *e = getenv("B200PT_TRACEQ_MINB"); s->launch.queue_minb = e && atoi(e) == 4 ? 4 : 5; }
+    if (s->launch.pair_queue && s->launch.queue_minb == 4 && !getenv("B200PT_TRACE_BLOCKS_PER_SM")) s->launch.grid = (int) s->n_sm * 4;
+    if (s->launch.pair_queue && s->launch.n_smem_nodes > 256) {          // the warp queues take 14 KiB of the CTA's shared memory
+        s->launch.n_smem_nodes = 256;
+        s->launch.smem_trace = ((size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
     }
-    set_trace_smem_attr(std::max(s->launch.smem_trace, s->launch.smem_trace_w) + s->launch.smem_tables);
+    set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
     S_TRY(cudaMalloc(&s->film_own, npix * 4 * sizeof(float))); s->allocs.push_back(s->film_own);
@@ -470,13 +449,6 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
     if (s->dev.env_type >= 0) CU_TRY(A(slack * 4, (void **) &w.q.slots[Q_ENV])); else w.q.slots[Q_ENV] = nullptr;
     w.n_counts = (size_t) (MAX_BOUNCE_SLOTS + 2) * 8;
     CU_TRY(A(w.n_counts * 4, (void **) &w.counts));
-    w.cell_keyrank = nullptr; w.cell_hist = w.cell_offsets = w.cell_sorted = w.wave_order = nullptr;
-    if (s->cell_order || s->order_waves) {
-        CU_TRY(A(slack * 8, (void **) &w.cell_keyrank));
-        CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_hist)); CU_TRY(A(CELL_BINS * 4, (void **) &w.cell_offsets));
-    }
-    if (s->cell_order) CU_TRY(A(slack * 4, (void **) &w.cell_sorted));
-    if (s->order_waves) CU_TRY(A((slack + 4) * 4, (void **) &w.wave_order));
     w.q.counts = w.counts;
     w.cap = cap;
     return B200PT_OK;
@@ -549,7 +521,6 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     uint32_t lanes = cfg.chunk_lanes;
     cfg.adjoint = mode >= 1; cfg.forward = mode == 2;
     CU_TRY(cudaMemsetAsync(w.counts, 0, w.n_counts * 4, st));
-    if (s->cell_order || s->order_waves) CU_TRY(cudaMemsetAsync(w.cell_hist, 0, CELL_BINS * 4, st));
     int g_all = grid_for(s, lanes);
     launch_generate(d, cfg, s->cur_pix_ids, w.buf[0], w.lane_dL, w.lane_result, g_all, st);
     s->stats.kernel_launches++;
@@ -559,17 +530,9 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     auto trace = [&](int bufi, const uint32_t *n_in, uint32_t *qcounts, bool first) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (s->profile) { e0 = next_trace_event(s); e1 = next_trace_event(s); cudaEventRecord(e0, st); }
-        if (!first && s->order_waves && L.dynamic_fetch) {
-            // experimental: walk the wave in (origin cell, direction octant) order
-            launch_wave_order(w.buf[bufi], n_in, s->cell_grid, w.cell_keyrank, w.cell_hist, w.cell_offsets, w.wave_order, g_all, st);
-            Launch Lo = L; Lo.ordered = true;
-            launch_trace(d, cfg, w.buf[bufi], w.hit, w.wave_order, w.q, qcounts, w.lane_result, s->stats_dev, first, Lo, st);
-            s->stats.kernel_launches += 3;
-        } else
         launch_trace(d, cfg, w.buf[bufi], w.hit, n_in, w.q, qcounts, w.lane_result, s->stats_dev, first, L, st);
         if (s->profile) cudaEventRecord(e1, st);
         s->stats.kernel_launches++; s->stats.trace_launches++;
-        if (!first && L.dynamic_fetch && L.split_phases) { s->stats.kernel_launches++; s->stats.trace_launches++; }
     };
     int cur = 0;
     trace(cur, nullptr, w.counts + 0, true);
@@ -583,10 +546,6 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
         for (int t = 0; t < N_BSDF_TYPES; ++t) {
             if (!s->type_present[t]) continue;
             const uint32_t *queue = w.q.slots[t];
-            if (s->cell_order) {      // experimental: shade the queue cell by cell of the hit points
-                launch_cell_order(w.buf[cur], w.hit, w.q.slots[t], cnt + t, s->cell_grid, w.cell_keyrank, w.cell_hist, w.cell_offsets, w.cell_sorted, g_all, st);
-                queue = w.cell_sorted; s->stats.kernel_launches += 3;
-            }
             launch_shade(t, d, cfg, w.buf[cur], w.hit, queue, cnt + t, w.buf[cur ^ 1], cnt + 4, w.lane_result, s->stats_dev, Ls, st);
             s->stats.kernel_launches++;
         }
@@ -625,7 +584,6 @@ static size_t wavefront_bytes_per_lane(const b200pt_scene *s, bool adjoint) {
     size_t per = 2 * (8 * 16 + 8 + (adjoint ? 32 : 0)) + 3 * 16;      // two path buffers + hit, lane_result, lane_dL
     for (int t = 0; t < N_BSDF_TYPES; ++t) if (s->type_present[t]) per += 4;
     if (s->dev.env_type >= 0) per += 4;
-    if (s->cell_order || s->order_waves) per += 8 + 4;
     return per;
 }
 

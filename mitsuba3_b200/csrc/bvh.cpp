@@ -160,58 +160,4 @@ Bvh build_bvh(const float *tri, uint32_t n) {
     return out;
 }
 
-Bvh4 collapse_bvh4(const Bvh &bvh) {
-    struct Child { float lo[3], hi[3]; int32_t id; };
-    auto children_of = [&](int32_t node, Child out[2]) -> int {
-        const BvhNode &n = bvh.nodes[node]; int k = 0;
-        const int32_t ids[2] = { n.left, n.right };
-        for (int c = 0; c < 2; ++c) {
-            if (ids[c] == BVH_EMPTY) continue;
-            const float *f = n.f + 6 * c;
-            out[k].lo[0] = f[0]; out[k].lo[1] = f[1]; out[k].lo[2] = f[2]; out[k].hi[0] = f[3]; out[k].hi[1] = f[4]; out[k].hi[2] = f[5];
-            out[k++].id = ids[c];
-        }
-        return k;
-    };
-    Bvh4 out;
-    // breadth-first over the wide nodes; each queue entry is the binary node the wide node grows from
-    std::vector<int32_t> roots{ 0 };
-    std::vector<uint32_t> level{ 0 };
-    out.nodes.emplace_back();
-    for (size_t w = 0; w < roots.size(); ++w) {
-        Child ch[4]; int n = children_of(roots[w], ch);
-        while (n < 4) {
-            int best = -1; float best_area = -1.f;
-            for (int c = 0; c < n; ++c) {
-                if (ch[c].id < 0) continue;                                   // leaves stay as they are
-                float d[3] = { ch[c].hi[0] - ch[c].lo[0], ch[c].hi[1] - ch[c].lo[1], ch[c].hi[2] - ch[c].lo[2] };
-                float area = d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
-                if (area > best_area) { best_area = area; best = c; }
-            }
-            if (best < 0) break;
-            Child sub[2]; int m = children_of(ch[best].id, sub);
-            if (n - 1 + m > 4) break;
-            ch[best] = sub[0];
-            for (int g = 1; g < m; ++g) ch[n++] = sub[g];
-        }
-        Bvh4Node nd; std::memset(&nd, 0, sizeof(nd));
-        for (int c = 0; c < 4; ++c) {
-            if (c < n) {
-                for (int a = 0; a < 3; ++a) { nd.lo[a][c] = ch[c].lo[a]; nd.hi[a][c] = ch[c].hi[a]; }
-                if (ch[c].id >= 0) {
-                    nd.child[c] = (int32_t) roots.size();
-                    roots.push_back(ch[c].id); level.push_back(level[w] + 1);
-                    out.nodes.emplace_back();
-                    out.depth = std::max(out.depth, level[w] + 1);
-                } else nd.child[c] = ch[c].id;
-            } else {
-                for (int a = 0; a < 3; ++a) { nd.lo[a][c] = std::numeric_limits<float>::infinity(); nd.hi[a][c] = -std::numeric_limits<float>::infinity(); }
-                nd.child[c] = BVH_EMPTY;
-            }
-        }
-        out.nodes[w] = nd;
-    }
-    return out;
-}
-
 } // namespace pt

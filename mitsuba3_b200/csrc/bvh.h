@@ -48,24 +48,4 @@ struct Bvh {
 // tri: n x 9 floats (p0, p1, p2)
 Bvh build_bvh(const float *tri, uint32_t n);
 
-// 4-wide tree collapsed from the binary one (same leaves, same triangle order): the inner child with the
-// largest box is replaced by its two children until the node has four. Fewer, fatter traversal steps
-// (profiles/r01_simt_model.md); consumed by the wide traversal kernel planned for round 2, covered on the
-// CPU by tests/test_bvh_host.py.
-//
-//   node (128 B, 8 x float4), boxes as structure-of-arrays so one 16-byte load serves all four children:
-//     q0 = lo.x[0..3]  q1 = lo.y[0..3]  q2 = lo.z[0..3]  q3 = hi.x[0..3]  q4 = hi.y[0..3]  q5 = hi.z[0..3]
-//     q6 = child[0..3] as int bits, same encoding as BvhNode (>= 0 inner, < 0 leaf, BVH_EMPTY)
-//     q7 = 0
-//   Occupied children come first; empty ones carry an inverted box. Breadth-first order, root = node 0.
-struct Bvh4Node { float lo[3][4], hi[3][4]; int32_t child[4]; int32_t pad[4]; };
-static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
-
-struct Bvh4 {
-    std::vector<Bvh4Node> nodes;
-    uint32_t depth = 0;
-};
-
-Bvh4 collapse_bvh4(const Bvh &bvh);
-
 } // namespace pt

@@ -122,14 +122,6 @@ PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
     return tri < c.n_smem_tris ? c.s_tris[3 * tri + k] : __ldg(&c.g_tris[3 * (size_t) tri + k]);
 }
 
-// 4-wide nodes (bvh.h: Bvh4Node, 8 x float4) of the experimental wide walk; the shared-memory window is
-// counted in 64-byte units like the binary nodes (a wide node = two units)
-template <bool SMEM_ALL>
-PT_DEV float4 ld_node4(const TraceCtx &c, uint32_t node, int byte_off) {     // byte offset of the row inside the 128-byte node
-    if (SMEM_ALL || 2 * node + 1 < c.n_smem_nodes) return *(const float4 *) ((const char *) (c.s_nodes + 8 * node) + byte_off);
-    return __ldg((const float4 *) ((const char *) (c.g_nodes + 8 * (size_t) node) + byte_off));
-}
-
 PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
 
 // slab test, subtraction first (no cancellation against o * inv)
@@ -139,20 +131,6 @@ PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float
     float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
     float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
     float tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
-    tnear = tmin;
-    return tmin <= tmx * 1.0000004f;
-}
-
-// slab test with the near / far plane of every axis already chosen by the sign of the ray direction
-// (wide walk: the planes are separate float4 rows, so the choice is an address, not a min/max per axis).
-// For lo <= hi and the finite non-zero `inv` of safe_inv this yields bit for bit the values of box_hit:
-// rounded subtraction and multiplication are monotonic, so min((lo-o)*inv, (hi-o)*inv) IS the near product.
-PT_DEV bool box_hit_nf(float nx, float ny, float nz, float fx, float fy, float fz, float3 o, float3 inv, float tmax, float &tnear) {
-    float t0x = (nx - o.x) * inv.x, t1x = (fx - o.x) * inv.x;
-    float t0y = (ny - o.y) * inv.y, t1y = (fy - o.y) * inv.y;
-    float t0z = (nz - o.z) * inv.z, t1z = (fz - o.z) * inv.z;
-    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.f));
-    float tmx = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
     tnear = tmin;
     return tmin <= tmx * 1.0000004f;
 }
@@ -345,28 +323,12 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
 // ray of the batch. The traversal itself is the same speculative while-while walk,
 // resumable across refills (node / leaf / stack live in registers + local memory).
 // Semantics per slot are identical to k_trace.
-//
-// PHASE (experimental, off by default: B200PT_TRACE_PHASES=1; profiles/r01_simt_model.md, "separate job
-// ranges"): 0 = a job is the shadow ray of a slot followed by its path ray (above); 1 = shadow rays only,
-// 2 = path rays only, as two launches over the same slots -- any-hit and closest-hit walks no longer share
-// warps. A slot without the ray of the phase is an empty job. Launch 1 completes before launch 2 starts
-// (same stream), so a path that ends in launch 2 reads `result` with its shadow contribution already added.
-//
-// WIDE (experimental, off by default: B200PT_BVH_WIDE=1, section 3.3 of the same note): the inner-node loop
-// walks the 4-wide tree of pt::collapse_bvh4 -- `sc.nodes` then points to the Bvh4Node array, four slab tests
-// per step, the nearest child first, up to three pushes. Leaves, the
-// triangle test and the tie-break are the binary walk's, so the hits are the same.
-//
-// ORDERED (experimental, off by default: B200PT_WAVE_ORDER=1, section 3.1): job i is slot order[i] instead of
-// slot i, `order` being the wave's slots sorted by (4x4x4 cell of the ray origin, direction octant) by the
-// k_wave_keys / k_cell_scan / k_cell_scatter pass. `n_in` then points to that list's header: n_in[0] = number
-// of slots, entries from n_in[4] on (no extra kernel parameter: the shipped instantiations keep their layout).
 // ---------------------------------------------------------------------------
 
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 5
 #endif
-template <bool FIRST, bool SMEM_ALL, int PHASE = 0, bool WIDE = false, bool ORDERED = false>
+template <bool FIRST, bool SMEM_ALL>
 __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
@@ -391,7 +353,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
     float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
     float maxt = 0.f;
     Hit hit; hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
-    int32_t stack[WIDE ? 128 : 64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
+    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
     bool occluded = false;
     bool exhausted = false;           // the global pool is empty
 
@@ -413,22 +375,10 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
             if (kind == 0) {
                 uint32_t i = base + __popc(idle_mask & ((1u << lane_id) - 1u));
                 if (i < n) {
-                    const uint32_t si = ORDERED ? __ldg(&n_in[4 + i]) : i;      // the slot of job i
+                    const uint32_t si = i;
                     slot = si;
                     flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[si].w);
-                    if (PHASE == 1) {          // shadow rays only; a slot without one is an empty job
-                        if (flags & PF_HAS_SHADOW) {
-                            float4 so = cur.sh_o[si], sd = cur.sh_d[si];
-                            kind = 1; n_shadow++;
-                            start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
-                        }
-                    } else if (PHASE == 2) {   // path rays only
-                        if (flags & PF_ALIVE) {
-                            float4 ro = cur.ray_o[si], rd = cur.ray_d[si];
-                            kind = 2; n_closest++;
-                            start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
-                        }
-                    } else if (!FIRST && (flags & PF_HAS_SHADOW)) {
+                    if (!FIRST && (flags & PF_HAS_SHADOW)) {
                         float4 so = cur.sh_o[si], sd = cur.sh_d[si];
                         kind = 1; n_shadow++;
                         start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
@@ -440,45 +390,13 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, kind != 0)) {
-            if (PHASE != 0 && !exhausted) continue;     // only empty jobs came back: fetch again
-            break;
-        }
+        if (!__any_sync(0xffffffffu, kind != 0)) break;
 
         // ---- traverse until this lane's ray is done or the warp wants to refill -----------
         if (kind != 0) {
             while (node != TRAV_SENTINEL) {
                 bool searching = true;
                 while (node >= 0 && node != TRAV_SENTINEL) {
-                    if (WIDE) {
-                        // rows 0..2 = lo.xyz, 3..5 = hi.xyz of the four children: the near plane of an axis is the lo row
-                        // for a positive direction component, the hi row for a negative one
-                        // (byte offsets: lo rows at 0 / 16 / 32, hi rows 48 further; x ^ 48 flips between the two)
-                        const int kx = inv.x < 0.f ? 48 : 0, ky = inv.y < 0.f ? 48 : 0, kz = inv.z < 0.f ? 48 : 0;
-                        float4 nx = ld_node4<SMEM_ALL>(c, node, kx), ny = ld_node4<SMEM_ALL>(c, node, 16 + ky), nz = ld_node4<SMEM_ALL>(c, node, 32 + kz);
-                        float4 fx = ld_node4<SMEM_ALL>(c, node, kx ^ 48), fy = ld_node4<SMEM_ALL>(c, node, 16 + (ky ^ 48)), fz = ld_node4<SMEM_ALL>(c, node, 32 + (kz ^ 48));
-                        float4 chf = ld_node4<SMEM_ALL>(c, node, 96);
-                        int32_t c0 = __float_as_int(chf.x), c1 = __float_as_int(chf.y), c2 = __float_as_int(chf.z), c3 = __float_as_int(chf.w);
-                        float t0, t1, t2, t3;
-                        // an empty child carries the inverted box (+inf, -inf): with the planes picked by sign its near
-                        // product is +inf and its far product -inf for every finite non-zero `inv`, so it always misses
-                        bool h0 = box_hit_nf(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, o, inv, maxt, t0);
-                        bool h1 = box_hit_nf(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, o, inv, maxt, t1);
-                        bool h2 = box_hit_nf(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, o, inv, maxt, t2);
-                        bool h3 = box_hit_nf(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, o, inv, maxt, t3);
-                        // children that are missed sort last
-                        t0 = h0 ? t0 : PT_INF; t1 = h1 ? t1 : PT_INF; t2 = h2 ? t2 : PT_INF; t3 = h3 ? t3 : PT_INF;
-#define PT_CSWAP(ta, ca, tb, cb) { bool sw = tb < ta; float tlo = sw ? tb : ta, thi = sw ? ta : tb; int32_t clo = sw ? cb : ca, chi = sw ? ca : cb; ta = tlo; tb = thi; ca = clo; cb = chi; }
-                        // nearest child to the front; the others keep their order (a full sort costs 16 more instructions
-                        // per step and saves only ~1 % of the node visits: tests/test_bvh_host.py, bvh_h_trace4_ordered)
-                        PT_CSWAP(t0, c0, t1, c1) PT_CSWAP(t0, c0, t2, c2) PT_CSWAP(t0, c0, t3, c3)
-#undef PT_CSWAP
-                        // the other children that were hit go onto the stack, the walk continues in the nearest
-                        if (t3 < PT_INF) stack[++sp] = c3;
-                        if (t2 < PT_INF) stack[++sp] = c2;
-                        if (t1 < PT_INF) stack[++sp] = c1;
-                        node = t0 < PT_INF ? c0 : stack[sp--];
-                    } else {
                     float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
                     int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                     float tl, tr;
@@ -492,7 +410,6 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                             if (tr < tl) { far = cl; node = cr; }
                             stack[++sp] = far;
                         }
-                    }
                     }
                     if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }
                     if (!__any_sync(__activemask(), searching)) break;
@@ -527,10 +444,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                     res.x += sd.w; res.y += cc.x; res.z += cc.y;
                     cur.result[slot] = res;
                 }
-                if (PHASE == 1) {          // the path ray of the slot belongs to the second launch
-                    if (!(flags & PF_ALIVE)) lane_result[cur.rng[slot].w] = cur.result[slot];
-                    kind = 0;
-                } else if (flags & PF_ALIVE) {
+                if (flags & PF_ALIVE) {
                     float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
                     kind = 2; n_closest++;
                     start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
@@ -565,6 +479,247 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
                 off = __shfl_sync(0xffffffffu, off, leader);
                 if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = slot;
+            }
+        }
+    }
+    for (int of = 16; of; of >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, of); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, of); }
+    if (lane_id == 0) {
+        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_trace_queue -- persistent dynamic-fetch traversal with a WARP-WIDE TRIANGLE QUEUE (default).
+//
+// k_trace_dyn tests a leaf's triangles in the lane that found the leaf: measured on the bench frame the
+// Moeller-Trumbore loop issues 28 % of the kernel's instructions at 7 of 32 threads, and the node loop runs at 16
+// because lanes that hold a leaf wait for the others (profiles/r01_simt_model.md section 1). Here a lane that reaches
+// a leaf only APPENDS (owner lane, triangle) pairs to a queue in shared memory and keeps walking; when 32 pairs are
+// queued the whole warp tests 32 pairs at once, one pair per lane, reading the owner's ray from shared memory.
+// Results go back through a 64-bit atomicMin per owner on the key (t bits << 32 | primitive): for t >= 0 the float
+// bit pattern orders like the value, so the minimum IS the closest hit with ties resolved towards the smaller
+// primitive index -- the rule of the per-lane walk, hence identical hits (order independent). A shadow ray stores
+// key 0 = occluded. The winner of a round writes (u, v). A lane's walk uses its current best t as maxt (refreshed
+// after every triangle phase); between phases it walks on with a slightly stale maxt, which only costs node visits.
+//
+//   node phase   every lane with a live walk: queue <= 2 triangles of its current leaf, then one node step
+//   tri phase    full rounds of 32 pairs (+ the partial rest when no lane walks any more or >= REFILL lanes wait)
+//   retire       walk finished AND all its pairs tested -> same per-slot semantics as k_trace / k_trace_dyn
+//
+// Entry = any-hit flag << 31 | owner lane << 26 | triangle index (api.cu limits scenes to 2^26 triangles).
+// ---------------------------------------------------------------------------
+constexpr int TQ_RING = 128;     // ring capacity; at most 31 + 2 * 32 = 95 entries are ever queued
+struct __align__(16) WarpTrace {
+    float o[3][32], d[3][32];         // ray of every lane of the warp
+    unsigned long long best[32];      // (bits of the closest t, or of maxt) << 32 | primitive (0xffffffff: none); 0: occluded
+    float2 uv[32];
+    uint32_t queue[TQ_RING];
+};
+
+template <bool FIRST, bool SMEM_ALL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
+                                                       const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
+                                                       float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ WarpTrace s_warp[BLOCK / 32];
+    DevScene sc = sc_in;
+    float4 *s_nodes = (float4 *) smem_raw;
+    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
+    TraceCtx c = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+    WarpTrace &ws = s_warp[threadIdx.x >> 5];
+
+    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
+    const uint32_t lane_id = threadIdx.x & 31u, lt_mask = (1u << lane_id) - 1u;
+    uint32_t n_shadow = 0, n_closest = 0;
+
+    // job state of this lane
+    int kind = 0;                     // 0 idle, 1 shadow ray, 2 path ray
+    uint32_t slot = 0, flags = 0;
+    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
+    float maxt = 0.f;
+    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL;
+    uint32_t leaf_first = 0, leaf_left = 0;      // triangles of the current leaf that are not queued yet
+    uint32_t my_last = 0;                        // queue position (monotonic count) behind this lane's last entry
+    // warp-uniform queue state
+    uint32_t q_head = 0, q_count = 0, q_done = 0;      // ring start, entries queued, entries tested since the kernel started
+    bool exhausted = false;           // the global pool is empty
+
+    auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
+        o = ro; d = rd; maxt = rmaxt;
+        inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+        ws.o[0][lane_id] = o.x; ws.o[1][lane_id] = o.y; ws.o[2][lane_id] = o.z;
+        ws.d[0][lane_id] = d.x; ws.d[1][lane_id] = d.y; ws.d[2][lane_id] = d.z;
+        ws.best[lane_id] = ((unsigned long long) __float_as_uint(rmaxt) << 32) | 0xffffffffull;
+        stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf_left = 0; my_last = q_done;
+    };
+
+    while (true) {
+        // ---- refill idle lanes from the global pool --------------------------------------
+        uint32_t idle_mask = __ballot_sync(0xffffffffu, kind == 0);
+        if (!exhausted && (__popc(idle_mask) >= DYN_REFILL_IDLE)) {
+            uint32_t cnt = __popc(idle_mask), base = 0;
+            if (lane_id == 0) base = atomicAdd(work_counter, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + cnt >= n) exhausted = true;
+            if (kind == 0) {
+                uint32_t i = base + __popc(idle_mask & lt_mask);
+                if (i < n) {
+                    slot = i;
+                    flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w);
+                    if (!FIRST && (flags & PF_HAS_SHADOW)) {
+                        float4 so = cur.sh_o[i], sd = cur.sh_d[i];
+                        kind = 1; n_shadow++;
+                        start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
+                    } else {       // every queued slot is alive or has a shadow ray
+                        float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
+                        kind = 2; n_closest++;
+                        start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, kind != 0)) break;
+        __syncwarp();                 // the rays written by start_ray are visible to the whole warp
+
+        // ---- node phase (warp-synchronous loop) --------------------------------------------------
+        bool drain = false;
+        while (true) {
+            const bool walking = kind != 0 && (node != TRAV_SENTINEL || leaf_left != 0);
+            const uint32_t wm = __ballot_sync(0xffffffffu, walking);
+            if (wm == 0) { drain = true; break; }
+            if (q_count >= 32) break;
+            if (!exhausted && __popc(wm) <= 32 - DYN_REFILL_IDLE) { drain = true; break; }     // enough lanes wait: test what is queued, retire, refill
+            // (a) queue up to two triangles of the leaf this lane holds
+            const uint32_t cpush = walking ? min(leaf_left, 2u) : 0u;
+            const uint32_t m1 = __ballot_sync(0xffffffffu, cpush >= 1), m2 = __ballot_sync(0xffffffffu, cpush == 2);
+            if (m1) {
+                if (cpush) {
+                    const uint32_t off = q_count + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
+                    const uint32_t tag = (kind == 1 ? 0x80000000u : 0u) | (lane_id << 26);
+                    ws.queue[(q_head + off) & (TQ_RING - 1)] = tag | leaf_first;
+                    if (cpush == 2) ws.queue[(q_head + off + 1) & (TQ_RING - 1)] = tag | (leaf_first + 1);
+                    leaf_first += cpush; leaf_left -= cpush;
+                    my_last = q_done + off + cpush;
+                }
+                q_count += __popc(m1) + __popc(m2);
+            }
+            // (b) one node step
+            if (walking && leaf_left == 0) {
+                if (node >= 0 && node != TRAV_SENTINEL) {
+                    float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
+                    int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+                    float tl, tr;
+                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
+                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
+                    if (!hl && !hr) node = stack[sp--];
+                    else {
+                        node = hl ? cl : cr;
+                        if (hl && hr) {
+                            int32_t far = cr;
+                            if (tr < tl) { far = cl; node = cr; }
+                            stack[++sp] = far;
+                        }
+                    }
+                }
+                if (node < 0) {       // a leaf (the sentinel is positive): take it and continue with the next node of the stack
+                    const uint32_t enc = (uint32_t) ~node;
+                    leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u;
+                    node = stack[sp--];
+                }
+            }
+        }
+        __syncwarp();                 // queue entries are visible
+
+        // ---- triangle phase: one (ray, triangle) pair per lane ------------------------------------
+        {
+            uint32_t todo = drain ? q_count : (q_count & ~31u);
+            while (todo) {
+                const uint32_t nr = min(todo, 32u);
+                bool won = false; unsigned long long key = 0; uint32_t owner = 0; float u = 0.f, v = 0.f;
+                if (lane_id < nr) {
+                    const uint32_t e = ws.queue[(q_head + lane_id) & (TQ_RING - 1)];
+                    owner = (e >> 26) & 31u;
+                    const uint32_t tri = e & 0x03ffffffu;
+                    const unsigned long long b = ws.best[owner];
+                    if (b != 0ull) {
+                        const float mt = __uint_as_float((uint32_t) (b >> 32));
+                        const float3 ro = V(ws.o[0][owner], ws.o[1][owner], ws.o[2][owner]), rd = V(ws.d[0][owner], ws.d[1][owner], ws.d[2][owner]);
+                        float4 ta = ld_tri<SMEM_ALL>(c, tri, 0), tb = ld_tri<SMEM_ALL>(c, tri, 1), te = ld_tri<SMEM_ALL>(c, tri, 2);
+                        float t;
+                        if (moeller_trumbore(ro, rd, mt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
+                            // t + 0: a hit at t = -0 gets the bit pattern of +0, so that the unsigned order of the keys is the order of t
+                            key = (e >> 31) ? 0ull : (((unsigned long long) __float_as_uint(t + 0.f) << 32) | __float_as_uint(ta.w));
+                            const unsigned long long old = atomicMin(&ws.best[owner], key);
+                            won = !(e >> 31) && key < old;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (won && ws.best[owner] == key) ws.uv[owner] = make_float2(u, v);     // the round's closest hit of that ray
+                __syncwarp();
+                q_head = (q_head + nr) & (TQ_RING - 1); q_count -= nr; q_done += nr; todo -= nr;
+            }
+        }
+
+        // ---- refresh maxt / occlusion of the walking lanes, retire finished rays -------------------------
+        int mytype = -1;
+        if (kind != 0) {
+            const unsigned long long b = ws.best[lane_id];
+            if (kind == 1) { if (b == 0ull) { node = TRAV_SENTINEL; leaf_left = 0; } }     // any-hit: stop at the first occluder
+            else maxt = __uint_as_float((uint32_t) (b >> 32));
+            const bool done = node == TRAV_SENTINEL && leaf_left == 0 && (int32_t) (q_done - my_last) >= 0;
+            if (done) {
+                if (kind == 1) {
+                    if (b != 0ull) {
+                        float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
+                        res.x += sd.w; res.y += cc.x; res.z += cc.y;
+                        cur.result[slot] = res;
+                    }
+                    if (flags & PF_ALIVE) {
+                        float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
+                        kind = 2; n_closest++;
+                        start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
+                    } else {
+                        lane_result[cur.rng[slot].w] = cur.result[slot];
+                        kind = 0;
+                    }
+                } else {
+                    const uint32_t prim = (uint32_t) b;
+                    const bool found = prim != 0xffffffffu;
+                    const float ht = __uint_as_float((uint32_t) (b >> 32));
+                    const float2 huv = ws.uv[lane_id];
+                    if (FIRST && cfg.hide_emitters && found && sc.shapes[sc.prim_verts[prim].w].emitter >= 0) {
+                        // skip_area_emitters (integrator.cpp:96-123)
+                        SurfaceInteraction si = compute_si(sc, ht, huv.x, huv.y, prim, d);
+                        Ray r = spawn_ray(si.p, si.n, d);
+                        cur.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt);
+                        start_ray(r.o, d, r.maxt);
+                    } else {
+                        if (found) {
+                            hit_out[slot] = make_float4(ht, huv.x, huv.y, __uint_as_float(prim));
+                            mytype = sc.bsdfs[sc.shapes[sc.prim_verts[prim].w].bsdf].type;
+                        } else if (sc.env_type >= 0) mytype = Q_ENV;     // the ray left the scene: environment emitter (k_shade_env)
+                        else lane_result[cur.rng[slot].w] = cur.result[slot];
+                        kind = 0;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < N_QUEUES; ++t) {
+            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
+            if (m) {
+                uint32_t leader = __ffs(m) - 1, off = 0;
+                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (mytype == t) q.slots[t][off + __popc(m & lt_mask)] = slot;
             }
         }
     }
@@ -958,13 +1113,12 @@ PT_DEV void sample_film_pos(const DevScene &sc, const RenderCfg &cfg, uint32_t p
 // with shuffles and issues one fp32 atomicAdd per (tap, channel) instead of 32.
 // WEIGHTS_ONLY accumulates only the weight channel (first pass of the adjoint).
 //
-// FOLD (experimental, off by default: B200PT_SPLAT_FOLD=1, not yet run on a GPU): SHFL issues at a quarter of the
-// ALU rate, and the 100 butterfly reductions (500 shuffles per warp and pass) are what bounds this kernel
-// (67 M samples / 32 x 500 shuffles / 148 SMs at 1 per clock = 3.6 of its 4.1 ms). A folding reduction sums
-// 32 values per lane with 16 + 8 + 4 + 2 + 1 = 31 shuffles: at offset o the lane keeps the half of its values
-// selected by its bit o and hands the other half to its partner. Lane L ends up with the warp total of value L,
-// added in the same pairwise order as the butterfly, i.e. bit-identical (emulation in profiles/r01_simt_model.md).
-template <bool WEIGHTS_ONLY, bool FOLD = false>
+// The reduction folds: SHFL issues at a quarter of the ALU rate and 100 butterfly reductions (500 shuffles per warp)
+// bounded this kernel. A folding reduction sums 32 values per lane with 16 + 8 + 4 + 2 + 1 = 31 shuffles: at offset o
+// the lane keeps the half of its values selected by its bit o and hands the other half to its partner. Lane L ends up
+// with the warp total of value L, added in the same pairwise order as a butterfly (measured on the B200:
+// +2.6 % of the whole frame, profiles/r02_switches.md). The weights-only pass (25 values) keeps the butterfly.
+template <bool WEIGHTS_ONLY>
 __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cfg, const uint32_t *__restrict__ pix_ids,
                                                        const float4 *__restrict__ lane_result, float *__restrict__ film) {
     const uint32_t lane_id = threadIdx.x & 31u;
@@ -996,7 +1150,7 @@ __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cf
                 wx[k] = (x >= x0 && x <= x1) ? rfilter_eval(sc, (float) x - pfx) : 0.f;
                 wy[k] = (y >= y0 && y <= y1) ? rfilter_eval(sc, (float) y - pfy) : 0.f;
             }
-            if (FOLD && !WEIGHTS_ONLY) {
+            if (!WEIGHTS_ONLY) {
                 // value m = tap * 4 + channel (tap = ky * 5 + kx; channels r, g, b, weight), 100 values in 4 batches of 32
                 const bool b16 = (lane_id & 16u) != 0, b8 = (lane_id & 8u) != 0, b4 = (lane_id & 4u) != 0, b2 = (lane_id & 2u) != 0, b1 = (lane_id & 1u) != 0;
 #pragma unroll
@@ -1024,26 +1178,20 @@ __global__ void __launch_bounds__(BLOCK) k_splat_gauss(DevScene sc, RenderCfg cf
                 }
                 continue;
             }
-            float mine0 = 0.f, mine1 = 0.f, mine2 = 0.f, mine3 = 0.f;
+            float mine3 = 0.f;
 #pragma unroll
             for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
-                    float w = wx[kx] * wy[ky];
-                    float a0 = v.x * w, a1 = v.y * w, a2 = v.z * w, a3 = w;
+                    float a3 = wx[kx] * wy[ky];      // weights-only pass: the weight channel
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        if (!WEIGHTS_ONLY) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
-                        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-                    }
-                    if ((int) lane_id == ky * 5 + kx) { mine0 = a0; mine1 = a1; mine2 = a2; mine3 = a3; }
+                    for (int o = 16; o; o >>= 1) a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+                    if ((int) lane_id == ky * 5 + kx) mine3 = a3;
                 }
             if (lane_id < 25) {
                 int x = px - 2 + (int) (lane_id % 5), y = py - 2 + (int) (lane_id / 5);
                 if (x >= 0 && y >= 0 && x < W && y < H && mine3 != 0.f) {
-                    float *f = film + 4 * ((size_t) y * W + x);
-                    if (!WEIGHTS_ONLY) { atomicAdd(f + 0, mine0); atomicAdd(f + 1, mine1); atomicAdd(f + 2, mine2); }
-                    atomicAdd(f + 3, mine3);
+                    atomicAdd(film + 4 * ((size_t) y * W + x) + 3, mine3);
                 }
             }
         } else if (valid) {
@@ -1137,114 +1285,8 @@ __global__ void k_bsdf_eval(DevScene sc, uint32_t bsdf, uint32_t n, const float 
 }
 
 // ---------------------------------------------------------------------------
-// Experimental, off by default (B200PT_CELL_ORDER=1; profiles/r01_simt_model.md section 3.1, not yet run on a
-// GPU): reorder a material queue by the 8 x 8 x 8 cell of the hit point before it is shaded. The shading
-// kernels compact their survivors in processing order, so the next wave's slots end up grouped by ray
-// origin and the traversal warps see more coherent rays. Counting sort in three small launches:
-//   k_cell_keys     per queue entry: cell id of o + t d, rank inside the cell (warp-aggregated atomicAdd)
-//   k_cell_scan     exclusive scan of the 512 counters (and resets them for the next queue)
-//   k_cell_scatter  sorted[offset[cell] + rank] = slot
-// Per-lane results do not depend on the slot order (every lane carries its own RNG and film position).
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_cell_keys(PathBuf cur, const float4 *__restrict__ hit, const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount,
-                                                     CellGrid g, uint2 *__restrict__ keyrank, uint32_t *__restrict__ hist) {
-    const uint32_t n = *qcount;
-    const uint32_t lane_id = threadIdx.x & 31u;
-    const uint32_t warp_stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
-        uint32_t qi = base + lane_id;
-        bool valid = qi < n;
-        uint32_t key = 0xffffffffu;
-        if (valid) {
-            uint32_t slot = queue[qi];
-            float4 o = cur.ray_o[slot], d = cur.ray_d[slot];
-            float t = hit[slot].x;
-            int cx = (int) ((__fmaf_rn(t, d.x, o.x) - g.lo.x) * g.scale.x);
-            int cy = (int) ((__fmaf_rn(t, d.y, o.y) - g.lo.y) * g.scale.y);
-            int cz = (int) ((__fmaf_rn(t, d.z, o.z) - g.lo.z) * g.scale.z);
-            cx = min(CELL_AXIS - 1, max(0, cx)); cy = min(CELL_AXIS - 1, max(0, cy)); cz = min(CELL_AXIS - 1, max(0, cz));
-            key = (uint32_t) ((cz * CELL_AXIS + cy) * CELL_AXIS + cx);
-        }
-        uint32_t peers = __match_any_sync(0xffffffffu, key);
-        uint32_t leader = __ffs(peers) - 1, first = 0;
-        if (valid && lane_id == leader) first = atomicAdd(&hist[key], (uint32_t) __popc(peers));
-        first = __shfl_sync(0xffffffffu, first, leader);
-        if (valid) keyrank[qi] = make_uint2(key, first + __popc(peers & ((1u << lane_id) - 1u)));
-    }
-}
-
-__global__ void __launch_bounds__(CELL_BINS) k_cell_scan(uint32_t *__restrict__ hist, uint32_t *__restrict__ offsets) {
-    __shared__ uint32_t sh[CELL_BINS];
-    const uint32_t t = threadIdx.x;
-    const uint32_t v = hist[t];
-    hist[t] = 0;                      // ready for the next queue
-    sh[t] = v;
-    __syncthreads();
-    for (uint32_t of = 1; of < CELL_BINS; of <<= 1) {
-        uint32_t add = t >= of ? sh[t - of] : 0u;
-        __syncthreads();
-        sh[t] += add;
-        __syncthreads();
-    }
-    offsets[t] = sh[t] - v;           // exclusive
-}
-
-// queue == nullptr: the entries are the slots 0 .. n-1 themselves (ordering of a whole wave);
-// header != nullptr: header[0] receives n (the ordered traversal kernel reads count and list from one pointer)
-__global__ void __launch_bounds__(BLOCK) k_cell_scatter(const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, const uint2 *__restrict__ keyrank,
-                                                        const uint32_t *__restrict__ offsets, uint32_t *__restrict__ sorted, uint32_t *__restrict__ header) {
-    const uint32_t n = *qcount;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    if (header && blockIdx.x == 0 && threadIdx.x == 0) header[0] = n;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += stride) {
-        uint2 kr = keyrank[qi];
-        sorted[offsets[kr.x] + kr.y] = queue ? queue[qi] : qi;
-    }
-}
-
-// Key of a wave's slot for the ordered traversal (B200PT_WAVE_ORDER=1): 4 x 4 x 4 cell of the ray origin and the
-// octant of the ray direction, 512 bins like the hit-point cells above.
-__global__ void __launch_bounds__(BLOCK) k_wave_keys(PathBuf cur, const uint32_t *__restrict__ n_in, CellGrid g, uint2 *__restrict__ keyrank, uint32_t *__restrict__ hist) {
-    const uint32_t n = *n_in;
-    const uint32_t lane_id = threadIdx.x & 31u;
-    const uint32_t warp_stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
-        uint32_t i = base + lane_id;
-        bool valid = i < n;
-        uint32_t key = 0xffffffffu;
-        if (valid) {
-            float4 o = cur.ray_o[i], d = cur.ray_d[i];
-            int cx = (int) ((o.x - g.lo.x) * (0.5f * g.scale.x)), cy = (int) ((o.y - g.lo.y) * (0.5f * g.scale.y)), cz = (int) ((o.z - g.lo.z) * (0.5f * g.scale.z));
-            cx = min(CELL_AXIS / 2 - 1, max(0, cx)); cy = min(CELL_AXIS / 2 - 1, max(0, cy)); cz = min(CELL_AXIS / 2 - 1, max(0, cz));
-            uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-            key = (uint32_t) (((cz * (CELL_AXIS / 2) + cy) * (CELL_AXIS / 2) + cx) * 8) + oct;
-        }
-        uint32_t peers = __match_any_sync(0xffffffffu, key);
-        uint32_t leader = __ffs(peers) - 1, first = 0;
-        if (valid && lane_id == leader) first = atomicAdd(&hist[key], (uint32_t) __popc(peers));
-        first = __shfl_sync(0xffffffffu, first, leader);
-        if (valid) keyrank[i] = make_uint2(key, first + __popc(peers & ((1u << lane_id) - 1u)));
-    }
-}
-
-// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
-void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount, const CellGrid &g, uint2 *keyrank,
-                       uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st) {
-    k_cell_keys<<<grid, BLOCK, 0, st>>>(cur, hit, queue, qcount, g, keyrank, hist);
-    k_cell_scan<<<1, CELL_BINS, 0, st>>>(hist, offsets);
-    k_cell_scatter<<<grid, BLOCK, 0, st>>>(queue, qcount, keyrank, offsets, sorted, nullptr);
-}
-
-// order_buf[0] = number of slots of the wave, order_buf[4 ..] = the slots sorted by (origin cell, direction octant)
-void launch_wave_order(PathBuf cur, const uint32_t *n_in, const CellGrid &g, uint2 *keyrank, uint32_t *hist, uint32_t *offsets, uint32_t *order_buf,
-                       int grid, cudaStream_t st) {
-    k_wave_keys<<<grid, BLOCK, 0, st>>>(cur, n_in, g, keyrank, hist);
-    k_cell_scan<<<1, CELL_BINS, 0, st>>>(hist, offsets);
-    k_cell_scatter<<<grid, BLOCK, 0, st>>>(nullptr, n_in, keyrank, offsets, order_buf + 4, order_buf);
-}
-
 void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, PathBuf buf, const float4 *adj_dL_lane,
                      const float4 *adj_L_lane, int grid, cudaStream_t st) {
     k_generate<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, buf, adj_dL_lane, adj_L_lane);
@@ -1253,34 +1295,19 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
-    if (L.dynamic_fetch && (L.wide || (L.ordered && !first))) {
-        // experimental variants. Wide walk: the kernel's scene copy points to the Bvh4Node array (counted in 64-byte
-        // units). Ordered: n_in is the header of the wave's order list (launch_wave_order).
-        DevScene scw = sc; uint32_t nsm = L.n_smem_nodes; size_t smem = L.smem_trace;
-        if (L.wide) { scw.nodes = L.nodes4; scw.n_nodes = L.n_nodes4_units; nsm = L.n_smem_nodes_w; smem = L.smem_trace_w; }
-        const bool allw = nsm == scw.n_nodes && L.n_smem_tris == sc.n_tris;
-#define LAUNCH_X(F, A, P, W, O, CTR) k_trace_dyn<F, A, P, W, O><<<L.grid, BLOCK, smem + L.smem_tables, st>>>(scw, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, nsm, L.n_smem_tris, L.refill_idle)
-#define LAUNCH_XA(F, P, W, O, CTR) { if (allw) LAUNCH_X(F, true, P, W, O, CTR); else LAUNCH_X(F, false, P, W, O, CTR); }
-#define LAUNCH_XP(W, O) { if (L.split_phases) { LAUNCH_XA(false, 1, W, O, 5) LAUNCH_XA(false, 2, W, O, 7) } else LAUNCH_XA(false, 0, W, O, 5) }
-        if (first) LAUNCH_XA(true, 0, true, false, 5)          // only reached with L.wide
-        else if (L.wide && L.ordered) LAUNCH_XP(true, true)
-        else if (L.wide) LAUNCH_XP(true, false)
-        else LAUNCH_XP(false, true)
-#undef LAUNCH_XP
-#undef LAUNCH_XA
-#undef LAUNCH_X
+    if (L.dynamic_fetch && L.pair_queue) {
+#define LAUNCH_Q(F, A, M) k_trace_queue<F, A, M><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
+#define LAUNCH_QM(F, A) { if (L.queue_minb == 4) LAUNCH_Q(F, A, 4); else LAUNCH_Q(F, A, 5); }
+        if (first) { if (all) LAUNCH_QM(true, true) else LAUNCH_QM(true, false) }
+        else { if (all) LAUNCH_QM(false, true) else LAUNCH_QM(false, false) }
+#undef LAUNCH_QM
+#undef LAUNCH_Q
         return;
     }
     if (L.dynamic_fetch) {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
-#define LAUNCH_DYN_PHASE(A, P, CTR) k_trace_dyn<false, A, P><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + CTR, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
         if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
-        else if (L.split_phases) {      // experimental: shadow rays, then path rays (work counters 5 and 7 of the bounce's block)
-            if (all) { LAUNCH_DYN_PHASE(true, 1, 5); LAUNCH_DYN_PHASE(true, 2, 7); }
-            else { LAUNCH_DYN_PHASE(false, 1, 5); LAUNCH_DYN_PHASE(false, 2, 7); }
-        }
         else { if (all) LAUNCH_DYN(false, true); else LAUNCH_DYN(false, false); }
-#undef LAUNCH_DYN_PHASE
 #undef LAUNCH_DYN
         return;
     }
@@ -1337,12 +1364,8 @@ void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *ou
     k_env_query<<<(int) ((n + 127) / 128), 128, 0, st>>>(sc, n, in, out);
 }
 
-static bool g_splat_fold = false;     // experimental folding reduction of the gaussian splat (B200PT_SPLAT_FOLD=1), process-wide
-void set_splat_fold(bool on) { g_splat_fold = on; }
-
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st) {
     if (sc.rfilter == B200PT_RFILTER_BOX) k_splat_box<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
-    else if (g_splat_fold) k_splat_gauss<false, true><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
     else k_splat_gauss<false><<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, lane_result, film);
 }
 
@@ -1391,22 +1414,9 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<true, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_dyn<false, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-#define PT_ATTR_ORD(A, P, W) cudaFuncSetAttribute(k_trace_dyn<false, A, P, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    PT_ATTR_ORD(true, 0, false) PT_ATTR_ORD(false, 0, false) PT_ATTR_ORD(true, 1, false) PT_ATTR_ORD(false, 1, false) PT_ATTR_ORD(true, 2, false) PT_ATTR_ORD(false, 2, false)
-    PT_ATTR_ORD(true, 0, true) PT_ATTR_ORD(false, 0, true) PT_ATTR_ORD(true, 1, true) PT_ATTR_ORD(false, 1, true) PT_ATTR_ORD(true, 2, true) PT_ATTR_ORD(false, 2, true)
-#undef PT_ATTR_ORD
+#define PT_ATTR_Q(F, A) cudaFuncSetAttribute(k_trace_queue<F, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes); cudaFuncSetAttribute(k_trace_queue<F, A, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    PT_ATTR_Q(true, true) PT_ATTR_Q(false, true) PT_ATTR_Q(true, false) PT_ATTR_Q(false, false)
+#undef PT_ATTR_Q
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

@@ -56,15 +56,9 @@ constexpr int BLOCK = 256;
 constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 registers -> 4 blocks / SM
 
 struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
-                bool split_phases;   // experimental (B200PT_TRACE_PHASES=1): shadow rays and path rays of a wave as two launches
-                // experimental (B200PT_BVH_WIDE=1): 4-wide walk over the Bvh4Node array, sizes in 64-byte units
-                bool wide; const float4 *nodes4; uint32_t n_nodes4_units, n_smem_nodes_w; size_t smem_trace_w;
-                bool ordered;        // experimental (B200PT_WAVE_ORDER=1): the traversal walks the wave's order list (n_in = its header)
+                bool pair_queue;     // traversal kernel: k_trace_queue (warp-wide triangle queue) instead of k_trace_dyn
+                int queue_minb;      // its launch bound: CTAs per SM (4: 64 registers, 5: 48)
 };
-
-// experimental cell ordering of the material queues (kernels.cu: k_cell_keys), off by default
-constexpr int CELL_AXIS = 8, CELL_BINS = CELL_AXIS * CELL_AXIS * CELL_AXIS;
-struct CellGrid { float3 lo, scale; };     // cell = clamp(int((p - lo) * scale), 0, CELL_AXIS - 1) per axis
 
 // counters in the stats buffer
 enum { ST_BOUNCES = 0, ST_SHADOW = 1, ST_CLOSEST = 2, ST_COUNT = 8 };
@@ -77,10 +71,6 @@ void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cu
                   const uint32_t *qcount, PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st);
 void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
                       float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st);
-void launch_cell_order(PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount, const CellGrid &g, uint2 *keyrank,
-                       uint32_t *hist, uint32_t *offsets, uint32_t *sorted, int grid, cudaStream_t st);
-void launch_wave_order(PathBuf cur, const uint32_t *n_in, const CellGrid &g, uint2 *keyrank, uint32_t *hist, uint32_t *offsets, uint32_t *order_buf,
-                       int grid, cudaStream_t st);
 void launch_flush(PathBuf cur, Queues q, const uint32_t *qcounts, float4 *lane_result, int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
@@ -91,7 +81,6 @@ void launch_develop(const DevScene &sc, const float *film, float *out, cudaStrea
 void launch_ray_intersect(const DevScene &sc, uint32_t n, const float *rays, float *t, float *uv, uint32_t *prim, int32_t *shape, const Launch &L, cudaStream_t st);
 void launch_ray_test(const DevScene &sc, uint32_t n, const float *rays, uint8_t *hit, const Launch &L, cudaStream_t st);
 void set_trace_smem_attr(size_t bytes);
-void set_splat_fold(bool on);     // experimental (B200PT_SPLAT_FOLD=1): folding reduction in k_splat_gauss
 void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, const float *in, float *out, cudaStream_t st);
 
 } // namespace pt

@@ -303,13 +303,13 @@ def register(mi):
             self._cache = {}
 
         def _host_scene(self, scene, sensor):
-            # keyed by the scene object itself (weak reference: an id() can be reused after the scene is collected)
-            import weakref
+            # the entry holds the scene object itself (mi.Scene has no weak references): its id() cannot be reused
+            # by another scene while the entry lives
             key = (id(scene), sensor if isinstance(sensor, int) else id(sensor))
             ent = self._cache.get(key)
-            if ent is None or ent[1]() is not scene:
+            if ent is None or ent[1] is not scene:
                 host = extract_scene(mi, scene, sensor)
-                ent = (host, weakref.ref(scene), mi.traverse(scene))     # the parameter map is built once per scene
+                ent = (host, scene, mi.traverse(scene))     # the parameter map is built once per scene
                 self._cache[key] = ent
             self._params_of = ent[2]
             return ent[0]

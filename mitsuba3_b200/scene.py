@@ -757,8 +757,8 @@ def cornell_box_heightfield(n: int = 64, **kw) -> dict:
 
 
 # ---------------------------------------------------------------------------
-# Synthetic stand-in for BASELINE.json configs[3] ("matpreview scene: principled BSDF + envmap");
-# the real asset (resources/data/scenes/matpreview) is not in the reference tree.
+# Synthetic scene of the flavour of BASELINE.json configs[3] (principled BSDF + envmap), used by unit tests; the
+# reference's real matpreview asset is loaded by matpreview_scene() further down.
 # ---------------------------------------------------------------------------
 def uv_sphere_mesh(n_theta: int = 128, n_phi: int = 256, radius: float = 1.0, center=(0.0, 0.0, 0.0)) -> dict:
     """Latitude-longitude sphere with smooth normals and texture coordinates:
@@ -821,3 +821,36 @@ def matpreview_like(n_theta: int = 256, n_phi: int = 512, env_res=(1024, 512)) -
     d["small-sphere"] = s2
     d["sky"] = {"type": "envmap", "bitmap": synthetic_sky(*env_res), "scale": 1.0, "to_world": T().rotate([0, 1, 0], 25)}
     return d
+
+
+def matpreview_scene(path: str | None = None) -> dict:
+    """BASELINE.json configs[3]: the reference's own asset resources/data/scenes/matpreview, from the arrays that
+    tests/golden/gen_matpreview.py extracted with the unmodified reference (three meshes as loaded, envmap.exr as linear
+    float32 RGB, envmap / sensor transforms). `bsdf-matpreview` is the principled model of SURVEY.md 8(d)
+    (base_color .94/.271/.361, roughness .3, metallic 0, specular .5); everything else follows matpreview.xml."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "matpreview_scene.npz")
+    z = np.load(path, allow_pickle=False)
+
+    def mesh(sid, bsdf):
+        m = {"type": "mesh", "positions": z[f"{sid}|positions"], "texcoords": z[f"{sid}|texcoords"], "faces": z[f"{sid}|faces"], "bsdf": {"type": "ref", "id": bsdf}}
+        if bool(z[f"{sid}|has_normals"]):
+            m["normals"] = z[f"{sid}|normals"]
+        return m
+    return {
+        "type": "scene",
+        "integrator": {"type": "path", "max_depth": 8},
+        "sensor": {"type": "perspective", "fov_axis": "smaller", "fov": float(z["sensor_fov"][0]), "near_clip": float(z["sensor_clip"][0]),
+                   "far_clip": float(z["sensor_clip"][1]), "to_world": Transform4f(z["sensor_to_world"]),
+                   "sampler": {"type": "independent", "sample_count": 64},
+                   "film": {"type": "hdrfilm", "width": 683, "height": 512, "pixel_format": "rgb", "rfilter": {"type": "gaussian"}}},
+        "emitter-envmap": {"type": "envmap", "data": z["envmap"], "scale": float(z["envmap_scale"]), "to_world": Transform4f(z["envmap_to_world"])},
+        "bsdf-diffuse": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.18, 0.18, 0.18]}},
+        "bsdf-plane": {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.4, 0.4, 0.4]},
+                                                          "color1": {"type": "rgb", "value": [0.2, 0.2, 0.2]}, "to_uv": [[8, 0, 0], [0, 8, 0], [0, 0, 1]]}},
+        "bsdf-matpreview": {"type": "principled", "base_color": {"type": "rgb", "value": [0.940, 0.271, 0.361]}, "roughness": 0.3, "metallic": 0.0, "specular": 0.5},
+        "shape-plane": mesh("shape-plane", "bsdf-plane"),
+        "shape-matpreview-interior": mesh("shape-matpreview-interior", "bsdf-diffuse"),
+        "shape-matpreview-exterior": mesh("shape-matpreview-exterior", "bsdf-matpreview"),
+    }

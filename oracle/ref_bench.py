@@ -33,11 +33,7 @@ jit = variant.startswith("llvm")
 
 
 def scene_dict(integrator, textured=False):
-    if workload.startswith("matpreview"):
-        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-        from ref_matpreview import matpreview_dict
-        d = matpreview_dict(mi)
-    else:
+    if True:
         d = mi.cornell_box()
         if textured:     # BASELINE.json configs[2]: back wall albedo = 64x64x3 bilinear bitmap
             d["wall-tex"] = {"type": "diffuse", "reflectance": {"type": "bitmap", "bitmap": mi.Bitmap(np.full((64, 64, 3), 0.5, np.float32)),
@@ -53,7 +49,12 @@ def sync(x):
         dr.eval(x); dr.sync_thread()
 
 
-scene = mi.load_dict(scene_dict("path"))
+if workload.startswith("matpreview"):      # the reference's own asset, rebuilt from the committed fixture arrays
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from ref_matpreview import load_matpreview
+    scene = load_matpreview(mi, w, h, spp, max_depth)
+else:
+    scene = mi.load_dict(scene_dict("path"))
 sync(mi.render(scene, spp=1))                    # warm-up: thread pool, page-in, (JIT) kernel compilation at this launch size
 if jit:
     sync(mi.render(scene, spp=spp, seed=99))     # the timed launch size compiles / caches its kernel here

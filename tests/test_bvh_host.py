@@ -42,15 +42,6 @@ def load_harness():
     lib.bvh_h_validate.restype = ctypes.c_int
     lib.bvh_h_validate.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     lib.bvh_h_trace.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    for f in (lib.bvh_h_n_nodes4, lib.bvh_h_depth4):
-        f.restype = ctypes.c_uint32
-        f.argtypes = [ctypes.c_void_p]
-    lib.bvh_h_nodes4.restype = ctypes.c_void_p
-    lib.bvh_h_nodes4.argtypes = [ctypes.c_void_p]
-    lib.bvh_h_validate4.restype = ctypes.c_int
-    lib.bvh_h_validate4.argtypes = [ctypes.c_void_p]
-    lib.bvh_h_trace4_ordered.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    lib.bvh_h_trace4.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
@@ -92,38 +83,6 @@ class Tree:
         self.last_steps = steps.value
         return t, prim, n.value
 
-    # ---- 4-wide tree ----
-    @property
-    def n_nodes4(self):
-        return self.lib.bvh_h_n_nodes4(self.h)
-
-    def nodes4(self):
-        raw = (ctypes.c_uint8 * (128 * self.n_nodes4)).from_address(self.lib.bvh_h_nodes4(self.h))
-        return np.frombuffer(raw, np.float32).reshape(-1, 32).copy()
-
-    def validate4(self):
-        return self.lib.bvh_h_validate4(self.h)
-
-    def trace4_ordered(self, rays, any_hit=False, nearest_only=False):
-        """The wide walk with the traversal kernel's node step (near-to-far network, push order, fixed stack)."""
-        rays = np.ascontiguousarray(rays, np.float32)
-        t = np.empty(len(rays), np.float32)
-        prim = np.empty(len(rays), np.uint32)
-        max_sp = ctypes.c_uint32(0)
-        steps = ctypes.c_uint64(0)
-        self.lib.bvh_h_trace4_ordered(self.h, len(rays), rays.ctypes.data, int(any_hit) | (2 if nearest_only else 0), t.ctypes.data, prim.ctypes.data,
-                                      ctypes.byref(max_sp), ctypes.byref(steps))
-        self.last_steps4 = steps.value
-        return t, prim, max_sp.value
-
-    def trace4(self, rays):
-        rays = np.ascontiguousarray(rays, np.float32)
-        t = np.empty(len(rays), np.float32)
-        prim = np.empty(len(rays), np.uint32)
-        n = ctypes.c_uint64(0)
-        steps = ctypes.c_uint64(0)
-        self.lib.bvh_h_trace4(self.h, len(rays), rays.ctypes.data, t.ctypes.data, prim.ctypes.data, ctypes.byref(n), ctypes.byref(steps))
-        return t, prim, n.value, steps.value
 
 
 def random_rays(rng, n, lo, hi, tri):
@@ -190,26 +149,6 @@ def test_invariants_and_walk_equals_brute_force(harness, name):
     assert (p_ref != 0xFFFFFFFF).sum() >= 20                      # the rays do hit something
     if len(tri) >= 1000:
         assert n_tree < n_ref // 10                               # and the tree actually culls
-    # the 4-wide collapse of the same tree: same leaves, same answers, fewer node visits
-    assert tree.validate4() == 0
-    t_w, p_w, n_w, steps4 = tree.trace4(rays)
-    assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
-    # the node step of the traversal kernel (sorting network, push order, fixed stack): same hits, the same
-    # occlusion answers, and the stack stays within the bound api.cu checks before enabling the wide walk
-    t_o, p_o, max_sp = tree.trace4_ordered(rays)
-    assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
-    full_sort_steps = tree.last_steps4
-    t_o, p_o, max_sp = tree.trace4_ordered(rays, nearest_only=True)      # what the kernel does
-    assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
-    assert tree.last_steps4 <= 1.10 * full_sort_steps                    # nearest-first costs a few % of visits (worst: overlapping soup)
-    occl, _, _ = tree.trace4_ordered(rays, any_hit=True, nearest_only=True)
-    assert np.array_equal(occl > 0, p_ref != 0xFFFFFFFF)
-    assert max_sp <= 3 * (tree.lib.bvh_h_depth4(tree.h) + 1) + 1 <= 127
-    tree.trace(rays, brute=False)
-    steps2 = tree.last_steps
-    assert steps4 <= steps2
-    if len(tri) >= 300:
-        assert steps4 < 0.62 * steps2
 
 
 def test_empty_scene_has_a_root_that_is_never_entered(harness):
@@ -219,31 +158,6 @@ def test_empty_scene_has_a_root_that_is_never_entered(harness):
     assert nodes.view(np.int32)[0, 12] == 0x7FFFFFFF and nodes.view(np.int32)[0, 13] == 0x7FFFFFFF
     t, p, _ = tree.trace(np.array([[0, 0, 0, 0, 0, 1, np.inf]], np.float32), brute=False)
     assert np.isinf(t[0]) and p[0] == 0xFFFFFFFF
-
-
-def test_wide_layout(harness):
-    rng = np.random.default_rng(6)
-    tri = soup(rng, 777)
-    tree = Tree(harness, tri)
-    n4 = tree.nodes4()
-    ints = n4.view(np.int32)
-    child = ints[:, 24:28]
-    assert not ints[:, 28:32].any()
-    inner = child[(child >= 0) & (child != 0x7FFFFFFF)]
-    assert np.array_equal(inner, np.arange(1, tree.n_nodes4))      # breadth-first, root = 0
-    lo, hi = n4[:, 0:12].reshape(-1, 3, 4), n4[:, 12:24].reshape(-1, 3, 4)
-    empty = child == 0x7FFFFFFF
-    assert (lo[:, 0][empty] > hi[:, 0][empty]).all() and (lo[:, 0][~empty] <= hi[:, 0][~empty]).all()
-    leaves = ~child[child < 0]
-    assert ((leaves & 7) + 1).sum() == len(tri)
-    # the collapse fills the nodes wherever an inner child was left to open: the top of the tree is full,
-    # only nodes whose children are all leaves stay narrower
-    occupied = (~empty).sum(1)
-    assert occupied[: tree.n_nodes4 // 4].mean() > 3.9 and occupied.mean() > 2.8
-    has_inner = ((child >= 0) & ~empty).any(1)
-    assert (occupied[has_inner] == 4).all()
-    assert tree.n_nodes4 < 0.55 * tree.n_nodes
-    assert tree.lib.bvh_h_depth4(tree.h) <= (tree.lib.bvh_h_depth(tree.h) + 1) // 2 + 3
 
 
 def test_layout_breadth_first_and_leaf_encoding(harness):
@@ -282,10 +196,7 @@ def test_boxes_are_conservative_for_grazing_hits(harness):
     t_tree, p_tree, _ = tree.trace(rays, brute=False)
     t_ref, p_ref, _ = tree.trace(rays, brute=True)
     assert np.array_equal(p_tree, p_ref) and np.array_equal(t_tree, t_ref)
-    t_w, p_w, _, _ = tree.trace4(rays)
-    assert np.array_equal(p_w, p_ref) and np.array_equal(t_w, t_ref)
-    # axis-parallel rays (direction components exactly +0 / -0: the reciprocal is the signed 1e30 of safe_inv),
-    # through the kernel's node step incl. its sign-selected slab test
+    # axis-parallel rays (direction components exactly +0 / -0: the reciprocal is the signed 1e30 of safe_inv)
     n = 1500
     o = rng.uniform(-1.2, 1.2, (n, 3))
     axis = rng.integers(0, 3, n)
@@ -298,6 +209,6 @@ def test_boxes_are_conservative_for_grazing_hits(harness):
     d[axis == 1, 1] = -sign[axis == 1]
     rays = np.concatenate([o, d, np.full((n, 1), np.inf)], 1).astype(np.float32)
     t_ref, p_ref, _ = tree.trace(rays, brute=True)
-    t_o, p_o, _ = tree.trace4_ordered(rays, nearest_only=True)
+    t_o, p_o, _ = tree.trace(rays, brute=False)
     assert np.array_equal(p_o, p_ref) and np.array_equal(t_o, t_ref)
     assert (p_ref != 0xFFFFFFFF).sum() > 200
