@@ -124,13 +124,11 @@ class B200PTError(RuntimeError):
 
 
 def adjoint_covers_slot(bsdf_type: int, flags: int, slot: int) -> bool:
-    """BSDF slots whose parameter derivative the PRB adjoint implements (csrc/api.cu: adjoint_covers_slot).
-    Delta lobes have an exact-zero gradient in detached PRB (prb.py:296), so smooth conductor / dielectric count."""
-    if bsdf_type == BSDF_DIFFUSE:
-        return slot == SLOT_REFLECTANCE
-    if bsdf_type in (BSDF_CONDUCTOR, BSDF_DIELECTRIC):
-        return not (flags & M_ROUGH)
-    return False
+    """BSDF slots whose parameter derivative the PRB adjoint implements (csrc/api.cu: adjoint_covers_slot): all texture
+    slots of all models (delta lobes: an exact zero, prb.py:296) except principled `specular`."""
+    if bsdf_type == BSDF_PRINCIPLED:
+        return slot != SLOT_P_SPECULAR
+    return BSDF_DIFFUSE <= bsdf_type <= BSDF_PLASTIC
 
 
 def load() -> C.CDLL:

@@ -88,15 +88,16 @@ static cudaError_t dev_upload(b200pt_scene *s, const T *host, size_t n, T **out)
     return e;
 }
 
-// BSDF slots whose parameter derivative the PRB adjoint implements (kernels.cu: bsdf_backward). Delta lobes have
-// a zero gradient in detached PRB by construction (prb.py:296: bsdf.eval of a delta lobe is 0), so the smooth
-// conductor / dielectric slots are covered -- by an exact zero.
+// BSDF slots whose parameter derivative the PRB adjoint implements: diffuse reflectance in closed form
+// (kernels.cu: bsdf_backward), every texture slot of the principled, rough conductor, rough dielectric and plastic
+// models through the dual-number evaluation of pt_bsdf_grad.cuh. Delta lobes (smooth conductor / dielectric, the
+// specular component of plastic) have a zero gradient in detached PRB by construction (prb.py:296: bsdf.eval of a delta
+// lobe is 0), so their slots are covered -- by an exact zero. Not covered: principled `specular` (it enters through
+// the index of refraction, which the reference keeps as a non-differentiable float as well).
 static bool adjoint_covers_slot(int32_t type, uint32_t flags, int slot) {
-    switch (type) {
-        case B200PT_BSDF_DIFFUSE: return slot == B200PT_SLOT_REFLECTANCE;
-        case B200PT_BSDF_CONDUCTOR: case B200PT_BSDF_DIELECTRIC: return !(flags & B200PT_M_ROUGH);
-        default: return false;
-    }
+    (void) flags;
+    if (type == B200PT_BSDF_PRINCIPLED) return slot != B200PT_SLOT_P_SPECULAR;
+    return type >= B200PT_BSDF_DIFFUSE && type <= B200PT_BSDF_PLASTIC;
 }
 
 extern "C" {
@@ -373,10 +374,8 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
-    { const char *e = getenv("B200PT_TRACE_QUEUE"); s->launch.pair_queue = e ? atoi(e) != 0 : true; }
-    { const char *e = getenv("B200PT_TRACEQ_MINB"); s->launch.queue_minb = e && atoi(e) == 4 ? 4 : 5; }
-    if (s->launch.pair_queue && s->launch.queue_minb == 4 && !getenv("B200PT_TRACE_BLOCKS_PER_SM")) s->launch.grid = (int) s->n_sm * 4;
-    if (s->launch.pair_queue && s->launch.n_smem_nodes > 256) {          // the warp queues take 14 KiB of the CTA's shared memory
+    { const char *e = getenv("B200PT_TRACE_COOP"); s->launch.coop_leaves = e ? atoi(e) != 0 : true; }
+    if (s->launch.coop_leaves && s->launch.n_smem_nodes > 256) {          // the warp lists take 12 KiB of the CTA's shared memory
         s->launch.n_smem_nodes = 256;
         s->launch.smem_trace = ((size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
     }

@@ -490,37 +490,32 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
 }
 
 // ---------------------------------------------------------------------------
-// k_trace_queue -- persistent dynamic-fetch traversal with a WARP-WIDE TRIANGLE QUEUE (default).
+// k_trace_coop -- k_trace_dyn with WARP-COOPERATIVE LEAF ROUNDS.
 //
-// k_trace_dyn tests a leaf's triangles in the lane that found the leaf: measured on the bench frame the
-// Moeller-Trumbore loop issues 28 % of the kernel's instructions at 7 of 32 threads, and the node loop runs at 16
-// because lanes that hold a leaf wait for the others (profiles/r01_simt_model.md section 1). Here a lane that reaches
-// a leaf only APPENDS (owner lane, triangle) pairs to a queue in shared memory and keeps walking; when 32 pairs are
-// queued the whole warp tests 32 pairs at once, one pair per lane, reading the owner's ray from shared memory.
-// Results go back through a 64-bit atomicMin per owner on the key (t bits << 32 | primitive): for t >= 0 the float
-// bit pattern orders like the value, so the minimum IS the closest hit with ties resolved towards the smaller
-// primitive index -- the rule of the per-lane walk, hence identical hits (order independent). A shadow ray stores
-// key 0 = occluded. The winner of a round writes (u, v). A lane's walk uses its current best t as maxt (refreshed
-// after every triangle phase); between phases it walks on with a slightly stale maxt, which only costs node visits.
-//
-//   node phase   every lane with a live walk: queue <= 2 triangles of its current leaf, then one node step
-//   tri phase    full rounds of 32 pairs (+ the partial rest when no lane walks any more or >= REFILL lanes wait)
-//   retire       walk finished AND all its pairs tested -> same per-slot semantics as k_trace / k_trace_dyn
+// In k_trace_dyn every lane tests the triangles of the leaf it found itself: measured on the bench frame the
+// Moeller-Trumbore loop issues 28 % of the kernel's instructions at 7 of 32 threads (profiles/r01_simt_model.md
+// section 1) -- only the lanes that hold a leaf work, and a lane with two triangles keeps the warp for two passes.
+// Here the walk is unchanged (speculative while-while, one postponed leaf per lane), but when the warp reaches its
+// leaf phase the (owner lane, triangle) pairs of all postponed leaves go to a list in shared memory and the WHOLE warp
+// tests them, one pair per lane -- idle lanes included -- reading the owner's ray from shared memory. A hit returns
+// through a 64-bit atomicMin per owner on the key (t bits << 32 | primitive): for t >= 0 the float bit pattern orders
+// like the value, so the minimum is the closest hit with ties resolved towards the smaller primitive index, the rule
+// of the per-lane loop -- identical hits. A shadow ray stores key 0 = occluded. The lane whose key is the round's
+// minimum writes (u, v). No test is deferred: every lane has its new maxt before it walks on.
 //
 // Entry = any-hit flag << 31 | owner lane << 26 | triangle index (api.cu limits scenes to 2^26 triangles).
 // ---------------------------------------------------------------------------
-constexpr int TQ_RING = 128;     // ring capacity; at most 31 + 2 * 32 = 95 entries are ever queued
 struct __align__(16) WarpTrace {
     float o[3][32], d[3][32];         // ray of every lane of the warp
     unsigned long long best[32];      // (bits of the closest t, or of maxt) << 32 | primitive (0xffffffff: none); 0: occluded
     float2 uv[32];
-    uint32_t queue[TQ_RING];
+    uint32_t pairs[64];               // <= 2 triangles per postponed leaf and round
 };
 
-template <bool FIRST, bool SMEM_ALL, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
-                                                       const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
-                                                       float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
+template <bool FIRST, bool SMEM_ALL>
+__global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_coop(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
+                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
+                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ WarpTrace s_warp[BLOCK / 32];
@@ -543,11 +538,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_consta
     uint32_t slot = 0, flags = 0;
     float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
     float maxt = 0.f;
-    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL;
-    uint32_t leaf_first = 0, leaf_left = 0;      // triangles of the current leaf that are not queued yet
-    uint32_t my_last = 0;                        // queue position (monotonic count) behind this lane's last entry
-    // warp-uniform queue state
-    uint32_t q_head = 0, q_count = 0, q_done = 0;      // ring start, entries queued, entries tested since the kernel started
+    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
+    uint32_t leaf_first = 0, leaf_left = 0;      // triangles of the postponed leaf that are not tested yet
     bool exhausted = false;           // the global pool is empty
 
     auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
@@ -556,7 +548,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_consta
         ws.o[0][lane_id] = o.x; ws.o[1][lane_id] = o.y; ws.o[2][lane_id] = o.z;
         ws.d[0][lane_id] = d.x; ws.d[1][lane_id] = d.y; ws.d[2][lane_id] = d.z;
         ws.best[lane_id] = ((unsigned long long) __float_as_uint(rmaxt) << 32) | 0xffffffffull;
-        stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf_left = 0; my_last = q_done;
+        stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf = 0; leaf_left = 0;
     };
 
     while (true) {
@@ -585,33 +577,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_consta
             }
         }
         if (!__any_sync(0xffffffffu, kind != 0)) break;
-        __syncwarp();                 // the rays written by start_ray are visible to the whole warp
 
-        // ---- node phase (warp-synchronous loop) --------------------------------------------------
-        bool drain = false;
+        // ---- traverse until the warp wants to refill ---------------------------------------------------
         while (true) {
-            const bool walking = kind != 0 && (node != TRAV_SENTINEL || leaf_left != 0);
-            const uint32_t wm = __ballot_sync(0xffffffffu, walking);
-            if (wm == 0) { drain = true; break; }
-            if (q_count >= 32) break;
-            if (!exhausted && __popc(wm) <= 32 - DYN_REFILL_IDLE) { drain = true; break; }     // enough lanes wait: test what is queued, retire, refill
-            // (a) queue up to two triangles of the leaf this lane holds
-            const uint32_t cpush = walking ? min(leaf_left, 2u) : 0u;
-            const uint32_t m1 = __ballot_sync(0xffffffffu, cpush >= 1), m2 = __ballot_sync(0xffffffffu, cpush == 2);
-            if (m1) {
-                if (cpush) {
-                    const uint32_t off = q_count + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
-                    const uint32_t tag = (kind == 1 ? 0x80000000u : 0u) | (lane_id << 26);
-                    ws.queue[(q_head + off) & (TQ_RING - 1)] = tag | leaf_first;
-                    if (cpush == 2) ws.queue[(q_head + off + 1) & (TQ_RING - 1)] = tag | (leaf_first + 1);
-                    leaf_first += cpush; leaf_left -= cpush;
-                    my_last = q_done + off + cpush;
-                }
-                q_count += __popc(m1) + __popc(m2);
-            }
-            // (b) one node step
-            if (walking && leaf_left == 0) {
-                if (node >= 0 && node != TRAV_SENTINEL) {
+            // node phase: every walking lane steps until it holds a leaf (speculatively on, until all of them do)
+            if (kind != 0 && node != TRAV_SENTINEL) {
+                bool searching = leaf >= 0;
+                while (node >= 0 && node != TRAV_SENTINEL) {
                     float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
                     int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                     float tl, tr;
@@ -626,88 +598,103 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_trace_queue(const __grid_consta
                             stack[++sp] = far;
                         }
                     }
-                }
-                if (node < 0) {       // a leaf (the sentinel is positive): take it and continue with the next node of the stack
-                    const uint32_t enc = (uint32_t) ~node;
-                    leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u;
-                    node = stack[sp--];
+                    if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }   // postpone the first leaf
+                    if (!__any_sync(__activemask(), searching)) break;
                 }
             }
-        }
-        __syncwarp();                 // queue entries are visible
-
-        // ---- triangle phase: one (ray, triangle) pair per lane ------------------------------------
-        {
-            uint32_t todo = drain ? q_count : (q_count & ~31u);
-            while (todo) {
-                const uint32_t nr = min(todo, 32u);
-                bool won = false; unsigned long long key = 0; uint32_t owner = 0; float u = 0.f, v = 0.f;
-                if (lane_id < nr) {
-                    const uint32_t e = ws.queue[(q_head + lane_id) & (TQ_RING - 1)];
-                    owner = (e >> 26) & 31u;
-                    const uint32_t tri = e & 0x03ffffffu;
-                    const unsigned long long b = ws.best[owner];
-                    if (b != 0ull) {
-                        const float mt = __uint_as_float((uint32_t) (b >> 32));
-                        const float3 ro = V(ws.o[0][owner], ws.o[1][owner], ws.o[2][owner]), rd = V(ws.d[0][owner], ws.d[1][owner], ws.d[2][owner]);
-                        float4 ta = ld_tri<SMEM_ALL>(c, tri, 0), tb = ld_tri<SMEM_ALL>(c, tri, 1), te = ld_tri<SMEM_ALL>(c, tri, 2);
-                        float t;
-                        if (moeller_trumbore(ro, rd, mt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
-                            // t + 0: a hit at t = -0 gets the bit pattern of +0, so that the unsigned order of the keys is the order of t
-                            key = (e >> 31) ? 0ull : (((unsigned long long) __float_as_uint(t + 0.f) << 32) | __float_as_uint(ta.w));
-                            const unsigned long long old = atomicMin(&ws.best[owner], key);
-                            won = !(e >> 31) && key < old;
+            __syncwarp();
+            // leaf phase: the pairs of all postponed leaves, one pair per lane of the WHOLE warp
+            if (kind != 0 && leaf < 0 && leaf_left == 0) { const uint32_t enc = (uint32_t) ~leaf; leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u; }
+            while (true) {
+                const uint32_t cpush = min(leaf_left, 2u);
+                const uint32_t m1 = __ballot_sync(0xffffffffu, cpush >= 1);
+                if (m1 == 0) break;
+                const uint32_t m2 = __ballot_sync(0xffffffffu, cpush == 2);
+                if (cpush) {
+                    const uint32_t off = __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
+                    const uint32_t tag = (kind == 1 ? 0x80000000u : 0u) | (lane_id << 26);
+                    ws.pairs[off] = tag | leaf_first;
+                    if (cpush == 2) ws.pairs[off + 1] = tag | (leaf_first + 1);
+                    leaf_first += cpush; leaf_left -= cpush;
+                }
+                const uint32_t total = __popc(m1) + __popc(m2);
+                __syncwarp();
+                for (uint32_t base = 0; base < total; base += 32) {
+                    bool won = false; unsigned long long key = 0; uint32_t owner = 0; float u = 0.f, v = 0.f;
+                    if (base + lane_id < total) {
+                        const uint32_t e = ws.pairs[base + lane_id];
+                        owner = (e >> 26) & 31u;
+                        const uint32_t tri = e & 0x03ffffffu;
+                        const unsigned long long b = ws.best[owner];
+                        if (b != 0ull) {
+                            const float mt = __uint_as_float((uint32_t) (b >> 32));
+                            const float3 ro = V(ws.o[0][owner], ws.o[1][owner], ws.o[2][owner]), rd = V(ws.d[0][owner], ws.d[1][owner], ws.d[2][owner]);
+                            float4 ta = ld_tri<SMEM_ALL>(c, tri, 0), tb = ld_tri<SMEM_ALL>(c, tri, 1), te = ld_tri<SMEM_ALL>(c, tri, 2);
+                            float t;
+                            if (moeller_trumbore(ro, rd, mt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
+                                // t + 0: a hit at t = -0 gets the bit pattern of +0, so that the unsigned order of the keys is the order of t
+                                key = (e >> 31) ? 0ull : (((unsigned long long) __float_as_uint(t + 0.f) << 32) | __float_as_uint(ta.w));
+                                const unsigned long long old = atomicMin(&ws.best[owner], key);
+                                won = !(e >> 31) && key < old;
+                            }
                         }
                     }
+                    __syncwarp();
+                    if (won && ws.best[owner] == key) ws.uv[owner] = make_float2(u, v);     // the round's closest hit of that ray
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (won && ws.best[owner] == key) ws.uv[owner] = make_float2(u, v);     // the round's closest hit of that ray
-                __syncwarp();
-                q_head = (q_head + nr) & (TQ_RING - 1); q_count -= nr; q_done += nr; todo -= nr;
+                // owners: new maxt / occlusion, next postponed leaf
+                if (kind != 0 && leaf < 0 && leaf_left == 0) {
+                    const unsigned long long b = ws.best[lane_id];
+                    if (kind == 1) { if (b == 0ull) { node = TRAV_SENTINEL; leaf = 0; } }     // any-hit: stop at the first occluder
+                    else maxt = __uint_as_float((uint32_t) (b >> 32));
+                    if (leaf < 0) {
+                        leaf = node;
+                        if (node < 0) { node = stack[sp--]; const uint32_t enc = (uint32_t) ~leaf; leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u; }
+                    }
+                }
             }
+            // dynamic fetch: leave when too few lanes of the warp are still walking, or none is
+            const uint32_t wm = __ballot_sync(0xffffffffu, kind != 0 && node != TRAV_SENTINEL);
+            if (wm == 0 || (!exhausted && __popc(wm) < 32 - DYN_REFILL_IDLE)) break;
         }
 
-        // ---- refresh maxt / occlusion of the walking lanes, retire finished rays -------------------------
+        // ---- retire finished rays -----------------------------------------------------------
         int mytype = -1;
-        if (kind != 0) {
+        if (kind != 0 && node == TRAV_SENTINEL) {
             const unsigned long long b = ws.best[lane_id];
-            if (kind == 1) { if (b == 0ull) { node = TRAV_SENTINEL; leaf_left = 0; } }     // any-hit: stop at the first occluder
-            else maxt = __uint_as_float((uint32_t) (b >> 32));
-            const bool done = node == TRAV_SENTINEL && leaf_left == 0 && (int32_t) (q_done - my_last) >= 0;
-            if (done) {
-                if (kind == 1) {
-                    if (b != 0ull) {
-                        float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
-                        res.x += sd.w; res.y += cc.x; res.z += cc.y;
-                        cur.result[slot] = res;
-                    }
-                    if (flags & PF_ALIVE) {
-                        float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
-                        kind = 2; n_closest++;
-                        start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
-                    } else {
-                        lane_result[cur.rng[slot].w] = cur.result[slot];
-                        kind = 0;
-                    }
+            if (kind == 1) {
+                if (b != 0ull) {
+                    float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
+                    res.x += sd.w; res.y += cc.x; res.z += cc.y;
+                    cur.result[slot] = res;
+                }
+                if (flags & PF_ALIVE) {
+                    float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
+                    kind = 2; n_closest++;
+                    start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
                 } else {
-                    const uint32_t prim = (uint32_t) b;
-                    const bool found = prim != 0xffffffffu;
-                    const float ht = __uint_as_float((uint32_t) (b >> 32));
-                    const float2 huv = ws.uv[lane_id];
-                    if (FIRST && cfg.hide_emitters && found && sc.shapes[sc.prim_verts[prim].w].emitter >= 0) {
-                        // skip_area_emitters (integrator.cpp:96-123)
-                        SurfaceInteraction si = compute_si(sc, ht, huv.x, huv.y, prim, d);
-                        Ray r = spawn_ray(si.p, si.n, d);
-                        cur.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt);
-                        start_ray(r.o, d, r.maxt);
-                    } else {
-                        if (found) {
-                            hit_out[slot] = make_float4(ht, huv.x, huv.y, __uint_as_float(prim));
-                            mytype = sc.bsdfs[sc.shapes[sc.prim_verts[prim].w].bsdf].type;
-                        } else if (sc.env_type >= 0) mytype = Q_ENV;     // the ray left the scene: environment emitter (k_shade_env)
-                        else lane_result[cur.rng[slot].w] = cur.result[slot];
-                        kind = 0;
-                    }
+                    lane_result[cur.rng[slot].w] = cur.result[slot];
+                    kind = 0;
+                }
+            } else {
+                const uint32_t prim = (uint32_t) b;
+                const bool found = prim != 0xffffffffu;
+                const float ht = __uint_as_float((uint32_t) (b >> 32));
+                const float2 huv = ws.uv[lane_id];
+                if (FIRST && cfg.hide_emitters && found && sc.shapes[sc.prim_verts[prim].w].emitter >= 0) {
+                    // skip_area_emitters (integrator.cpp:96-123)
+                    SurfaceInteraction si = compute_si(sc, ht, huv.x, huv.y, prim, d);
+                    Ray r = spawn_ray(si.p, si.n, d);
+                    cur.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt);
+                    start_ray(r.o, d, r.maxt);
+                } else {
+                    if (found) {
+                        hit_out[slot] = make_float4(ht, huv.x, huv.y, __uint_as_float(prim));
+                        mytype = sc.bsdfs[sc.shapes[sc.prim_verts[prim].w].bsdf].type;
+                    } else if (sc.env_type >= 0) mytype = Q_ENV;     // the ray left the scene: environment emitter (k_shade_env)
+                    else lane_result[cur.rng[slot].w] = cur.result[slot];
+                    kind = 0;
                 }
             }
         }
@@ -854,6 +841,10 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
         // gradient scatter requests of this vertex (adjoint)
         int32_t gt0 = -1, gt1 = -1, gt2 = -1; float2 guv0 = make_float2(0.f, 0.f), guv1 = guv0, guv2 = guv0;
         float3 gv0 = V(0.f, 0.f, 0.f), gv1 = gv0, gv2 = gv0;
+        // non-diffuse models: the BSDF-parameter derivatives of this vertex are evaluated slot by slot at the converged
+        // point below (pt_bsdf_grad.cuh); what they need is kept here
+        int32_t pg_bsdf = -1; bool pg_dir = false, pg_ind = false;
+        float3 pg_wi = V(0.f, 0.f, 1.f), pg_wo_em = pg_wi, pg_wo_s = pg_wi, pg_adir = V(0.f, 0.f, 0.f), pg_aind = pg_adir;
         if (valid) {
             n_bounces++;
             uint32_t slot = __ldg(&queue[qi]);
@@ -943,7 +934,29 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                     L = (L - Le) - Lr_dir;                                            // prb.py:227
                     float3 g_dir = active_em ? dL * ((beta_vertex * mis_em) * em_weight) : V(0.f, 0.f, 0.f);
                     float3 g_ind = active ? dL * L : V(0.f, 0.f, 0.f);
-                    gv1 = bsdf_backward<TYPE>(sc, bsdf, si.uv, si.wi, wo, br.bs.wo, g_dir, g_ind, gt1); guv1 = si.uv;
+                    guv1 = si.uv;
+                    if (TYPE == B200PT_BSDF_DIFFUSE) gv1 = bsdf_backward<TYPE>(sc, bsdf, si.uv, si.wi, wo, br.bs.wo, g_dir, g_ind, gt1);
+                    else {
+                        pg_bsdf = sh.bsdf; pg_dir = active_em; pg_ind = active; pg_adir = g_dir; pg_aind = g_ind;
+                        pg_wi = si.wi; pg_wo_em = wo; pg_wo_s = br.bs.wo;
+                        if (bsdf.twosided && si.wi.z < 0.f) { pg_wi.z = -pg_wi.z; pg_wo_em.z = -pg_wo_em.z; pg_wo_s.z = -pg_wo_s.z; }
+                        if (fwd) {
+                            // forward mode (dL = 1, so a_dir / a_ind are per-channel coefficients): d(radiance) of this vertex
+                            // = sum over parameter channels of coefficient x the parameter's tangent at this texture position
+                            for (int k = 0; k < B200PT_MAX_SLOTS; ++k) {
+                                int32_t pt = bsdf_grad_slot(sc, bsdf, k);
+                                if (pt < 0) continue;
+                                const int nch = sc.textures[pt].channels;
+                                for (int ch = 0; ch < nch; ++ch) {
+                                    float3 cf = bsdf_param_coeff<TYPE>(sc, bsdf, si.uv, pg_wi, pg_wo_em, pg_wo_s, pg_adir, pg_aind, pg_dir, pg_ind, pt, ch);
+                                    float3 e = V(ch == 0 ? 1.f : 0.f, ch == 1 ? 1.f : 0.f, ch == 2 ? 1.f : 0.f);
+                                    float3 td = tangent_dot(sc, pt, si.uv, e);
+                                    result = result + cf * (nch == 1 ? td.x : (ch == 0 ? td.x : ch == 1 ? td.y : td.z));
+                                }
+                            }
+                            pg_bsdf = -1;
+                        }
+                    }
                     if (active_em) {
                         // emitter radiance inside em_weight = radiance / pdf (area.cpp:161, envmap.cpp:374-377;
                         // the sampling density is detached); envmap: rad = scale * sum_taps w * data[texel]
@@ -984,6 +997,25 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
             warp_scatter3(sc, gt0, guv0, gv0);
             warp_scatter3(sc, gt1, guv1, gv1);
             warp_scatter3(sc, gt2, guv2, gv2);
+            if (TYPE != B200PT_BSDF_DIFFUSE && __any_sync(0xffffffffu, pg_bsdf >= 0)) {
+                // the lanes of a material queue may hold different BSDFs of this model: the slot loop is uniform, a lane
+                // without a differentiable texture in slot k passes -1
+                for (int k = 0; k < B200PT_MAX_SLOTS; ++k) {
+                    const int32_t pt = pg_bsdf >= 0 ? bsdf_grad_slot(sc, sc.bsdfs[pg_bsdf >= 0 ? pg_bsdf : 0], k) : -1;
+                    if (!__any_sync(0xffffffffu, pt >= 0)) continue;
+                    float3 g = V(0.f, 0.f, 0.f);
+                    if (pt >= 0) {
+                        const DevBsdf &pb = sc.bsdfs[pg_bsdf];
+                        const int nch = sc.textures[pt].channels;
+                        for (int ch = 0; ch < nch; ++ch) {
+                            float3 cf = bsdf_param_coeff<TYPE>(sc, pb, guv1, pg_wi, pg_wo_em, pg_wo_s, pg_adir, pg_aind, pg_dir, pg_ind, pt, ch);
+                            float sum = cf.x + cf.y + cf.z;      // a_dir / a_ind carry dL per colour channel
+                            if (ch == 0) g.x = sum; else if (ch == 1) g.y = sum; else g.z = sum;
+                        }
+                    }
+                    warp_scatter3(sc, pt, guv1, g);
+                }
+            }
         }
         // compaction: survivors get consecutive slots of the next buffer (one atomic per warp)
         uint32_t m = __ballot_sync(0xffffffffu, write_next);
@@ -1295,12 +1327,10 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
-    if (L.dynamic_fetch && L.pair_queue) {
-#define LAUNCH_Q(F, A, M) k_trace_queue<F, A, M><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
-#define LAUNCH_QM(F, A) { if (L.queue_minb == 4) LAUNCH_Q(F, A, 4); else LAUNCH_Q(F, A, 5); }
-        if (first) { if (all) LAUNCH_QM(true, true) else LAUNCH_QM(true, false) }
-        else { if (all) LAUNCH_QM(false, true) else LAUNCH_QM(false, false) }
-#undef LAUNCH_QM
+    if (L.dynamic_fetch && L.coop_leaves) {
+#define LAUNCH_Q(F, A) k_trace_coop<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
+        if (first) { if (all) LAUNCH_Q(true, true); else LAUNCH_Q(true, false); }
+        else { if (all) LAUNCH_Q(false, true); else LAUNCH_Q(false, false); }
 #undef LAUNCH_Q
         return;
     }
@@ -1414,9 +1444,10 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-#define PT_ATTR_Q(F, A) cudaFuncSetAttribute(k_trace_queue<F, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes); cudaFuncSetAttribute(k_trace_queue<F, A, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    PT_ATTR_Q(true, true) PT_ATTR_Q(false, true) PT_ATTR_Q(true, false) PT_ATTR_Q(false, false)
-#undef PT_ATTR_Q
+    cudaFuncSetAttribute(k_trace_coop<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_coop<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_coop<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_coop<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

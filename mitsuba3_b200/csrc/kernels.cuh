@@ -56,8 +56,7 @@ constexpr int BLOCK = 256;
 constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 registers -> 4 blocks / SM
 
 struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
-                bool pair_queue;     // traversal kernel: k_trace_queue (warp-wide triangle queue) instead of k_trace_dyn
-                int queue_minb;      // its launch bound: CTAs per SM (4: 64 registers, 5: 48)
+                bool coop_leaves;    // traversal kernel: k_trace_coop (warp-cooperative leaf rounds) instead of k_trace_dyn
 };
 
 // counters in the stats buffer

@@ -430,6 +430,7 @@ PT_DEV uint32_t bsdf_flags(const DevBsdf &b) {
 
 #include "pt_principled.cuh"
 #include "pt_rough.cuh"
+#include "pt_bsdf_grad.cuh"
 
 namespace pt {
 
