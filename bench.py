@@ -240,7 +240,12 @@ def e2e_mi_render(workload, steps, device):
                            env=env, capture_output=True, text=True, timeout=900)
         return json.loads(r.stdout.strip().splitlines()[-1])
     except Exception as e:      # noqa: BLE001
-        return {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        tail = ""
+        try:
+            tail = (r.stdout[-300:] + " | " + r.stderr[-500:]).replace("\n", " ")
+        except Exception:
+            pass
+        return {"error": f"{type(e).__name__}: {str(e)[:160]}", "output_tail": tail}
 
 
 def main():

@@ -242,12 +242,26 @@ B200PT_API uint32_t    b200pt_abi_version(void);
 B200PT_API const char *b200pt_last_error(void);
 /* Number of visible CUDA devices (0 without a driver/GPU). */
 B200PT_API int         b200pt_device_count(void);
+/* Devices this process renders on. The multi-GPU layout is one process per GPU: `ids` is the list of
+ * CUDA ordinals of the job on this node and `b200pt_scene_create(desc, B200PT_DEVICE_AUTO, ..)` picks
+ * ids[LOCAL_RANK % n] (LOCAL_RANK from the environment, 0 if unset) -- what `jit_set_device` / `cuda_ad_rgb`'s device
+ * selection is to the reference (drjit-core jit.h: jit_cuda_set_device). n = 0 restores the default (device 0). */
+#define B200PT_DEVICE_AUTO (-1)
+B200PT_API b200pt_status b200pt_set_devices(int n, const int *ids);
 
 /* ---- scene life cycle: replaces Scene::Scene accel build (scene.cpp:93,
  *      scene_optix.inl:446) for triangle meshes ------------------------- */
 B200PT_API b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device,
                                   b200pt_scene **out);
 B200PT_API void          b200pt_scene_destroy(b200pt_scene *scene);
+/* Geometry update with unchanged topology (params['<mesh>.vertex_positions'] = ...; params.update() ->
+ * Mesh::parameters_changed + Scene::parameters_changed -> accel update, mesh.cpp:170-230, scene.cpp:517-540): replace
+ * the packed (V, 8) vertex records of shape `shape` and REFIT the BVH on the device (boxes recomputed bottom-up, tree
+ * topology and triangle order kept; a large deformation costs traversal efficiency, never correctness). Shapes that are
+ * sampled as emitters carry host-built sampling tables: for those the call fails with B200PT_ERR_UNSUPPORTED and the
+ * scene has to be created again. */
+B200PT_API b200pt_status b200pt_scene_update_vertices(b200pt_scene *scene, uint32_t shape, const float *vertices,
+                                           uint32_t n_vertices);
 /* Parameter update after an optimiser step (SceneParameters.update ->
  * parameters_changed, util.py:272-338): overwrite texture `tex` with `n`
  * floats (3/1 for constants, h*w*c for bitmaps). */

@@ -105,8 +105,8 @@ class Stats(C.Structure):
 
 # Every symbol include/b200pt.h declares (checked by tests/test_abi.py).
 SYMBOLS = [
-    "b200pt_abi_version", "b200pt_last_error", "b200pt_device_count",
-    "b200pt_scene_create", "b200pt_scene_destroy", "b200pt_scene_update_texture",
+    "b200pt_abi_version", "b200pt_last_error", "b200pt_device_count", "b200pt_set_devices",
+    "b200pt_scene_create", "b200pt_scene_destroy", "b200pt_scene_update_texture", "b200pt_scene_update_vertices",
     "b200pt_render", "b200pt_render_accumulate", "b200pt_develop",
     "b200pt_render_backward", "b200pt_render_backward_device", "b200pt_grad_zero",
     "b200pt_tangent_zero", "b200pt_tangent_write", "b200pt_render_forward",
@@ -146,10 +146,12 @@ def load() -> C.CDLL:
     lib.b200pt_abi_version.restype = C.c_uint32
     lib.b200pt_last_error.restype = C.c_char_p
     lib.b200pt_device_count.restype = C.c_int
+    lib.b200pt_set_devices.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.b200pt_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
     lib.b200pt_scene_destroy.argtypes = [vp]
     lib.b200pt_scene_destroy.restype = None
     lib.b200pt_scene_update_texture.argtypes = [vp, u32, f32p, C.c_size_t]
+    lib.b200pt_scene_update_vertices.argtypes = [vp, u32, f32p, u32]
     lib.b200pt_render.argtypes = [vp, C.POINTER(RenderParams), f32p]
     lib.b200pt_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
     lib.b200pt_develop.argtypes = [vp, vp, vp, vp]

@@ -41,6 +41,7 @@ struct Wavefront {
     size_t cap = 0;
     PathBuf buf[2];
     float4 *hit = nullptr, *lane_result = nullptr, *lane_dL = nullptr;
+    uint32_t *vis = nullptr;        // NEE visibility bits of a gradient call (PathBuf::vis)
     Queues q;
     uint32_t *counts = nullptr; size_t n_counts = 0;
     std::vector<void *> allocs;
@@ -60,6 +61,9 @@ struct b200pt_scene {
     uint32_t *pix_ids = nullptr; uint32_t n_shard_pix = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
     uint32_t *all_pix_ids = nullptr;   // identity list (whole frame; weights pre-pass of the gaussian adjoint)
     uint32_t *cur_pix_ids = nullptr; uint32_t n_pix_ids = 0;   // the list selected by the last ensure_pix_ids
+    // device refit (b200pt_scene_update_vertices): per shape (first vertex, count, sampling), BVH levels, un-inflated boxes
+    std::vector<uint32_t> shape_first_vertex, shape_n_vertices; std::vector<int32_t> shape_sampling;
+    std::vector<uint32_t> bvh_level_start; float *bvh_tight = nullptr;
     unsigned long long *stats_dev = nullptr;
     float *film_own = nullptr, *out_dev = nullptr, *grad_in_dev = nullptr, *film_w = nullptr;
     cudaStream_t stream = nullptr;
@@ -111,6 +115,16 @@ int b200pt_device_count(void) {
     return n;
 }
 
+static std::vector<int> g_devices;     // b200pt_set_devices
+
+b200pt_status b200pt_set_devices(int n, const int *ids) {
+    if (n < 0 || (n > 0 && !ids)) return fail(B200PT_ERR_INVALID, "null device list");
+    int count = b200pt_device_count();
+    for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] >= count) return fail(B200PT_ERR_CUDA, "no such CUDA device (mitsuba3_b200 has no CPU fallback)");
+    g_devices.assign(ids, ids + n);
+    return B200PT_OK;
+}
+
 void b200pt_scene_destroy(b200pt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
@@ -149,6 +163,11 @@ static void init_gaussian(DevScene &d, float stddev) {
 b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b200pt_scene **out) {
     if (!desc || !out) return fail(B200PT_ERR_INVALID, "null argument");
     if (desc->abi_version != B200PT_ABI_VERSION) return fail(B200PT_ERR_INVALID, "ABI version mismatch");
+    if (device == B200PT_DEVICE_AUTO) {      // b200pt_set_devices: the rank's device of the job's list
+        const char *lr = getenv("LOCAL_RANK");
+        int r = lr ? atoi(lr) : 0;
+        device = g_devices.empty() ? 0 : g_devices[(size_t) (r < 0 ? 0 : r) % g_devices.size()];
+    }
     if (b200pt_device_count() <= device || device < 0) return fail(B200PT_ERR_CUDA, "no such CUDA device (mitsuba3_b200 has no CPU fallback)");
     if (desc->sensor.rfilter == B200PT_RFILTER_GAUSSIAN_TABLE)
         return fail(B200PT_ERR_UNSUPPORTED, "the tabulated filter belongs to the scalar variants; JIT variants evaluate the filter analytically");
@@ -276,7 +295,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     // ---- shapes: flatten to one vertex / primitive array ---------------------
     size_t n_verts = 0, n_prims = 0;
     for (uint32_t i = 0; i < desc->n_shapes; ++i) { n_verts += desc->shapes[i].n_vertices; n_prims += desc->shapes[i].n_faces; }
-    if (n_prims >= (1u << 26)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles (the traversal queue addresses 2^26)");
+    if (n_prims >= (1u << 28)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles");
     std::vector<float> verts(n_verts * 8); std::vector<uint32_t> pv(n_prims * 4); std::vector<float> tri9(n_prims * 9);
     std::vector<DevShape> hs(desc->n_shapes);
     size_t vo = 0, po = 0;
@@ -288,6 +307,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         DevShape &o = hs[i]; memset(&o, 0, sizeof(o));
         o.layout = sh.layout; o.bsdf = sh.bsdf; o.emitter = sh.emitter; o.sampling = sh.sampling;
         o.first_prim = (uint32_t) po; o.n_prims = sh.n_faces; o.first_vertex = (uint32_t) vo;
+        s->shape_first_vertex.push_back((uint32_t) vo); s->shape_n_vertices.push_back(sh.n_vertices); s->shape_sampling.push_back(sh.sampling);
         memcpy(o.to_world, sh.to_world, sizeof(o.to_world)); memcpy(o.frame_n, sh.frame_n, sizeof(o.frame_n)); o.inv_area = sh.inv_area;
         s->type_present[hb[sh.bsdf].type] = true;       // the queue / kernel class (plastic -> conductor)
         memcpy(&verts[vo * 8], sh.vertices, (size_t) sh.n_vertices * 8 * sizeof(float));
@@ -352,6 +372,8 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { BvhNode *p; S_TRY(dev_upload(s, bvh.nodes.data(), bvh.nodes.size(), &p)); d.nodes = (const float4 *) p; d.n_nodes = (uint32_t) bvh.nodes.size(); }
     { float *p; S_TRY(dev_upload(s, tris.data(), tris.size(), &p)); d.tris = (const float4 *) p; d.n_tris = (uint32_t) n_prims; }
     if (bvh.depth > 60) S_FAIL(B200PT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    s->bvh_level_start = bvh.level_start;
+    { float *p = nullptr; S_TRY(cudaMalloc(&p, std::max<size_t>(bvh.nodes.size(), 1) * 12 * sizeof(float))); s->allocs.push_back(p); s->bvh_tight = p; }
 
     // ---- sensor / film -------------------------------------------------------
     const b200pt_sensor &se = desc->sensor;
@@ -374,11 +396,6 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
-    { const char *e = getenv("B200PT_TRACE_COOP"); s->launch.coop_leaves = e ? atoi(e) != 0 : true; }
-    if (s->launch.coop_leaves && s->launch.n_smem_nodes > 256) {          // the warp lists take 12 KiB of the CTA's shared memory
-        s->launch.n_smem_nodes = 256;
-        s->launch.smem_trace = ((size_t) s->launch.n_smem_nodes * 64 + (size_t) s->launch.n_smem_tris * 48 + 127) & ~(size_t) 127;
-    }
     set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
@@ -391,6 +408,21 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     return B200PT_OK;
 #undef S_TRY
 #undef S_FAIL
+}
+
+b200pt_status b200pt_scene_update_vertices(b200pt_scene *s, uint32_t shape, const float *vertices, uint32_t n_vertices) {
+    if (!s || !vertices) return fail(B200PT_ERR_INVALID, "null argument");
+    if (shape >= s->shape_first_vertex.size() || n_vertices != s->shape_n_vertices[shape]) return fail(B200PT_ERR_INVALID, "shape index / vertex count mismatch");
+    if (s->shape_sampling[shape] != B200PT_SAMPLING_NONE)
+        return fail(B200PT_ERR_UNSUPPORTED, "the shape is sampled as an emitter (host-built sampling tables): create the scene again");
+    if (s->dev.geom_bytes <= 20480) { /* small scenes: the shading kernels stage the geometry per launch from these arrays, nothing else to do */ }
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaMemcpy((float *) s->dev.vertices + 8 * (size_t) s->shape_first_vertex[shape], vertices, (size_t) n_vertices * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    launch_refit(s->dev, s->bvh_tight, s->bvh_level_start.data(), (uint32_t) s->bvh_level_start.size() - 1, (int) s->n_sm * 4, s->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return B200PT_OK;
 }
 
 b200pt_status b200pt_scene_update_texture(b200pt_scene *s, uint32_t tex, const float *host_data, size_t n) {
@@ -441,6 +473,8 @@ static b200pt_status ensure_wavefront(b200pt_scene *s, size_t cap, bool adjoint)
         CU_TRY(A(slack * 16, (void **) &pb.sh_o)); CU_TRY(A(slack * 16, (void **) &pb.sh_d)); CU_TRY(A(slack * 8, (void **) &pb.sh_c));
         if (adjoint) { CU_TRY(A(slack * 16, (void **) &pb.adj_L)); CU_TRY(A(slack * 16, (void **) &pb.adj_dL)); }
     }
+    w.vis = nullptr;
+    if (adjoint) CU_TRY(A(slack * 4, (void **) &w.vis));
     CU_TRY(A(slack * 16, (void **) &w.hit)); CU_TRY(A(slack * 16, (void **) &w.lane_result)); CU_TRY(A(slack * 16, (void **) &w.lane_dL));
     for (int t = 0; t < N_BSDF_TYPES; ++t) {
         if (s->type_present[t]) CU_TRY(A(slack * 4, (void **) &w.q.slots[t])); else w.q.slots[t] = nullptr;
@@ -514,8 +548,10 @@ static int grid_for(const b200pt_scene *s, size_t n) {
 // One chunk of the wavefront: lanes [pix0*spp, (pix0+npix)*spp) of this shard.
 // mode 0: primal (path / prb) -> lane_result; mode 1: PRB adjoint replay; mode 2: PRB forward-mode
 // replay (lane_result <- dL of every sample).
-static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStream_t st) {
+static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStream_t st, bool use_vis = false) {
     Wavefront &w = s->wf;
+    // gradient calls: the primal pass records the NEE visibility bits, the replay reads them (max_depth <= 32)
+    w.buf[0].vis = w.buf[1].vis = use_vis ? w.vis : nullptr;
     const DevScene &d = s->dev;
     uint32_t lanes = cfg.chunk_lanes;
     cfg.adjoint = mode >= 1; cfg.forward = mode == 2;
@@ -580,7 +616,7 @@ static RenderCfg make_cfg(const b200pt_scene *s, const b200pt_render_params *p) 
 
 // bytes of wavefront state per lane (ensure_wavefront)
 static size_t wavefront_bytes_per_lane(const b200pt_scene *s, bool adjoint) {
-    size_t per = 2 * (8 * 16 + 8 + (adjoint ? 32 : 0)) + 3 * 16;      // two path buffers + hit, lane_result, lane_dL
+    size_t per = 2 * (8 * 16 + 8 + (adjoint ? 32 : 0)) + 3 * 16 + (adjoint ? 4 : 0);      // two path buffers + hit, lane_result, lane_dL
     for (int t = 0; t < N_BSDF_TYPES; ++t) if (s->type_present[t]) per += 4;
     if (s->dev.env_type >= 0) per += 4;
     return per;
@@ -741,12 +777,13 @@ b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render
         size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
         cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
         // pass 1: primal with the same stream (sampler.clone(), common.py:752) -> L per lane
-        e = run_chunk(s, cfg, 0, st); if (e) return e;
+        const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
+        e = run_chunk(s, cfg, 0, st, use_vis); if (e) return e;
         // dL per lane: adjoint of splat + develop
         launch_splat_adjoint(d, cfg, s->cur_pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, cfg.chunk_lanes), st);
         s->stats.kernel_launches++;
         // pass 2: adjoint replay (common.py:765)
-        e = run_chunk(s, cfg, 1, st); if (e) return e;
+        e = run_chunk(s, cfg, 1, st, use_vis); if (e) return e;
     }
     CU_TRY(cudaGetLastError());
     return end_stats(s, st, (uint64_t) s->n_pix_ids * p.spp);
@@ -782,8 +819,9 @@ b200pt_status b200pt_render_forward(b200pt_scene *s, const b200pt_render_params 
         for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
             size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
             cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
-            e = run_chunk(s, cfg, 0, st); if (e) return e;      // primal: L per lane
-            e = run_chunk(s, cfg, 2, st); if (e) return e;      // forward replay: dL per lane
+            const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
+            e = run_chunk(s, cfg, 0, st, use_vis); if (e) return e;      // primal: L per lane (+ NEE visibility bits)
+            e = run_chunk(s, cfg, 2, st, use_vis); if (e) return e;      // forward replay: dL per lane
             launch_splat(s->dev, cfg, s->cur_pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
             s->stats.kernel_launches++;
         }

@@ -107,6 +107,7 @@ Bvh build_bvh(const float *tri, uint32_t n) {
         for (int k = 0; k < 2; ++k) for (int a = 0; a < 3; ++a) { root.f[6 * k + a] = std::numeric_limits<float>::infinity(); root.f[6 * k + 3 + a] = -std::numeric_limits<float>::infinity(); }
         root.left = root.right = BVH_EMPTY;
         out.nodes.push_back(root);
+        out.level_start = { 0u, 1u };
         return out;
     }
     Builder b; b.tri = tri; b.n = n;
@@ -138,15 +139,19 @@ Bvh build_bvh(const float *tri, uint32_t n) {
         for (int a = 0; a < 3; ++a) { rn.f[6 + a] = std::numeric_limits<float>::infinity(); rn.f[9 + a] = -std::numeric_limits<float>::infinity(); }
         rn.left = ~(int32_t) ((b.tmp[root].first << 3) | (b.tmp[root].count - 1)); rn.right = BVH_EMPTY;
         out.nodes.push_back(rn);
+        out.level_start = { 0u, 1u };
         return out;
     }
     std::queue<int> q; q.push(root);
+    size_t level_left = 1, next_level = 0;
+    out.level_start.push_back(0u);
     while (!q.empty()) {
         int id = q.front(); q.pop();
         bfs_index[id] = (int) bfs.size(); bfs.push_back(id);
         const TmpNode &t = b.tmp[id];
-        if (b.tmp[t.left].left >= 0) q.push(t.left);
-        if (b.tmp[t.right].left >= 0) q.push(t.right);
+        if (b.tmp[t.left].left >= 0) { q.push(t.left); ++next_level; }
+        if (b.tmp[t.right].left >= 0) { q.push(t.right); ++next_level; }
+        if (--level_left == 0) { out.level_start.push_back((uint32_t) bfs.size()); level_left = next_level; next_level = 0; }
     }
     out.nodes.resize(bfs.size());
     for (size_t i = 0; i < bfs.size(); ++i) {

@@ -43,6 +43,9 @@ struct Bvh {
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> order;   // leaf order -> input triangle index
     uint32_t depth = 0;
+    // breadth-first order is level order: level l = nodes [level_start[l], level_start[l + 1]). The device refit
+    // (kernels.cu: k_refit_level) recomputes the boxes level by level from the deepest one up.
+    std::vector<uint32_t> level_start;
 };
 
 // tri: n x 9 floats (p0, p1, p2)

@@ -22,6 +22,7 @@
 // bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) once per persistent CTA.
 #include "kernels.cuh"
 #include <mutex>
+#include <algorithm>
 
 namespace pt {
 
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
         buf.prev[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PF_PREV_DELTA | PF_ALIVE));
         buf.rng[i] = make_uint4((uint32_t) rng.state, (uint32_t) (rng.state >> 32), lane, i);
         buf.result[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (buf.vis && !cfg.adjoint) buf.vis[i] = 0u;       // primal pass of a gradient call: NEE visibility bits for the replay
         if (cfg.adjoint) { buf.adj_L[i] = adj_L_lane[i]; buf.adj_dL[i] = cfg.forward ? make_float4(1.f, 1.f, 1.f, 0.f) : adj_dL_lane[i]; }
     }
 }
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                 Hit h; n_shadow++;
                 bool occluded = traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
                 if (!occluded) {
+                    if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[i].w] |= 1u << bit; }
                     float2 c = cur.sh_c[i];
                     res = cur.result[i]; res_loaded = true;
                     res.x += sd.w; res.y += c.x; res.z += c.y;
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
         if (kind != 0 && node == TRAV_SENTINEL) {
             if (kind == 1) {
                 if (!occluded) {
+                    if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[slot].w] |= 1u << bit; }
                     float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
                     res.x += sd.w; res.y += cc.x; res.z += cc.y;
                     cur.result[slot] = res;
@@ -479,234 +483,6 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                 if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
                 off = __shfl_sync(0xffffffffu, off, leader);
                 if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = slot;
-            }
-        }
-    }
-    for (int of = 16; of; of >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, of); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, of); }
-    if (lane_id == 0) {
-        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
-        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// k_trace_coop -- k_trace_dyn with WARP-COOPERATIVE LEAF ROUNDS.
-//
-// In k_trace_dyn every lane tests the triangles of the leaf it found itself: measured on the bench frame the
-// Moeller-Trumbore loop issues 28 % of the kernel's instructions at 7 of 32 threads (profiles/r01_simt_model.md
-// section 1) -- only the lanes that hold a leaf work, and a lane with two triangles keeps the warp for two passes.
-// Here the walk is unchanged (speculative while-while, one postponed leaf per lane), but when the warp reaches its
-// leaf phase the (owner lane, triangle) pairs of all postponed leaves go to a list in shared memory and the WHOLE warp
-// tests them, one pair per lane -- idle lanes included -- reading the owner's ray from shared memory. A hit returns
-// through a 64-bit atomicMin per owner on the key (t bits << 32 | primitive): for t >= 0 the float bit pattern orders
-// like the value, so the minimum is the closest hit with ties resolved towards the smaller primitive index, the rule
-// of the per-lane loop -- identical hits. A shadow ray stores key 0 = occluded. The lane whose key is the round's
-// minimum writes (u, v). No test is deferred: every lane has its new maxt before it walks on.
-//
-// Entry = any-hit flag << 31 | owner lane << 26 | triangle index (api.cu limits scenes to 2^26 triangles).
-// ---------------------------------------------------------------------------
-struct __align__(16) WarpTrace {
-    float o[3][32], d[3][32];         // ray of every lane of the warp
-    unsigned long long best[32];      // (bits of the closest t, or of maxt) << 32 | primitive (0xffffffff: none); 0: occluded
-    float2 uv[32];
-    uint32_t pairs[64];               // <= 2 triangles per postponed leaf and round
-};
-
-template <bool FIRST, bool SMEM_ALL>
-__global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_coop(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out,
-                                                      const uint32_t *__restrict__ n_in, Queues q, uint32_t *__restrict__ qcounts, uint32_t *__restrict__ work_counter,
-                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ WarpTrace s_warp[BLOCK / 32];
-    DevScene sc = sc_in;
-    float4 *s_nodes = (float4 *) smem_raw;
-    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
-    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
-    TraceCtx c = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
-    WarpTrace &ws = s_warp[threadIdx.x >> 5];
-
-    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
-    const uint32_t lane_id = threadIdx.x & 31u, lt_mask = (1u << lane_id) - 1u;
-    uint32_t n_shadow = 0, n_closest = 0;
-
-    // job state of this lane
-    int kind = 0;                     // 0 idle, 1 shadow ray, 2 path ray
-    uint32_t slot = 0, flags = 0;
-    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
-    float maxt = 0.f;
-    int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
-    uint32_t leaf_first = 0, leaf_left = 0;      // triangles of the postponed leaf that are not tested yet
-    bool exhausted = false;           // the global pool is empty
-
-    auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
-        o = ro; d = rd; maxt = rmaxt;
-        inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
-        ws.o[0][lane_id] = o.x; ws.o[1][lane_id] = o.y; ws.o[2][lane_id] = o.z;
-        ws.d[0][lane_id] = d.x; ws.d[1][lane_id] = d.y; ws.d[2][lane_id] = d.z;
-        ws.best[lane_id] = ((unsigned long long) __float_as_uint(rmaxt) << 32) | 0xffffffffull;
-        stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf = 0; leaf_left = 0;
-    };
-
-    while (true) {
-        // ---- refill idle lanes from the global pool --------------------------------------
-        uint32_t idle_mask = __ballot_sync(0xffffffffu, kind == 0);
-        if (!exhausted && (__popc(idle_mask) >= DYN_REFILL_IDLE)) {
-            uint32_t cnt = __popc(idle_mask), base = 0;
-            if (lane_id == 0) base = atomicAdd(work_counter, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + cnt >= n) exhausted = true;
-            if (kind == 0) {
-                uint32_t i = base + __popc(idle_mask & lt_mask);
-                if (i < n) {
-                    slot = i;
-                    flags = FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w);
-                    if (!FIRST && (flags & PF_HAS_SHADOW)) {
-                        float4 so = cur.sh_o[i], sd = cur.sh_d[i];
-                        kind = 1; n_shadow++;
-                        start_ray(V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w);
-                    } else {       // every queued slot is alive or has a shadow ray
-                        float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
-                        kind = 2; n_closest++;
-                        start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
-                    }
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, kind != 0)) break;
-
-        // ---- traverse until the warp wants to refill ---------------------------------------------------
-        while (true) {
-            // node phase: every walking lane steps until it holds a leaf (speculatively on, until all of them do)
-            if (kind != 0 && node != TRAV_SENTINEL) {
-                bool searching = leaf >= 0;
-                while (node >= 0 && node != TRAV_SENTINEL) {
-                    float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
-                    int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-                    float tl, tr;
-                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
-                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
-                    if (!hl && !hr) node = stack[sp--];
-                    else {
-                        node = hl ? cl : cr;
-                        if (hl && hr) {
-                            int32_t far = cr;
-                            if (tr < tl) { far = cl; node = cr; }
-                            stack[++sp] = far;
-                        }
-                    }
-                    if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }   // postpone the first leaf
-                    if (!__any_sync(__activemask(), searching)) break;
-                }
-            }
-            __syncwarp();
-            // leaf phase: the pairs of all postponed leaves, one pair per lane of the WHOLE warp
-            if (kind != 0 && leaf < 0 && leaf_left == 0) { const uint32_t enc = (uint32_t) ~leaf; leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u; }
-            while (true) {
-                const uint32_t cpush = min(leaf_left, 2u);
-                const uint32_t m1 = __ballot_sync(0xffffffffu, cpush >= 1);
-                if (m1 == 0) break;
-                const uint32_t m2 = __ballot_sync(0xffffffffu, cpush == 2);
-                if (cpush) {
-                    const uint32_t off = __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
-                    const uint32_t tag = (kind == 1 ? 0x80000000u : 0u) | (lane_id << 26);
-                    ws.pairs[off] = tag | leaf_first;
-                    if (cpush == 2) ws.pairs[off + 1] = tag | (leaf_first + 1);
-                    leaf_first += cpush; leaf_left -= cpush;
-                }
-                const uint32_t total = __popc(m1) + __popc(m2);
-                __syncwarp();
-                for (uint32_t base = 0; base < total; base += 32) {
-                    bool won = false; unsigned long long key = 0; uint32_t owner = 0; float u = 0.f, v = 0.f;
-                    if (base + lane_id < total) {
-                        const uint32_t e = ws.pairs[base + lane_id];
-                        owner = (e >> 26) & 31u;
-                        const uint32_t tri = e & 0x03ffffffu;
-                        const unsigned long long b = ws.best[owner];
-                        if (b != 0ull) {
-                            const float mt = __uint_as_float((uint32_t) (b >> 32));
-                            const float3 ro = V(ws.o[0][owner], ws.o[1][owner], ws.o[2][owner]), rd = V(ws.d[0][owner], ws.d[1][owner], ws.d[2][owner]);
-                            float4 ta = ld_tri<SMEM_ALL>(c, tri, 0), tb = ld_tri<SMEM_ALL>(c, tri, 1), te = ld_tri<SMEM_ALL>(c, tri, 2);
-                            float t;
-                            if (moeller_trumbore(ro, rd, mt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
-                                // t + 0: a hit at t = -0 gets the bit pattern of +0, so that the unsigned order of the keys is the order of t
-                                key = (e >> 31) ? 0ull : (((unsigned long long) __float_as_uint(t + 0.f) << 32) | __float_as_uint(ta.w));
-                                const unsigned long long old = atomicMin(&ws.best[owner], key);
-                                won = !(e >> 31) && key < old;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (won && ws.best[owner] == key) ws.uv[owner] = make_float2(u, v);     // the round's closest hit of that ray
-                    __syncwarp();
-                }
-                // owners: new maxt / occlusion, next postponed leaf
-                if (kind != 0 && leaf < 0 && leaf_left == 0) {
-                    const unsigned long long b = ws.best[lane_id];
-                    if (kind == 1) { if (b == 0ull) { node = TRAV_SENTINEL; leaf = 0; } }     // any-hit: stop at the first occluder
-                    else maxt = __uint_as_float((uint32_t) (b >> 32));
-                    if (leaf < 0) {
-                        leaf = node;
-                        if (node < 0) { node = stack[sp--]; const uint32_t enc = (uint32_t) ~leaf; leaf_first = enc >> 3; leaf_left = (enc & 7u) + 1u; }
-                    }
-                }
-            }
-            // dynamic fetch: leave when too few lanes of the warp are still walking, or none is
-            const uint32_t wm = __ballot_sync(0xffffffffu, kind != 0 && node != TRAV_SENTINEL);
-            if (wm == 0 || (!exhausted && __popc(wm) < 32 - DYN_REFILL_IDLE)) break;
-        }
-
-        // ---- retire finished rays -----------------------------------------------------------
-        int mytype = -1;
-        if (kind != 0 && node == TRAV_SENTINEL) {
-            const unsigned long long b = ws.best[lane_id];
-            if (kind == 1) {
-                if (b != 0ull) {
-                    float4 sd = cur.sh_d[slot]; float2 cc = cur.sh_c[slot]; float4 res = cur.result[slot];
-                    res.x += sd.w; res.y += cc.x; res.z += cc.y;
-                    cur.result[slot] = res;
-                }
-                if (flags & PF_ALIVE) {
-                    float4 ro = cur.ray_o[slot], rd = cur.ray_d[slot];
-                    kind = 2; n_closest++;
-                    start_ray(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w);
-                } else {
-                    lane_result[cur.rng[slot].w] = cur.result[slot];
-                    kind = 0;
-                }
-            } else {
-                const uint32_t prim = (uint32_t) b;
-                const bool found = prim != 0xffffffffu;
-                const float ht = __uint_as_float((uint32_t) (b >> 32));
-                const float2 huv = ws.uv[lane_id];
-                if (FIRST && cfg.hide_emitters && found && sc.shapes[sc.prim_verts[prim].w].emitter >= 0) {
-                    // skip_area_emitters (integrator.cpp:96-123)
-                    SurfaceInteraction si = compute_si(sc, ht, huv.x, huv.y, prim, d);
-                    Ray r = spawn_ray(si.p, si.n, d);
-                    cur.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt);
-                    start_ray(r.o, d, r.maxt);
-                } else {
-                    if (found) {
-                        hit_out[slot] = make_float4(ht, huv.x, huv.y, __uint_as_float(prim));
-                        mytype = sc.bsdfs[sc.shapes[sc.prim_verts[prim].w].bsdf].type;
-                    } else if (sc.env_type >= 0) mytype = Q_ENV;     // the ray left the scene: environment emitter (k_shade_env)
-                    else lane_result[cur.rng[slot].w] = cur.result[slot];
-                    kind = 0;
-                }
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < N_QUEUES; ++t) {
-            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
-            if (m) {
-                uint32_t leader = __ffs(m) - 1, off = 0;
-                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
-                off = __shfl_sync(0xffffffffu, off, leader);
-                if (mytype == t) q.slots[t][off + __popc(m & lt_mask)] = slot;
             }
         }
     }
@@ -806,26 +582,30 @@ PT_DEV float3 bsdf_backward(const DevScene &sc, const DevBsdf &b, float2 uv, flo
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4
 #endif
-template <int TYPE, bool ADJOINT, bool EXT>
-__global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
+// ADJ: 0 primal; 1 adjoint / forward replay that resolves the NEE visibility with an inline any-hit walk; 2 replay that
+// reads the visibility bits the primal pass of the same call recorded (PathBuf::vis, one bit per bounce, max_depth <= 32):
+// no walk, no BVH in shared memory, twice the occupancy.
+template <int TYPE, int ADJ, bool EXT>
+__global__ void __launch_bounds__(BLOCK_SHADE, ADJ == 1 ? 2 : (ADJ == 2 ? (TYPE == B200PT_BSDF_DIFFUSE ? 4 : 2) : SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, const float4 *__restrict__ hit_in,
                                                  const uint32_t *__restrict__ queue, const uint32_t *__restrict__ qcount, PathBuf nxt,
                                                  uint32_t *__restrict__ nxt_count, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    constexpr bool ADJOINT = ADJ != 0;
     DevScene sc = sc_in;
     TraceCtx ctx = { nullptr, nullptr, sc.nodes, sc.tris, 0, 0 };
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     uint32_t bvh_bytes = 0;
-    if (ADJOINT) {
+    if (ADJ == 1) {
         float4 *s_nodes = (float4 *) smem_raw;
         float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
         stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
         ctx.s_nodes = s_nodes; ctx.s_tris = s_tris; ctx.n_smem_nodes = n_smem_nodes; ctx.n_smem_tris = n_smem_tris;
         bvh_bytes = (n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u;
     }
-    stage_tables(sc, smem_raw + bvh_bytes, &bar, ADJOINT ? 1u : 0u);
+    stage_tables(sc, smem_raw + bvh_bytes, &bar, ADJ == 1 ? 1u : 0u);
     const uint32_t n = *qcount;
     const uint32_t lane_id = threadIdx.x & 31u;
     const uint32_t warp_stride = gridDim.x * blockDim.x;
@@ -897,10 +677,15 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                     active_em = ds.pdf != 0.f;
                     wo = si.to_local(ds.d);
                     if (ADJOINT && active_em) {
-                        // the adjoint needs Lr_dir now (prb.py:227): resolve the visibility inline
-                        sray = spawn_ray_to(si.p, si.n, ds.p);
-                        Hit h; n_shadow++;
-                        if (traverse<true, false>(ctx, sray.o, sray.d, sray.maxt, h)) { em_weight = V(0.f, 0.f, 0.f); ds.pdf = 0.f; active_em = false; }
+                        // the adjoint needs Lr_dir now (prb.py:227)
+                        bool occluded;
+                        if (ADJ == 2) occluded = !((cur.vis[rs.w] >> depth) & 1u);      // recorded by the primal pass of this call (k_trace*)
+                        else {                                                           // resolve the visibility inline
+                            sray = spawn_ray_to(si.p, si.n, ds.p);
+                            Hit h; n_shadow++;
+                            occluded = traverse<true, false>(ctx, sray.o, sray.d, sray.maxt, h);
+                        }
+                        if (occluded) { em_weight = V(0.f, 0.f, 0.f); ds.pdf = 0.f; active_em = false; }
                     }
                 }
                 // ---- BSDF (path.cpp:263-267)
@@ -912,7 +697,9 @@ __global__ void __launch_bounds__(BLOCK_SHADE, ADJOINT ? 2 : SHADE_MIN_BLOCKS) k
                     mis_em = mis_weight(ds.pdf, br.pdf);
                     contrib = prb ? ((throughput * mis_em) * br.value) * em_weight : throughput * ((br.value * em_weight) * mis_em);
                     if (!ADJOINT) {
-                        has_shadow = contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f;
+                        // (a pass that records visibility for the replay traces every NEE ray: a zero contribution can
+                        //  still have a non-zero parameter derivative)
+                        has_shadow = contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f || cur.vis != nullptr;
                         if (has_shadow) sray = spawn_ray_to(si.p, si.n, ds.p);
                     }
                 }
@@ -1327,13 +1114,6 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
-    if (L.dynamic_fetch && L.coop_leaves) {
-#define LAUNCH_Q(F, A) k_trace_coop<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
-        if (first) { if (all) LAUNCH_Q(true, true); else LAUNCH_Q(true, false); }
-        else { if (all) LAUNCH_Q(false, true); else LAUNCH_Q(false, false); }
-#undef LAUNCH_Q
-        return;
-    }
     if (L.dynamic_fetch) {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
         if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
@@ -1352,9 +1132,10 @@ static void launch_shade_t(const DevScene &sc, const RenderCfg &cfg, PathBuf cur
                            PathBuf nxt, uint32_t *nxt_count, float4 *lane_result, unsigned long long *stats, const Launch &L, cudaStream_t st) {
     // EXT: environment emitter or non-uniform emitter selection present (pt_device.cuh: sample_emitter_direction)
     const bool ext = sc.env_type >= 0 || sc.em_cdf != nullptr;
-    if (cfg.adjoint) k_shade<TYPE, true, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-    else if (ext) k_shade<TYPE, false, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
-    else k_shade<TYPE, false, false><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    if (cfg.adjoint && cur.vis) k_shade<TYPE, 2, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    else if (cfg.adjoint) k_shade<TYPE, 1, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+    else if (ext) k_shade<TYPE, 0, true><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
+    else k_shade<TYPE, 0, false><<<L.grid * (BLOCK / BLOCK_SHADE), BLOCK_SHADE, L.smem_tables, st>>>(sc, cfg, cur, hit, queue, qcount, nxt, nxt_count, lane_result, stats, 0, 0);
 }
 
 void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const float4 *hit, const uint32_t *queue, const uint32_t *qcount,
@@ -1388,6 +1169,72 @@ __global__ void __launch_bounds__(BLOCK) k_flush(PathBuf cur, Queues q, const ui
 }
 void launch_flush(PathBuf cur, Queues q, const uint32_t *qcounts, float4 *lane_result, int grid, cudaStream_t st) {
     k_flush<<<grid, BLOCK, 0, st>>>(cur, q, qcounts, lane_result);
+}
+
+// ---------------------------------------------------------------------------
+// Device-side BVH refit (geometry update with unchanged topology; the reference's Scene::parameters_changed ->
+// accel update, scene.cpp:517-540, rebuilds or refits through Embree / OptiX). After new vertex positions have been
+// uploaded: k_refit_tris regathers the leaf-ordered triangle records, k_refit_level recomputes the child boxes of
+// one breadth-first level (deepest level first: children always have larger indices than their parent).
+// `tight` keeps the un-inflated child boxes (12 floats per node) so that the inflation (bvh.cpp: inflate) is applied
+// once per box, not once per level.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_refit_tris(uint32_t n_tris, float4 *__restrict__ tris, const uint4 *__restrict__ prim_verts, const float4 *__restrict__ vertices) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tris; i += gridDim.x * blockDim.x) {
+        const float4 t0 = tris[3 * (size_t) i];
+        const uint4 pv = prim_verts[__float_as_uint(t0.w)];
+        const float4 a = vertices[2 * (size_t) pv.x], b = vertices[2 * (size_t) pv.y], c = vertices[2 * (size_t) pv.z];
+        tris[3 * (size_t) i] = make_float4(a.x, a.y, a.z, t0.w);
+        tris[3 * (size_t) i + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.f);          // e1 = p1 - p0 (mesh.h:1139)
+        tris[3 * (size_t) i + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+    }
+}
+
+PT_DEV void refit_child(int32_t child, const float4 *tris, const uint4 *prim_verts, const float4 *vertices, const float *tight, float *out_tight, float *out_box) {
+    float lo[3] = { PT_INF, PT_INF, PT_INF }, hi[3] = { -PT_INF, -PT_INF, -PT_INF };
+    if (child == 0x7fffffff) { for (int a = 0; a < 3; ++a) { out_tight[a] = out_box[a] = PT_INF; out_tight[3 + a] = out_box[3 + a] = -PT_INF; } return; }
+    if (child < 0) {          // leaf: the exact vertex positions of its triangles
+        const uint32_t enc = (uint32_t) ~child, first = enc >> 3, count = (enc & 7u) + 1u;
+        for (uint32_t i = first; i < first + count; ++i) {
+            const uint4 pv = prim_verts[__float_as_uint(tris[3 * (size_t) i].w)];
+            const uint32_t vi[3] = { pv.x, pv.y, pv.z };
+            for (int k = 0; k < 3; ++k) {
+                const float4 p = vertices[2 * (size_t) vi[k]];
+                lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+                hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+            }
+        }
+    } else {                  // inner node: union of its two (tight) child boxes, already refitted (deeper level)
+        const float *t = tight + 12 * (size_t) child;
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(t[a], t[6 + a]); hi[a] = fmaxf(t[3 + a], t[9 + a]); }
+    }
+    for (int a = 0; a < 3; ++a) {
+        out_tight[a] = lo[a]; out_tight[3 + a] = hi[a];
+        const float m = fmaxf(fabsf(lo[a]), fabsf(hi[a])), pad = m * 4e-6f + 1e-7f;            // bvh.cpp: inflate
+        out_box[a] = nextafterf(lo[a] - pad, -PT_INF); out_box[3 + a] = nextafterf(hi[a] + pad, PT_INF);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_refit_level(float4 *__restrict__ nodes, float *__restrict__ tight, const float4 *__restrict__ tris, const uint4 *__restrict__ prim_verts,
+                                                       const float4 *__restrict__ vertices, uint32_t first, uint32_t count) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t i = first + k;
+        const float4 n3 = nodes[4 * (size_t) i + 3];
+        float box[12];
+        refit_child(__float_as_int(n3.x), tris, prim_verts, vertices, tight, tight + 12 * (size_t) i, box);
+        refit_child(__float_as_int(n3.y), tris, prim_verts, vertices, tight, tight + 12 * (size_t) i + 6, box + 6);
+        nodes[4 * (size_t) i] = make_float4(box[0], box[1], box[2], box[3]);
+        nodes[4 * (size_t) i + 1] = make_float4(box[4], box[5], box[6], box[7]);
+        nodes[4 * (size_t) i + 2] = make_float4(box[8], box[9], box[10], box[11]);
+    }
+}
+
+void launch_refit(const DevScene &sc, float *tight, const uint32_t *level_start, uint32_t n_levels, int grid, cudaStream_t st) {
+    k_refit_tris<<<grid, BLOCK, 0, st>>>(sc.n_tris, (float4 *) sc.tris, sc.prim_verts, sc.vertices);
+    for (uint32_t l = n_levels; l-- > 0;) {
+        const uint32_t first = level_start[l], count = level_start[l + 1] - first;
+        if (count) k_refit_level<<<(int) std::min<uint32_t>((count + BLOCK - 1) / BLOCK, (uint32_t) grid), BLOCK, 0, st>>>((float4 *) sc.nodes, tight, sc.tris, sc.prim_verts, sc.vertices, first, count);
+    }
 }
 
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st) {
@@ -1444,28 +1291,24 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_coop<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_coop<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_coop<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace_coop<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_CONDUCTOR, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIELECTRIC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_shade<B200PT_BSDF_PRINCIPLED, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
 } // namespace pt

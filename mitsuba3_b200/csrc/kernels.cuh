@@ -22,6 +22,9 @@ struct PathBuf {
     // PRB adjoint pass only
     float4 *adj_L;    // radiance still to come (rgb), unused
     float4 *adj_dL;   // dLoss/dL of this sample (rgb), unused
+    // gradient calls with max_depth <= 32: bit b of vis[chunk-local lane] = "the NEE ray of bounce b is unoccluded", written by
+    // the traversal kernels in the call's primal pass, read by the replay (k_shade<.., 2, ..>); nullptr otherwise
+    uint32_t *vis;
 };
 
 // flags word stored in prev.w
@@ -56,7 +59,6 @@ constexpr int BLOCK = 256;
 constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 registers -> 4 blocks / SM
 
 struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
-                bool coop_leaves;    // traversal kernel: k_trace_coop (warp-cooperative leaf rounds) instead of k_trace_dyn
 };
 
 // counters in the stats buffer
@@ -71,6 +73,7 @@ void launch_shade(int type, const DevScene &sc, const RenderCfg &cfg, PathBuf cu
 void launch_shade_env(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, const uint32_t *queue, const uint32_t *qcount,
                       float4 *lane_result, unsigned long long *stats, int grid, cudaStream_t st);
 void launch_flush(PathBuf cur, Queues q, const uint32_t *qcounts, float4 *lane_result, int grid, cudaStream_t st);
+void launch_refit(const DevScene &sc, float *tight, const uint32_t *level_start, uint32_t n_levels, int grid, cudaStream_t st);
 void launch_env_query(const DevScene &sc, uint32_t n, const float *in, float *out, cudaStream_t st);
 void launch_splat(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float4 *lane_result, float *film, int grid, cudaStream_t st);
 void launch_splat_adjoint(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, const float *grad_in, const float *film_w,

@@ -255,21 +255,27 @@ def update_params(scene: Scene, values: dict, device: int = 0) -> None:
 
 def update_vertices(scene: Scene, shape_id: str, packed_vertices) -> None:
     """Geometry update (``params['<shape>.vertex_positions'] = ...; params.update()`` in the reference,
-    scene.cpp:517-540): replaces the packed (V, 8) records of one mesh and drops the device scene, which
-    is re-created -- BVH rebuilt on the host, everything uploaded again -- by the next render. The
-    topology must stay the same. (A device-side refit is later work)"""
-    sh = next((s for s in scene.shapes if s.id == shape_id), None)
-    if sh is None:
+    scene.cpp:517-540): replaces the packed (V, 8) records of one mesh. With a live device scene the new vertices are
+    uploaded and the BVH is REFITTED on the device (``b200pt_scene_update_vertices``: same topology, boxes recomputed
+    bottom-up); shapes sampled as emitters (host-built sampling tables) drop the device scene instead, which the next
+    render re-creates. The mesh topology must stay the same."""
+    idx = next((i for i, s in enumerate(scene.shapes) if s.id == shape_id), None)
+    if idx is None:
         raise KeyError(shape_id)
+    sh = scene.shapes[idx]
     v = np.ascontiguousarray(packed_vertices, np.float32).reshape(-1, 8)
     if v.shape != sh.vertices.shape:
         raise ValueError(f"expected packed vertices of shape {sh.vertices.shape}, got {v.shape}")
     if sh.sampling == abi.SAMPLING_RECTANGLE:
         raise NotImplementedError("rectangle emitters are sampled through their to_world transform; re-create the shape instead")
     sh.vertices = v
-    if scene._handle is not None:
-        scene._handle.close()
-        scene._handle = None
+    ds = scene._handle
+    if ds is not None and ds.h is not None:
+        if sh.sampling == abi.SAMPLING_NONE:
+            abi.check(ds.lib.b200pt_scene_update_vertices(ds.h, idx, v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0]), ds.lib)
+        else:
+            ds.close()
+            scene._handle = None
 
 
 def render_torch(scene: Scene, params: dict, integrator=None, seed: int = 0, seed_grad=None, spp: int = 0, spp_grad: int = 0,

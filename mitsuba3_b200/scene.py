@@ -845,7 +845,7 @@ def matpreview_scene(path: str | None = None) -> dict:
                    "far_clip": float(z["sensor_clip"][1]), "to_world": Transform4f(z["sensor_to_world"]),
                    "sampler": {"type": "independent", "sample_count": 64},
                    "film": {"type": "hdrfilm", "width": 683, "height": 512, "pixel_format": "rgb", "rfilter": {"type": "gaussian"}}},
-        "emitter-envmap": {"type": "envmap", "data": z["envmap"], "scale": float(z["envmap_scale"]), "to_world": Transform4f(z["envmap_to_world"])},
+        "emitter-envmap": {"type": "envmap", "data": z["envmap"], "scale": float(np.asarray(z["envmap_scale"]).reshape(-1)[0]), "to_world": Transform4f(z["envmap_to_world"])},
         "bsdf-diffuse": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.18, 0.18, 0.18]}},
         "bsdf-plane": {"type": "diffuse", "reflectance": {"type": "checkerboard", "color0": {"type": "rgb", "value": [0.4, 0.4, 0.4]},
                                                           "color1": {"type": "rgb", "value": [0.2, 0.2, 0.2]}, "to_uv": [[8, 0, 0], [0, 8, 0], [0, 0, 1]]}},

@@ -313,8 +313,9 @@ def test_rough_materials_scene_matches_oracle(oracle_mod):
     compare_images(img, ref, max_bad_frac=0.01)
 
 
-def test_vertex_update_recreates_the_device_scene(oracle_mod):
-    """update_vertices: moving a mesh = the image of a scene created with the moved mesh."""
+def test_vertex_update_refits_the_bvh_on_the_device(oracle_mod):
+    """update_vertices: moving a mesh (device refit of the BVH, b200pt_scene_update_vertices) = the image of a scene
+    created with the moved mesh."""
     sc = mb.load_dict(cbox(res=32, spp=8, max_depth=4))
     img0 = mb.render(sc, spp=8, seed=1)
     sh = next(s for s in sc.shapes if s.id == "small-box")
@@ -325,6 +326,35 @@ def test_vertex_update_recreates_the_device_scene(oracle_mod):
     compare_images(img1, oracle_mod.OracleScene(sc).render(spp=8, seed=1, mode=0))
     with pytest.raises(ValueError):
         mb.update_vertices(sc, "small-box", moved[:4])
+    assert sc._handle is not None and sc._handle.h is not None          # the device scene survived: it was refitted, not rebuilt
+
+
+def test_device_refit_equals_a_fresh_build_on_a_large_mesh():
+    """205k-triangle heightfield, every vertex displaced: after the device refit (same tree topology, new boxes) the
+    closest hits and the occlusion tests are those of a scene built from scratch -- the box-filtered images are equal
+    sample for sample -- and a second refit back to the original vertices restores the original image."""
+    d = mb.cornell_box_heightfield(320)
+    d["sensor"]["film"].update(width=96, height=96, rfilter={"type": "box"})
+    sc = mb.load_dict(d)
+    img0 = mb.render(sc, spp=8, seed=2)
+    name = next(s.id for s in sc.shapes if s.faces.shape[0] > 100000)
+    sh = next(s for s in sc.shapes if s.id == name)
+    orig = sh.vertices.copy()
+    rng = np.random.default_rng(4)
+    moved = orig.copy()
+    moved[:, 1] += (0.03 * np.sin(9 * orig[:, 0]) * np.cos(7 * orig[:, 2]) + 0.004 * rng.standard_normal(len(orig))).astype(np.float32)
+    mb.update_vertices(sc, name, moved)
+    assert sc._handle is not None and sc._handle.h is not None
+    img1 = mb.render(sc, spp=8, seed=2)
+    assert np.abs(img1 - img0).max() > 1e-3
+    d2 = mb.cornell_box_heightfield(320)
+    d2["sensor"]["film"].update(width=96, height=96, rfilter={"type": "box"})
+    fresh = mb.load_dict(d2)
+    next(s for s in fresh.shapes if s.id == name).vertices = moved.copy()
+    img2 = mb.render(fresh, spp=8, seed=2)
+    assert np.array_equal(img1, img2)
+    mb.update_vertices(sc, name, orig)
+    assert np.array_equal(mb.render(sc, spp=8, seed=2), img0)
 
 
 def test_weighted_emitter_selection_matches_oracle(oracle_mod):
