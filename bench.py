@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--no-prb", action="store_true", help="skip the PRB gradient-step timing")
     ap.add_argument("--no-mi-render", action="store_true", help="skip the e2e leg through a live mi.render")
     args = ap.parse_args()
+    if os.environ.get("B200PT_HANG_DUMP"):      # debugging aid: python stacks of all threads after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200PT_HANG_DUMP"]), exit=False)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -57,6 +57,7 @@ struct b200pt_scene {
     uint32_t n_sm = 148;
     Launch launch;
     Wavefront wf;
+    int shade_blocks_per_sm = 8;
     // shard pixel list cache
     uint32_t *pix_ids = nullptr; uint32_t n_shard_pix = 0; uint32_t pix_key[3] = { ~0u, ~0u, ~0u };
     uint32_t *all_pix_ids = nullptr;   // identity list (whole frame; weights pre-pass of the gaussian adjoint)
@@ -183,6 +184,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     s->n_sm = (uint32_t) prop.multiProcessorCount;
     S_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     S_TRY(cudaEventCreate(&s->ev0)); S_TRY(cudaEventCreate(&s->ev1)); S_TRY(cudaEventCreate(&s->ev_stats));
+    { const char *e = getenv("B200PT_SHADE_BLOCKS_PER_SM"); s->shade_blocks_per_sm = e ? std::max(1, atoi(e)) : 8; }
     S_TRY(cudaMallocHost(&s->stats_host, ST_COUNT * sizeof(unsigned long long)));
     s->profile = getenv("B200PT_PROFILE") != nullptr;
 
@@ -396,6 +398,14 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     { const char *e = getenv("B200PT_TRACE_BLOCKS_PER_SM"); s->launch.grid = (int) s->n_sm * (e ? std::max(1, atoi(e)) : 5); }
     { const char *e = getenv("B200PT_DYNAMIC_FETCH"); s->launch.dynamic_fetch = e ? atoi(e) != 0 : true; }
     { const char *e = getenv("B200PT_REFILL_IDLE"); s->launch.refill_idle = e ? std::min(32, std::max(1, atoi(e))) : 8; }
+    {   // scenes of at most 32 leaves whose tree and triangles are staged whole: flat traversal (kernels.cu: traverse_flat)
+        uint32_t n_leaves = 0;
+        for (const auto &nd : bvh.nodes) { if (nd.left < 0) n_leaves++; if (nd.right < 0) n_leaves++; }
+        const char *e = getenv("B200PT_FLAT_TRAVERSAL");
+        s->launch.flat = (e ? atoi(e) != 0 : true) && n_leaves >= 1 && n_leaves <= 32 && s->launch.n_smem_nodes == d.n_nodes && s->launch.n_smem_tris == d.n_tris;
+        const char *g = getenv("B200PT_FLAT_BLOCKS_PER_SM");
+        s->launch.grid_flat = (int) s->n_sm * (g ? std::max(1, atoi(g)) : 4);
+    }
     set_trace_smem_attr(s->launch.smem_trace + s->launch.smem_tables);
     S_TRY(cudaMalloc(&s->stats_dev, ST_COUNT * sizeof(unsigned long long))); s->allocs.push_back(s->stats_dev);
     size_t npix = (size_t) d.crop_w * d.crop_h;
@@ -561,7 +571,7 @@ static b200pt_status run_chunk(b200pt_scene *s, RenderCfg cfg, int mode, cudaStr
     s->stats.kernel_launches++;
     Launch L = s->launch;
     L.grid = std::min<int>(s->launch.grid, (int) ((lanes + BLOCK - 1) / BLOCK)); if (L.grid < 1) L.grid = 1;
-    Launch Ls = L; Ls.grid = g_all;
+    Launch Ls = L; Ls.grid = (int) std::min<size_t>((size_t) g_all, (size_t) s->n_sm * (size_t) s->shade_blocks_per_sm);
     auto trace = [&](int bufi, const uint32_t *n_in, uint32_t *qcounts, bool first) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (s->profile) { e0 = next_trace_event(s); e1 = next_trace_event(s); cudaEventRecord(e0, st); }
@@ -622,21 +632,37 @@ static size_t wavefront_bytes_per_lane(const b200pt_scene *s, bool adjoint) {
     return per;
 }
 
+// Chunking of a call over `n_pix` pixels of this shard: equal chunks of at most 64 Mi lanes (fewest launches measured best,
+// profiles/r01_tuning.md), clamped to what the device can hold.
 static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p, uint32_t n_pix, bool adjoint) {
     size_t lanes = p->chunk_lanes;
-    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 26); }   // 64 Mi lanes (~26 GB of wavefront state): fewest launches, measured best (profiles/r01_tuning.md)
+    if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 26); }
     // never ask for more state than the device can hold next to what other users of the GPU (torch, NCCL) have taken:
     // the wavefront already allocated counts as available, 10 % of the free memory stays untouched
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         size_t per = wavefront_bytes_per_lane(s, adjoint);
-        bool have_adj = s->wf.cap && s->wf.buf[0].adj_L != nullptr;
-        size_t held = s->wf.cap * wavefront_bytes_per_lane(s, have_adj);
+        size_t held = s->wf.cap * wavefront_bytes_per_lane(s, s->wf.cap && s->wf.buf[0].adj_L != nullptr);
         size_t fit = (size_t) ((double) (free_b + held) * 0.9) / per;
         if (lanes > fit) lanes = std::max<size_t>(fit, 1024);
     }
     size_t px = std::max<size_t>(1, lanes / std::max(1u, p->spp));
-    return std::min<size_t>(px, std::max(1u, n_pix));
+    size_t n_chunks = (n_pix + px - 1) / px;                              // equal chunks: no short tail pass
+    return std::max<size_t>(1, (n_pix + n_chunks - 1) / std::max<size_t>(n_chunks, 1));
+}
+
+// Runs body(cfg of the chunk, pixels of the chunk) for every chunk of the shard, in order, on the caller's stream.
+template <typename Body>
+static b200pt_status for_each_chunk(b200pt_scene *s, const b200pt_render_params *p, RenderCfg cfg, bool adjoint, Body body) {
+    const size_t cpx = chunk_pixels(s, p, s->n_pix_ids, adjoint);
+    b200pt_status e = ensure_wavefront(s, cpx * p->spp, adjoint); if (e) return e;
+    for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
+        size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
+        cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p->spp);
+        e = body(cfg, npx); if (e) return e;
+    }
+    CU_TRY(cudaGetLastError());
+    return B200PT_OK;
 }
 
 static b200pt_status validate_params(const b200pt_scene *s, const b200pt_render_params *p) {
@@ -679,6 +705,9 @@ static b200pt_status resolve_stats(b200pt_scene *s) {
     for (size_t i = 0; i + 1 < s->trace_ev_used; i += 2) { float m = 0.f; if (cudaEventElapsedTime(&m, s->trace_events[i], s->trace_events[i + 1]) == cudaSuccess) tms += m; }
     s->stats.trace_ms = tms;
     s->stats_pending = false;
+#ifdef B200PT_WATCHDOG
+    { unsigned long long wd[4]; read_watchdog(wd); if (wd[0] | wd[1] | wd[2]) fprintf(stderr, "b200pt watchdog: mbarrier %llu, walk %llu, rounds %llu\n", wd[0], wd[1], wd[2]); }
+#endif
     return B200PT_OK;
 }
 
@@ -708,16 +737,13 @@ b200pt_status b200pt_render_accumulate(b200pt_scene *s, const b200pt_render_para
         return end_stats(s, st, 0);
     }
     RenderCfg cfg = make_cfg(s, p);
-    size_t cpx = chunk_pixels(s, p, s->n_pix_ids, false);
-    e = ensure_wavefront(s, cpx * p->spp, false); if (e) return e;
-    for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
-        size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
-        cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p->spp);
-        e = run_chunk(s, cfg, 0, st); if (e) return e;
-        launch_splat(s->dev, cfg, s->cur_pix_ids, s->wf.lane_result, film_device, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+    e = for_each_chunk(s, p, cfg, false, [&](const RenderCfg &c, size_t npx) -> b200pt_status {
+        b200pt_status e2 = run_chunk(s, c, 0, st); if (e2) return e2;
+        launch_splat(s->dev, c, s->cur_pix_ids, s->wf.lane_result, film_device, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : c.chunk_lanes), st);
         s->stats.kernel_launches++;
-    }
-    CU_TRY(cudaGetLastError());
+        return B200PT_OK;
+    });
+    if (e) return e;
     return end_stats(s, st, (uint64_t) s->n_pix_ids * p->spp);
 }
 
@@ -771,21 +797,17 @@ b200pt_status b200pt_render_backward_device(b200pt_scene *s, const b200pt_render
     }
     b200pt_status e = ensure_pix_ids(s, &p); if (e) return e;
     if (s->n_pix_ids == 0) return end_stats(s, st, 0);
-    size_t cpx = chunk_pixels(s, &p, s->n_pix_ids, true);
-    e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
-    for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
-        size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
-        cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
+    const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
+    e = for_each_chunk(s, &p, cfg, true, [&](const RenderCfg &c, size_t) -> b200pt_status {
         // pass 1: primal with the same stream (sampler.clone(), common.py:752) -> L per lane
-        const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
-        e = run_chunk(s, cfg, 0, st, use_vis); if (e) return e;
+        b200pt_status e2 = run_chunk(s, c, 0, st, use_vis); if (e2) return e2;
         // dL per lane: adjoint of splat + develop
-        launch_splat_adjoint(d, cfg, s->cur_pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, cfg.chunk_lanes), st);
+        launch_splat_adjoint(d, c, s->cur_pix_ids, grad_in_device, s->film_w, s->wf.lane_dL, grid_for(s, c.chunk_lanes), st);
         s->stats.kernel_launches++;
         // pass 2: adjoint replay (common.py:765)
-        e = run_chunk(s, cfg, 1, st, use_vis); if (e) return e;
-    }
-    CU_TRY(cudaGetLastError());
+        return run_chunk(s, c, 1, st, use_vis);
+    });
+    if (e) return e;
     return end_stats(s, st, (uint64_t) s->n_pix_ids * p.spp);
 }
 
@@ -814,17 +836,15 @@ b200pt_status b200pt_render_forward(b200pt_scene *s, const b200pt_render_params 
     begin_stats(s, st);
     if (p.max_depth != 0 && s->n_pix_ids != 0) {
         RenderCfg cfg = make_cfg(s, &p);
-        size_t cpx = chunk_pixels(s, &p, s->n_pix_ids, true);
-        e = ensure_wavefront(s, cpx * p.spp, true); if (e) return e;
-        for (size_t pix0 = 0; pix0 < s->n_pix_ids; pix0 += cpx) {
-            size_t npx = std::min<size_t>(cpx, s->n_pix_ids - pix0);
-            cfg.chunk_pix0 = (uint32_t) pix0; cfg.chunk_lanes = (uint32_t) (npx * p.spp);
-            const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
-            e = run_chunk(s, cfg, 0, st, use_vis); if (e) return e;      // primal: L per lane (+ NEE visibility bits)
-            e = run_chunk(s, cfg, 2, st, use_vis); if (e) return e;      // forward replay: dL per lane
-            launch_splat(s->dev, cfg, s->cur_pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : cfg.chunk_lanes), st);
+        const bool use_vis = cfg.max_depth <= 32 && !getenv("B200PT_INLINE_VISIBILITY");
+        e = for_each_chunk(s, &p, cfg, true, [&](const RenderCfg &c, size_t npx) -> b200pt_status {
+            b200pt_status e2 = run_chunk(s, c, 0, st, use_vis); if (e2) return e2;      // primal: L per lane (+ NEE visibility bits)
+            e2 = run_chunk(s, c, 2, st, use_vis); if (e2) return e2;                     // forward replay: dL per lane
+            launch_splat(s->dev, c, s->cur_pix_ids, s->wf.lane_result, s->film_own, grid_for(s, s->dev.rfilter == B200PT_RFILTER_BOX ? npx * 32 : c.chunk_lanes), st);
             s->stats.kernel_launches++;
-        }
+            return B200PT_OK;
+        });
+        if (e) return e;
     }
     e = end_stats(s, st, (uint64_t) s->n_pix_ids * p.spp); if (e) return e;
     e = b200pt_develop(s, s->film_own, s->out_dev, st); if (e) return e;

@@ -41,16 +41,21 @@ PT_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#ifdef B200PT_WATCHDOG
+// debugging build only: counters of loops that ran past any plausible bound (0: mbarrier wait, 1: BVH walk of one ray, 2: rounds of a warp)
+__device__ unsigned long long g_watchdog[4];
+#endif
 PT_DEV void mbar_wait(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+    uint32_t done = 0;
+#ifdef B200PT_WATCHDOG
+    uint32_t spins = 0;
+#endif
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+#ifdef B200PT_WATCHDOG
+        if (++spins > (1u << 22)) { atomicAdd(&g_watchdog[0], 1ull); break; }
+#endif
+    }
 }
 
 // Stage `n_nodes` BVH nodes (64 B each) and `n_tris` triangles (48 B each) into
@@ -66,6 +71,11 @@ PT_DEV void stage_bvh(const DevScene &sc, float4 *s_nodes, float4 *s_tris, uint3
         for (uint32_t off = 0; off < tb; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, tb - off), bar);
     }
     mbar_wait(bar, 0);
+    // Every thread must have seen phase 0 complete before thread 0 arms phase 1 (stage_tables): a thread that still polls
+    // parity 0 after phase 1 has completed as well waits for phase 2, which nobody arms -- the block spins forever. It takes
+    // a busy SM to delay a warp that long (blocks that become resident while other blocks keep the issue slots busy:
+    // grids larger than one wave, kernels of another stream); measured as hangs, profiles/r02_summary.md.
+    __syncthreads();
 }
 
 // Scene tables (shapes, BSDFs, emitters, textures) and -- for small scenes -- the shading
@@ -125,15 +135,27 @@ PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
 
 PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
 
-// slab test, subtraction first (no cancellation against o * inv)
-PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, float3 o, float3 inv, float tmax, float &tnear) {
-    float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
-    float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
-    float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+// Slab test in fused form: t = lo * inv - (o * inv), one FFMA per plane instead of a subtraction and a multiplication.
+// The product o * inv is rounded once per ray, so a plane distance is off by up to 2^-24 |o * inv| against the exact
+// (lo - o) * inv; `slack` = 2^-22 max |o * inv| (RaySlabs::slack) widens the interval test by more than twice that. The
+// boxes only cull -- a hit is only ever decided by the reference's Moeller-Trumbore arithmetic -- so a wider test costs
+// node visits (rays almost parallel to an axis stop culling on it), never a result.
+struct RaySlabs { float3 inv, oi; float slack; };
+PT_DEV RaySlabs make_slabs(float3 o, float3 d) {
+    RaySlabs r;
+    r.inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    r.oi = V(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+    r.slack = fmaxf(fmaxf(fabsf(r.oi.x), fabsf(r.oi.y)), fabsf(r.oi.z)) * 2.3841858e-7f;
+    return r;
+}
+PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, const RaySlabs &r, float tmax, float &tnear) {
+    float t0x = __fmaf_rn(lox, r.inv.x, -r.oi.x), t1x = __fmaf_rn(hix, r.inv.x, -r.oi.x);
+    float t0y = __fmaf_rn(loy, r.inv.y, -r.oi.y), t1y = __fmaf_rn(hiy, r.inv.y, -r.oi.y);
+    float t0z = __fmaf_rn(loz, r.inv.z, -r.oi.z), t1z = __fmaf_rn(hiz, r.inv.z, -r.oi.z);
     float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
     float tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
     tnear = tmin;
-    return tmin <= tmx * 1.0000004f;
+    return tmin <= __fmaf_rn(tmx, 1.0000004f, r.slack);
 }
 
 // Speculative while-while traversal (Aila & Laine, "Understanding the Efficiency of Ray
@@ -146,7 +168,7 @@ constexpr int32_t TRAV_SENTINEL = 0x76543210;
 template <bool ANY, bool SMEM_ALL>
 PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit) {
     hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
-    float3 inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    const RaySlabs rs = make_slabs(o, d);
     int32_t stack[64]; stack[0] = TRAV_SENTINEL; int sp = 0;
     int32_t node = 0, leaf = 0;     // leaf >= 0: none postponed
     bool any = false;
@@ -158,8 +180,8 @@ PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit
             float tl, tr;
             // both slab tests are evaluated unconditionally (no short-circuit branches); the
             // "no child" marker only exists in the synthetic root of a <= 2-triangle scene
-            bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
-            bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
+            bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rs, maxt, tl) & (cl != 0x7fffffff);
+            bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rs, maxt, tr) & (cr != 0x7fffffff);
             if (!hl && !hr) node = stack[sp--];
             else {
                 node = hl ? cl : cr;
@@ -186,6 +208,70 @@ PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit
             }
             leaf = node;
             if (node < 0) node = stack[sp--];
+        }
+    }
+    return any;
+}
+
+// ---------------------------------------------------------------------------
+// Flat traversal for scenes of at most FLAT_MAX_LEAVES leaves (the Cornell box: 36 triangles in 18+ leaves). In a closed
+// room the top of a binary tree culls nothing -- every inner box near the root spans the room -- so a walk spends ~10
+// divergent node steps per ray before it reaches the two or three leaves that matter. Here every lane tests the boxes of
+// ALL leaves in the same order instead (one broadcast LDS pair and ~16 arithmetic instructions per leaf, 32 of 32 threads
+// active, no stack), keeps the hit boxes as a bit mask, and then runs the reference's Moeller-Trumbore on the candidate
+// leaves only: the nearest box first, the others re-tested against the shortened ray. Results are those of any other
+// traversal order: closest hit with ties resolved towards the smaller primitive index, any-hit a boolean.
+// ---------------------------------------------------------------------------
+constexpr uint32_t FLAT_MAX_LEAVES = 32;
+
+// Leaf list from the staged nodes: every negative child of an inner node is a leaf; entry l = { (lo.xyz, hi.x), (hi.yz, leaf code, -) }.
+PT_DEV void build_leaf_list(const float4 *s_nodes, uint32_t n_nodes, float4 *s_leaf, uint32_t *s_nleaf) {
+    if (threadIdx.x == 0) *s_nleaf = 0;
+    __syncthreads();
+    for (uint32_t node = threadIdx.x; node < n_nodes; node += blockDim.x) {
+        float4 n0 = s_nodes[4 * node], n1 = s_nodes[4 * node + 1], n2 = s_nodes[4 * node + 2], n3 = s_nodes[4 * node + 3];
+        int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+        if (cl < 0) { uint32_t k = atomicAdd(s_nleaf, 1u); if (k < FLAT_MAX_LEAVES) { s_leaf[2 * k] = make_float4(n0.x, n0.y, n0.z, n0.w); s_leaf[2 * k + 1] = make_float4(n1.x, n1.y, __int_as_float(~cl), 0.f); } }
+        if (cr < 0) { uint32_t k = atomicAdd(s_nleaf, 1u); if (k < FLAT_MAX_LEAVES) { s_leaf[2 * k] = make_float4(n1.z, n1.w, n2.x, n2.y); s_leaf[2 * k + 1] = make_float4(n2.z, n2.w, __int_as_float(~cr), 0.f); } }
+    }
+    __syncthreads();
+}
+
+template <bool ANY>
+PT_DEV bool traverse_flat(const float4 *s_leaf, uint32_t n_leaves, const float4 *s_tris, float3 o, float3 d, float maxt, Hit &hit) {
+    hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
+    const RaySlabs rs = make_slabs(o, d);
+    uint32_t mask = 0; float best_tn = PT_INF; uint32_t best = 0;
+#pragma unroll 3
+    for (uint32_t l = 0; l < n_leaves; ++l) {
+        float4 a = s_leaf[2 * l], b = s_leaf[2 * l + 1];
+        float tn;
+        if (box_hit(a.x, a.y, a.z, a.w, b.x, b.y, rs, maxt, tn)) {
+            mask |= 1u << l;
+            if (!ANY && tn < best_tn) { best_tn = tn; best = l; }
+        }
+    }
+    bool any = false;
+    bool first = !ANY && mask != 0;           // closest hit: the nearest box goes first
+    while (mask) {
+        uint32_t l;
+        if (first) l = best; else l = (uint32_t) __ffs((int) mask) - 1u;
+        mask &= ~(1u << l);
+        float4 b = s_leaf[2 * l + 1];
+        if (!ANY && any) {                     // the ray has been shortened since the box pass
+            float4 a = s_leaf[2 * l]; float tn;
+            if (!box_hit(a.x, a.y, a.z, a.w, b.x, b.y, rs, maxt, tn)) continue;
+        }
+        first = false;
+        uint32_t enc = __float_as_uint(b.z), t0 = enc >> 3, count = (enc & 7u) + 1u;
+        for (uint32_t i = t0; i < t0 + count; ++i) {
+            float4 ta = s_tris[3 * i], tb = s_tris[3 * i + 1], te = s_tris[3 * i + 2];
+            float t, u, v;
+            if (moeller_trumbore(o, d, maxt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
+                if (ANY) return true;
+                uint32_t prim = __float_as_uint(ta.w);
+                if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; maxt = t; any = true; }
+            }
         }
     }
     return any;
@@ -228,8 +314,8 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
 //      into the queue of the BSDF model it hit; a miss ends the path
 //   3. finished lanes write their radiance to lane_result (consumed by k_splat)
 // ---------------------------------------------------------------------------
-template <bool FIRST, bool SMEM_ALL>
-__global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
+template <bool FIRST, bool SMEM_ALL, bool FLAT>
+__global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
                                                  Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -242,6 +328,11 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
     stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
     TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+    __shared__ float4 s_leaf[FLAT ? 2 * FLAT_MAX_LEAVES : 1];
+    __shared__ uint32_t s_nleaf;
+    if (FLAT) build_leaf_list(s_nodes, n_smem_nodes, s_leaf, &s_nleaf);
+    const uint32_t n_leaves = FLAT ? min(s_nleaf, FLAT_MAX_LEAVES) : 0u;
+    auto closest = [&](float3 o, float3 d, float maxt, Hit &h) { return FLAT ? traverse_flat<false>(s_leaf, n_leaves, s_tris, o, d, maxt, h) : traverse<false, SMEM_ALL>(ctx, o, d, maxt, h); };
 
     const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
     const uint32_t lane_id = threadIdx.x & 31u;
@@ -258,7 +349,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
             if (!FIRST && (flags & PF_HAS_SHADOW)) {
                 float4 so = cur.sh_o[i], sd = cur.sh_d[i];
                 Hit h; n_shadow++;
-                bool occluded = traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
+                bool occluded = FLAT ? traverse_flat<true>(s_leaf, n_leaves, s_tris, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h) : traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
                 if (!occluded) {
                     if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[i].w] |= 1u << bit; }
                     float2 c = cur.sh_c[i];
@@ -273,7 +364,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                 float3 o = V(ro.x, ro.y, ro.z), d = V(rd.x, rd.y, rd.z);
                 float maxt = ro.w;
                 Hit h; n_closest++;
-                bool found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
+                bool found = closest(o, d, maxt, h);
                 if (FIRST && cfg.hide_emitters) {
                     // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
                     while (found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0) {
@@ -281,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScen
                         Ray r = spawn_ray(si.p, si.n, d);
                         o = r.o; maxt = r.maxt;
                         cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
-                        found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
+                        found = closest(o, d, maxt, h);
                     }
                 }
                 if (found) {
@@ -337,37 +428,57 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                                                      float4 *__restrict__ lane_result, unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris, int DYN_REFILL_IDLE) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    __shared__ uint32_t s_pool_open;
     DevScene sc = sc_in;
     float4 *s_nodes = (float4 *) smem_raw;
     float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        // a block that becomes resident late (another stream's kernels held the SM) finds the pool already claimed: it
+        // leaves before staging anything
+        s_pool_open = *(volatile uint32_t *) work_counter < n ? 1u : 0u;
+    }
     __syncthreads();
+    if (!s_pool_open) return;
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
     stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
     TraceCtx c = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
 
-    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
     const uint32_t lane_id = threadIdx.x & 31u;
     uint32_t n_shadow = 0, n_closest = 0;
 
     // job state of this lane
     int kind = 0;                     // 0 idle, 1 shadow ray, 2 path ray
     uint32_t slot = 0, flags = 0;
-    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
+    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f);
+    RaySlabs rs; rs.inv = rs.oi = V(0.f, 0.f, 0.f); rs.slack = 0.f;
     float maxt = 0.f;
     Hit hit; hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
     int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
     bool occluded = false;
     bool exhausted = false;           // the global pool is empty
+#ifdef B200PT_WATCHDOG
+    uint32_t wd_steps = 0;
+#endif
 
     auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
         o = ro; d = rd; maxt = rmaxt;
-        inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+        rs = make_slabs(o, d);
         hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
         stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf = 0; occluded = false;
+#ifdef B200PT_WATCHDOG
+        wd_steps = 0;
+#endif
     };
+#ifdef B200PT_WATCHDOG
+    uint32_t wd_rounds = 0;
+#endif
 
     while (true) {
+#ifdef B200PT_WATCHDOG
+        if (++wd_rounds > (1u << 24)) { if (lane_id == 0) atomicAdd(&g_watchdog[2], 1ull); break; }
+#endif
         // ---- refill idle lanes from the global pool --------------------------------------
         uint32_t idle_mask = __ballot_sync(0xffffffffu, kind == 0);
         if (!exhausted && (__popc(idle_mask) >= DYN_REFILL_IDLE)) {
@@ -396,6 +507,8 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
         if (!__any_sync(0xffffffffu, kind != 0)) break;
 
         // ---- traverse until this lane's ray is done or the warp wants to refill -----------
+        // (lanes run these loops divergently on purpose: with a full-mask vote per node step -- measured, profiles/r02_summary.md --
+        //  every step waits for the slowest lane's node fetch, 11 % slower on the 205k-triangle scene whose nodes come from L2)
         if (kind != 0) {
             while (node != TRAV_SENTINEL) {
                 bool searching = true;
@@ -403,8 +516,8 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                     float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
                     int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                     float tl, tr;
-                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
-                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
+                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rs, maxt, tl) & (cl != 0x7fffffff);
+                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rs, maxt, tr) & (cr != 0x7fffffff);
                     if (!hl && !hr) node = stack[sp--];
                     else {
                         node = hl ? cl : cr;
@@ -415,6 +528,9 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                         }
                     }
                     if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[sp--]; }
+#ifdef B200PT_WATCHDOG
+                    if (++wd_steps > 200000u) { atomicAdd(&g_watchdog[1], 1ull); node = TRAV_SENTINEL; leaf = 0; wd_steps = 0; }
+#endif
                     if (!__any_sync(__activemask(), searching)) break;
                 }
                 while (leaf < 0) {
@@ -1069,7 +1185,7 @@ __global__ void __launch_bounds__(BLOCK) k_develop(uint32_t n_pix, const float *
 template <bool ANY>
 __global__ void __launch_bounds__(BLOCK) k_ray_query(DevScene sc, uint32_t n, const float *__restrict__ rays, float *__restrict__ t_out, float *__restrict__ uv_out,
                                                      uint32_t *__restrict__ prim_out, int32_t *__restrict__ shape_out, uint8_t *__restrict__ occ_out,
-                                                     uint32_t n_smem_nodes, uint32_t n_smem_tris) {
+                                                     uint32_t n_smem_nodes, uint32_t n_smem_tris, bool flat) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     float4 *s_nodes = (float4 *) smem_raw;
@@ -1078,10 +1194,14 @@ __global__ void __launch_bounds__(BLOCK) k_ray_query(DevScene sc, uint32_t n, co
     __syncthreads();
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
     TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
+    __shared__ float4 s_leaf[2 * FLAT_MAX_LEAVES];
+    __shared__ uint32_t s_nleaf;
+    if (flat) build_leaf_list(s_nodes, n_smem_nodes, s_leaf, &s_nleaf);     // the traversal the render kernels use for this scene
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float *r = rays + 7 * (size_t) i;
         Hit h;
-        bool found = traverse<ANY, false>(ctx, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h);
+        bool found = flat ? traverse_flat<ANY>(s_leaf, min(s_nleaf, FLAT_MAX_LEAVES), s_tris, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h)
+                          : traverse<ANY, false>(ctx, V(r[0], r[1], r[2]), V(r[3], r[4], r[5]), r[6], h);
         if (ANY) { occ_out[i] = found ? 1 : 0; continue; }
         t_out[i] = found ? h.t : PT_INF; uv_out[2 * i] = found ? h.u : 0.f; uv_out[2 * i + 1] = found ? h.v : 0.f;
         if (found) {
@@ -1106,6 +1226,14 @@ __global__ void k_bsdf_eval(DevScene sc, uint32_t bsdf, uint32_t n, const float 
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
+void read_watchdog(unsigned long long out[4]) {
+#ifdef B200PT_WATCHDOG
+    cudaMemcpyFromSymbol(out, g_watchdog, sizeof(unsigned long long) * 4);
+#else
+    out[0] = out[1] = out[2] = out[3] = 0;
+#endif
+}
+
 void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *pix_ids, PathBuf buf, const float4 *adj_dL_lane,
                      const float4 *adj_L_lane, int grid, cudaStream_t st) {
     k_generate<<<grid, BLOCK, 0, st>>>(sc, cfg, pix_ids, buf, adj_dL_lane, adj_L_lane);
@@ -1114,6 +1242,12 @@ void launch_generate(const DevScene &sc, const RenderCfg &cfg, const uint32_t *p
 void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 *hit, const uint32_t *n_in, Queues q, uint32_t *qcounts,
                   float4 *lane_result, unsigned long long *stats, bool first, const Launch &L, cudaStream_t st) {
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
+    if (L.flat) {       // <= FLAT_MAX_LEAVES leaves: every lane tests every leaf box, no tree walk (see traverse_flat)
+        int grid = L.grid_flat;
+        if (first) k_trace<true, true, true><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+        else k_trace<false, true, true><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+        return;
+    }
     if (L.dynamic_fetch) {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
         if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
@@ -1121,7 +1255,7 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
 #undef LAUNCH_DYN
         return;
     }
-#define LAUNCH_TRACE(F, A) k_trace<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
+#define LAUNCH_TRACE(F, A) k_trace<F, A, false><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
     if (first) { if (all) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
     else { if (all) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
 #undef LAUNCH_TRACE
@@ -1261,10 +1395,10 @@ void launch_develop(const DevScene &sc, const float *film, float *out, cudaStrea
 }
 
 void launch_ray_intersect(const DevScene &sc, uint32_t n, const float *rays, float *t, float *uv, uint32_t *prim, int32_t *shape, const Launch &L, cudaStream_t st) {
-    k_ray_query<false><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, t, uv, prim, shape, nullptr, L.n_smem_nodes, L.n_smem_tris);
+    k_ray_query<false><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, t, uv, prim, shape, nullptr, L.n_smem_nodes, L.n_smem_tris, L.flat);
 }
 void launch_ray_test(const DevScene &sc, uint32_t n, const float *rays, uint8_t *hit, const Launch &L, cudaStream_t st) {
-    k_ray_query<true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, nullptr, nullptr, nullptr, nullptr, hit, L.n_smem_nodes, L.n_smem_tris);
+    k_ray_query<true><<<L.grid, BLOCK, L.smem_trace, st>>>(sc, n, rays, nullptr, nullptr, nullptr, nullptr, hit, L.n_smem_nodes, L.n_smem_tris, L.flat);
 }
 void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, const float *in, float *out, cudaStream_t st) {
     int grid = (int) ((n + 127) / 128); if (grid < 1) grid = 1;
@@ -1291,10 +1425,12 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);

@@ -59,6 +59,7 @@ constexpr int BLOCK = 256;
 constexpr int BLOCK_SHADE = 128;   // shading kernels: 128 threads x <=128 registers -> 4 blocks / SM
 
 struct Launch { int grid; size_t smem_trace, smem_tables; uint32_t n_smem_nodes, n_smem_tris; bool dynamic_fetch; int refill_idle;
+    bool flat; int grid_flat;      // scenes of <= 32 leaves: flat traversal (kernels.cu: traverse_flat), its own grid
 };
 
 // counters in the stats buffer
@@ -83,6 +84,7 @@ void launch_develop(const DevScene &sc, const float *film, float *out, cudaStrea
 void launch_ray_intersect(const DevScene &sc, uint32_t n, const float *rays, float *t, float *uv, uint32_t *prim, int32_t *shape, const Launch &L, cudaStream_t st);
 void launch_ray_test(const DevScene &sc, uint32_t n, const float *rays, uint8_t *hit, const Launch &L, cudaStream_t st);
 void set_trace_smem_attr(size_t bytes);
+void read_watchdog(unsigned long long out[4]);   // debugging builds (-DB200PT_WATCHDOG); zeros otherwise
 void launch_bsdf_eval(const DevScene &sc, uint32_t bsdf, int type, uint32_t n, const float *in, float *out, cudaStream_t st);
 
 } // namespace pt

@@ -35,6 +35,113 @@ def _np(x, dtype=np.float32):
     return np.array(x, dtype=dtype)
 
 
+def _f(x) -> float:
+    """A scalar parameter as a Python float: JIT variants hand out width-1 Dr.Jit arrays where scalar variants hand out floats."""
+    return float(np.array(x, dtype=np.float64).reshape(-1)[0])
+
+
+# ---- state that neither mi.traverse nor to_string expose: recovered by probing the live object ------------------------
+def _wrap_index(i, n, wrap):
+    """dr::tex_wrap (drjit/texture_impl.h:85-104) for integer texel coordinates."""
+    i = np.asarray(i, np.int64)
+    if wrap == abi.WRAP_CLAMP:
+        return np.clip(i, 0, n - 1)
+    shift = np.where(i < 0, i + 1, i)
+    div = np.trunc(shift / n).astype(np.int64)          # C++ integer division truncates
+    mod = i - div * n
+    mod = np.where(mod < 0, mod + n, mod)
+    if wrap == abi.WRAP_MIRROR:
+        mod = np.where(((div & 1) == 0) ^ (i < 0), mod, n - 1 - mod)
+    return mod
+
+
+def _bitmap_eval_host(data, uv, wrap, filt):
+    """BitmapTexture::eval on raw float data (bitmap.cpp:496-519 + dr::Texture::eval, texture_impl.h:156-205), float64 --
+    only used to tell the wrap / filter modes of a live texture apart."""
+    h, w = data.shape[:2]
+    x, y = uv[:, 0] * w, uv[:, 1] * h
+    if filt == abi.FILTER_NEAREST:
+        ix, iy = _wrap_index(np.floor(x), w, wrap), _wrap_index(np.floor(y), h, wrap)
+        return data[iy, ix].astype(np.float64)
+    x, y = x - 0.5, y - 0.5
+    x0, y0 = np.floor(x), np.floor(y)
+    wx, wy = (x - x0)[:, None], (y - y0)[:, None]
+    ix0, ix1 = _wrap_index(x0, w, wrap), _wrap_index(x0 + 1, w, wrap)
+    iy0, iy1 = _wrap_index(y0, h, wrap), _wrap_index(y0 + 1, h, wrap)
+    d = data.astype(np.float64)
+    return (d[iy0, ix0] * (1 - wx) + d[iy0, ix1] * wx) * (1 - wy) + (d[iy1, ix0] * (1 - wx) + d[iy1, ix1] * wx) * wy
+
+
+def _probe_bitmap_modes(mi, tex_obj, data, to_uv):
+    """`wrap_mode` and `filter_type` of a BitmapTexture are construction-time properties that appear neither among its
+    traversed parameters nor in its string form (bitmap.cpp:842-850): evaluate the live texture at positions outside the
+    unit square and off the texel centres and keep the combination of modes that reproduces every value. Ambiguity
+    (a constant image, say) is harmless -- every surviving combination then renders the same values at the probes --
+    but no surviving combination is an error, not a guess."""
+    rs = np.random.RandomState(7)
+    uv = np.concatenate([rs.uniform(-1.3, 2.3, (24, 2)), rs.uniform(0.02, 0.98, (8, 2))]).astype(np.float32)
+    uvt = uv.astype(np.float64) @ np.asarray(to_uv, np.float64)[:2, :2].T + np.asarray(to_uv, np.float64)[:2, 2]
+    got = np.zeros((uv.shape[0], data.shape[2]))
+    for k in range(uv.shape[0]):
+        si = mi.SurfaceInteraction3f()
+        si.uv = mi.Point2f(float(uv[k, 0]), float(uv[k, 1]))
+        si.t = 1.0
+        if data.shape[2] == 1:
+            got[k, 0] = float(np.array(tex_obj.eval_1(si)).reshape(-1)[0])
+        else:
+            got[k] = np.array(tex_obj.eval(si), dtype=np.float64).reshape(-1)[:data.shape[2]]
+    scale = max(1e-6, float(np.abs(data).max()))
+    fits = [(wrap, filt) for wrap in (abi.WRAP_REPEAT, abi.WRAP_CLAMP, abi.WRAP_MIRROR) for filt in (abi.FILTER_BILINEAR, abi.FILTER_NEAREST)
+            if np.abs(_bitmap_eval_host(data, uvt, wrap, filt) - got).max() <= 2e-4 * scale]
+    if not fits:
+        raise NotImplementedError("bitmap texture: its values match none of the repeat/clamp/mirror x bilinear/nearest modes "
+                                  "(sRGB-encoded 8-bit storage, spectral upsampling or a cubic filter are outside the hot-path scope)")
+    return fits[0]
+
+
+def _probe_envmap_mis_compensation(mi, em, data, to_world):
+    """`mis_compensation` (envmap.cpp:196,498-517) is not exposed either. It subtracts the mean luminance from the sampling
+    density, so the RATIO of pdf_direction between two texel centres of one image row tells it apart (the row's
+    sin(theta) and the normalisation cancel): lum_a / lum_b without, max(lum_a - mean, 0) / max(lum_b - mean, 0) with it."""
+    d = np.asarray(data, np.float64)                           # without the halo columns
+    lum = d @ np.array([0.212671, 0.715160, 0.072169])
+    h, w = lum.shape
+    mean, mn = lum.mean(), lum.min()
+    if mean - mn <= 0.01 * mean:
+        return False                                           # the emitter disables the compensation itself (envmap.cpp:515)
+    best = None
+    for y in range(1, h - 1):
+        a, b = int(np.argmax(lum[y])), int(np.argmin(lum[y]))
+        la, lb = lum[y, a], lum[y, b]
+        if la <= 0 or la == lb:
+            continue
+        plain, comp = lb / la, max(lb - mean, 0.0) / max(la - mean, 1e-30) if la > mean else None
+        if comp is None or abs(plain - comp) < 0.05:
+            continue
+        if best is None or abs(plain - comp) > best[0]:
+            best = (abs(plain - comp), y, a, b, plain, comp)
+    if best is None:
+        raise NotImplementedError("envmap: cannot tell whether mis_compensation is set from this image (no row with two texels of "
+                                  "sufficiently different luminance)")
+    _, y, a, b, plain, comp = best
+    tw = np.asarray(to_world, np.float64)[:3, :3]
+
+    def pdf_at(x):
+        # vertex (x, y) of the sampling grid (envmap.cpp:366-384,436-447,519-527: columns are texel-centred in phi, rows
+        # align-corners in theta) -> direction d = (sin phi sin theta, cos theta, -cos phi sin theta)
+        theta, phi = y / (h - 1) * np.pi, (x + 0.5) / w * 2 * np.pi
+        dl = np.array([np.sin(phi) * np.sin(theta), np.cos(theta), -np.cos(phi) * np.sin(theta)])
+        dw = tw @ dl
+        it = mi.Interaction3f(); it.p = mi.Point3f(0, 0, 0); it.t = 0.0
+        ds = mi.DirectionSample3f(); ds.d = mi.Vector3f(float(dw[0]), float(dw[1]), float(dw[2]))
+        return float(np.array(em.pdf_direction(it, ds)).reshape(-1)[0])
+    pa, pb = pdf_at(a), pdf_at(b)
+    if not pa > 0:
+        raise NotImplementedError("envmap: pdf_direction probe returned zero at the brightest texel of a row")
+    r = pb / pa
+    return abs(r - comp) < abs(r - plain)
+
+
 class _Extractor:
     def __init__(self, mi, scene, sensor):
         self.mi, self.scene_mi = mi, scene
@@ -61,6 +168,11 @@ class _Extractor:
             t.name = name + ".data"
             if f"{prefix}{key}.to_uv" in params:
                 t.to_uv = _np(params[f"{prefix}{key}.to_uv"].matrix).reshape(3, 3)
+            # wrap_mode / filter_type: from the live texture object that owns the parameter (SceneParameters.properties)
+            node = params.properties[k_data][2] if hasattr(params, "properties") else None
+            if node is None or not hasattr(node, "eval"):
+                raise NotImplementedError(f"bitmap texture {name}: the texture object is not reachable, its wrap / filter modes are unknown")
+            t.wrap, t.filter = _probe_bitmap_modes(self.mi, node, t.data, t.to_uv if t.to_uv is not None else np.eye(3, dtype=f32))
         elif default is not None:
             t.value = np.full(3, default, f32); t.name = name + ".value"
         else:
@@ -79,9 +191,12 @@ class _Extractor:
         prefix, twosided = "", False
         if cls in ("TwoSidedBRDF", "TwoSided"):
             twosided, prefix = True, "brdf_0."
-            inner = [k for k in params.keys() if k.startswith("brdf_0.")]
-            cls = self._guess_class(inner)
             desc = str(b)
+            import re
+            m = re.search(r"brdf\[0\]\s*=\s*(\w+)\[", desc)      # twosided.cpp to_string: the nested plugin's class name
+            if not m:
+                raise NotImplementedError("twosided: cannot read the nested BRDF's class from its string form")
+            cls = m.group(1)
         else:
             desc = str(b)
         if cls not in _BSDF_CLASS:
@@ -98,14 +213,14 @@ class _Extractor:
             else:
                 d.tex[abi.SLOT_SPEC_REFL] = T("specular_reflectance", 3, 1.0)
         elif d.type == abi.BSDF_DIELECTRIC:
-            d.eta = float(params[f"{prefix}eta"])
+            d.eta = _f(params[f"{prefix}eta"])
             d.tex[abi.SLOT_D_SPEC_REFL] = T("specular_reflectance", 3)
             d.tex[abi.SLOT_D_SPEC_TRANS] = T("specular_transmittance", 3)
             if cls == "RoughDielectric":
                 self._microfacet(d, desc, T, abi.SLOT_D_ALPHA_U, abi.SLOT_D_ALPHA_V)
         elif d.type == abi.BSDF_PLASTIC:
             import re
-            d.eta = float(params[f"{prefix}eta"])
+            d.eta = _f(params[f"{prefix}eta"])
             d.tex[abi.SLOT_PL_DIFFUSE] = T("diffuse_reflectance", 3, 0.5)
             d.tex[abi.SLOT_PL_SPEC_REFL] = T("specular_reflectance", 3)
             # derived members (plastic.cpp:196-208) as the plugin reports them (to_string, plastic.cpp:382-398)
@@ -127,13 +242,13 @@ class _Extractor:
                 if flag and (t.kind == abi.TEX_BITMAP or float(t.value[0]) != 0.0):
                     flags |= flag           # m_has_* (principledhelpers.h get_flag): a zero constant == lobe off
             if f"{prefix}eta" in params:
-                d.eta = float(params[f"{prefix}eta"]); flags |= abi.P_ETA_SPECULAR
+                d.eta = _f(params[f"{prefix}eta"]); flags |= abi.P_ETA_SPECULAR
             else:
-                spec = f32(float(params[f"{prefix}specular"]))
+                spec = f32(_f(params[f"{prefix}specular"]))
                 d.eta = float(f32(2) * (f32(1) / (f32(1) - np.sqrt(f32(0.08) * spec, dtype=f32))) - f32(1))
-            d.spec_srate = float(params[f"{prefix}main_specular_sampling_rate"])
-            d.clearcoat_srate = float(params[f"{prefix}clearcoat_sampling_rate"])
-            d.diff_refl_srate = float(params[f"{prefix}diffuse_reflectance_sampling_rate"])
+            d.spec_srate = _f(params[f"{prefix}main_specular_sampling_rate"])
+            d.clearcoat_srate = _f(params[f"{prefix}clearcoat_sampling_rate"])
+            d.diff_refl_srate = _f(params[f"{prefix}diffuse_reflectance_sampling_rate"])
             d.flags = flags
         self.out.bsdfs.append(d)
         self.bsdf_index[key] = len(self.out.bsdfs) - 1
@@ -159,17 +274,6 @@ class _Extractor:
             d.tex[slot_u], d.tex[slot_v] = T("alpha_u", 1), T("alpha_v", 1)
             raise NotImplementedError("anisotropic BSDFs need packed tangent frames, which are outside the hot-path scope")
 
-    @staticmethod
-    def _guess_class(keys):
-        ks = " ".join(keys)
-        if "base_color" in ks: return "Principled"
-        if "diffuse_reflectance" in ks: return "SmoothPlastic"
-        if "alpha" in ks and ".k." in ks: return "RoughConductor"
-        if "alpha" in ks: return "RoughDielectric"
-        if "specular_transmittance" in ks or ".eta" in ks and ".k" not in ks and "reflectance.value" not in ks: return "SmoothDielectric"
-        if ".k." in ks: return "SmoothConductor"
-        return "SmoothDiffuse"
-
     # ---- shapes / emitters ---------------------------------------------------------------
     def shapes(self):
         mi = self.mi
@@ -194,7 +298,7 @@ class _Extractor:
                 sh.emitter = self._emitter_slot(s.emitter())
                 self.out.emitters[sh.emitter] = EmitterData(
                     shape=len(self.out.shapes), radiance_tex=rad,
-                    sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
+                    sampling_weight=_f(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
                 sp = mi.traverse(s)
                 if "to_world" in sp and verts.shape[0] == 4 and faces.shape[0] == 2:
                     # Rectangle: sampled by its parameterisation (rectangle.cpp:159-172)
@@ -223,11 +327,18 @@ class _Extractor:
             raise NotImplementedError(f"rfilter {rf.class_name()} is outside the hot-path scope")
         if film.sample_border():
             raise NotImplementedError("sample_border is outside the hot-path scope")
+        sampler = se.sampler()
+        if sampler.class_name() != "IndependentSampler":
+            raise NotImplementedError(f"sampler {sampler.class_name()}: only `independent` (PCG32 streams, sampler.cpp:129-148) is on the hot path")
+        import re
+        m = re.search(r"base_seed\s*=\s*(\d+)", str(sampler))
+        if not m:
+            raise NotImplementedError("independent sampler: cannot read base_seed from its string form")
         self.out.sensor = SensorData(
             sample_to_camera=_np(proj.inverse().matrix), to_world=_np(p["to_world"].matrix),
-            near_clip=float(p["near_clip"]), far_clip=float(p["far_clip"]), film_size=tuple(size), crop_size=tuple(crop),
-            crop_offset=tuple(off), rfilter=rfilter, rfilter_stddev=stddev, base_seed=0,
-            sample_count=int(se.sampler().sample_count()), x_fov=float(p["x_fov"]))
+            near_clip=_f(p["near_clip"]), far_clip=_f(p["far_clip"]), film_size=tuple(size), crop_size=tuple(crop),
+            crop_offset=tuple(off), rfilter=rfilter, rfilter_stddev=stddev, base_seed=int(m.group(1)) & 0xffffffff,
+            sample_count=int(se.sampler().sample_count()), x_fov=_f(p["x_fov"]))
 
     # ---- emitters ----------------------------------------------------------------------------
     def _emitter_slot(self, em) -> int:
@@ -257,15 +368,16 @@ class _Extractor:
                 self.out.textures.append(t)
                 self.out.emitters[k] = EmitterData(
                     shape=-1, radiance_tex=len(self.out.textures) - 1, type=abi.EMITTER_ENVMAP,
-                    sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0,
-                    env_scale=float(_np(ep["scale"]).reshape(-1)[0]), env_mis_compensation=False,
+                    sampling_weight=_f(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0,
+                    env_scale=float(_np(ep["scale"]).reshape(-1)[0]),
+                    env_mis_compensation=_probe_envmap_mis_compensation(mi, em, t.data, tw.matrix),
                     to_world=tw.matrix.copy(), to_world_inv=np.ascontiguousarray(tw.inverse_transpose.T, f32))
             elif any(key.startswith("radiance") for key in ep.keys()):
                 rad = self._texture(ep, "", "radiance", f"{eid}.radiance", 3)
                 if rad < 0 or self.out.textures[rad].kind != abi.TEX_CONST:
                     raise NotImplementedError("constant emitter: expected a uniform radiance")
                 self.out.emitters[k] = EmitterData(shape=-1, radiance_tex=rad, type=abi.EMITTER_CONSTANT,
-                                                   sampling_weight=float(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
+                                                   sampling_weight=_f(ep["sampling_weight"]) if "sampling_weight" in ep else 1.0)
             else:
                 raise NotImplementedError(f"environment emitter {em.class_name()} is outside the hot-path scope")
 

@@ -90,6 +90,48 @@ def main(mode):
       img4 = oracle.OracleScene(host4).render(spp=16, seed=0, mode=1, max_depth=8)
       rel = np.abs(img4 - ref4) / np.maximum(np.abs(ref4), 1e-2)
       assert rel.max() < 5e-4, rel.max()
+      # state that mi.traverse does not expose is recovered by probing the live objects: bitmap wrap / filter modes, the
+      # envmap's mis_compensation, the sampler's base seed; what cannot be represented raises instead of rendering wrongly
+      rs = np.random.RandomState(3)
+      tex = rs.uniform(0.05, 0.95, (5, 7, 3)).astype(np.float32)
+      for wrap in ("repeat", "clamp", "mirror"):
+          for filt in ("bilinear", "nearest"):
+              d5 = cbox(32, {"type": "path", "max_depth": 4, "block_size": 32})
+              d5["floor"]["bsdf"] = {"type": "diffuse", "reflectance": {"type": "bitmap", "data": mi.TensorXf(tex), "raw": True, "wrap_mode": wrap,
+                                                                         "filter_type": filt, "to_uv": mi.ScalarTransform3f().scale([2.5, 3.0]).translate([0.3, -0.2])}}
+              d5["sensor"]["sampler"]["seed"] = 11
+              sm5 = mi.load_dict(d5)
+              host5 = plug.extract_scene(mi, sm5)
+              t5 = [t for t in host5.textures if t.kind == mb.abi.TEX_BITMAP][0]
+              assert (t5.wrap, t5.filter) == (mb.scene._WRAP[wrap], mb.scene._FILT[filt]), (wrap, filt, t5.wrap, t5.filter)
+              assert host5.sensor.base_seed == 11
+              ref5 = np.array(mi.render(sm5, seed=1, spp=16))
+              img5 = oracle.OracleScene(host5).render(spp=16, seed=1, mode=1, max_depth=4)
+              rel = np.abs(img5 - ref5) / np.maximum(np.abs(ref5), 1e-2)
+              assert rel.max() < 2e-4, (wrap, filt, rel.max())
+      for comp in (False, True):
+          d6 = env_scene(res=32, spp=16, kind="envmap", T=mi.ScalarTransform4f, bitmap=mi.Bitmap)
+          [e for e in d6.values() if isinstance(e, dict) and e.get("type") == "envmap"][0]["mis_compensation"] = comp
+          d6["integrator"]["block_size"] = 32
+          sm6 = mi.load_dict(d6)
+          host6 = plug.extract_scene(mi, sm6)
+          assert [e for e in host6.emitters if e.type == mb.abi.EMITTER_ENVMAP][0].env_mis_compensation == comp, comp
+          ref6 = np.array(mi.render(sm6, seed=2, spp=16))
+          img6 = oracle.OracleScene(host6).render(spp=16, seed=2, mode=1, max_depth=6)
+          rel = np.abs(img6 - ref6) / np.maximum(np.abs(ref6), 1e-2)
+          assert rel.max() < 2e-4, (comp, rel.max())
+      for bad, why in (({"type": "twosided", "bsdf": {"type": "roughplastic", "alpha": 0.2}}, "RoughPlastic"),):
+          d7 = cbox(32, {"type": "path", "max_depth": 4})
+          d7["back"]["bsdf"] = bad
+          try:
+              plug.extract_scene(mi, mi.load_dict(d7)); raise AssertionError("extracted " + why)
+          except NotImplementedError as e:
+              assert why in str(e), e
+      d8 = cbox(32, {"type": "path", "max_depth": 4}); d8["sensor"]["sampler"] = {"type": "stratified", "sample_count": 16}
+      try:
+          plug.extract_scene(mi, mi.load_dict(d8)); raise AssertionError("extracted a stratified sampler")
+      except NotImplementedError as e:
+          assert "sampler" in str(e)
       plug.register(mi)
       integ = mi.load_dict({"type": "b200_path", "max_depth": 8})
       assert "max_depth = 8" in str(integ)

@@ -352,7 +352,8 @@ def test_device_refit_equals_a_fresh_build_on_a_large_mesh():
     fresh = mb.load_dict(d2)
     next(s for s in fresh.shapes if s.id == name).vertices = moved.copy()
     img2 = mb.render(fresh, spp=8, seed=2)
-    assert np.array_equal(img1, img2)
+    diff = np.abs(img1 - img2).max(axis=2)
+    assert np.array_equal(img1, img2), (int((diff > 0).sum()), float(diff.max()), np.argwhere(diff > 0)[:8].tolist())
     mb.update_vertices(sc, name, orig)
     assert np.array_equal(mb.render(sc, spp=8, seed=2), img0)
 
