@@ -443,7 +443,7 @@ def main():
         # `ncu --set full` capture (profiles/*_trace_traffic.json: dram__bytes_{read,write}.sum over all traversal launches
         # of a frame / rays traced) times the rays one launch of this run processed
         traffic = None; traffic_src = None
-        for fn in ("r02_trace_traffic.json", "r01_trace_traffic.json"):
+        for fn in (("r02_trace_traffic.json", "r01_trace_traffic.json") if args.workload.startswith("cornell") else ()):
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
                 traffic = tj["dram_bytes_per_ray"] * trace_rays / max(1, trace_launches)
@@ -467,7 +467,8 @@ def main():
                          "imbalance": (max(render_ms_ranks) / (sum(render_ms_ranks) / len(render_ms_ranks)) - 1) if render_ms_ranks else None,
                          "note": "step_ms: CUDA events around the timed region of every rank / steps; render_kernels_ms: the rank's own kernels of a frame "
                                  "(no collective), separate untimed pass; film_allreduce_us: 20 back-to-back all-reduces of the raw film, max over ranks"},
-            "roofline": {"kernel": "k_trace_dyn (BVH traversal: NEE shadow ray + closest hit)", "bound": "hbm",
+            "roofline": {"kernel": ("k_trace_flat (<= 32 leaves: every lane tests every leaf box, warp-shared exact triangle tests; NEE shadow ray + closest hit)"
+                                    if args.workload.startswith("cornell") else "k_trace_dyn (BVH walk with dynamic fetch: NEE shadow ray + closest hit)"), "bound": "hbm",
                          "achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (trace_gbs / hbm_peak) if trace_gbs else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": trace_bytes / max(1, trace_launches), "peak_source": peak_src,

@@ -82,13 +82,23 @@ struct b200pt_scene {
     uint32_t env_w = 0, env_h = 0;
 };
 
+// Host-to-device copy that has LANDED when it returns. cudaMemcpy from pageable host memory returns once the data sits in the
+// driver's staging buffer; the DMA to the device is ordered on the legacy default stream only, and every stream this library
+// launches on is non-blocking -- a kernel launched right after the call may read the old contents (measured: a device BVH refit
+// of a 205k-triangle mesh that saw part of the previous vertices, tests/test_gpu_parity.py). Waiting for the legacy stream closes it.
+static cudaError_t h2d(void *dst, const void *src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 template <typename T>
 static cudaError_t dev_upload(b200pt_scene *s, const T *host, size_t n, T **out) {
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
     if (e != cudaSuccess) return e;
     s->allocs.push_back(p);
-    if (n) e = cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (n) e = h2d(p, host, n * sizeof(T));
     *out = (T *) p;
     return e;
 }
@@ -402,7 +412,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
         uint32_t n_leaves = 0;
         for (const auto &nd : bvh.nodes) { if (nd.left < 0) n_leaves++; if (nd.right < 0) n_leaves++; }
         const char *e = getenv("B200PT_FLAT_TRAVERSAL");
-        s->launch.flat = (e ? atoi(e) != 0 : true) && n_leaves >= 1 && n_leaves <= 32 && s->launch.n_smem_nodes == d.n_nodes && s->launch.n_smem_tris == d.n_tris;
+        s->launch.flat = (e ? atoi(e) != 0 : true) && n_leaves >= 1 && n_leaves <= 32 && d.n_tris <= 256 && s->launch.n_smem_nodes == d.n_nodes && s->launch.n_smem_tris == d.n_tris;
         const char *g = getenv("B200PT_FLAT_BLOCKS_PER_SM");
         s->launch.grid_flat = (int) s->n_sm * (g ? std::max(1, atoi(g)) : 4);
     }
@@ -428,7 +438,7 @@ b200pt_status b200pt_scene_update_vertices(b200pt_scene *s, uint32_t shape, cons
     if (s->dev.geom_bytes <= 20480) { /* small scenes: the shading kernels stage the geometry per launch from these arrays, nothing else to do */ }
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    CU_TRY(cudaMemcpy((float *) s->dev.vertices + 8 * (size_t) s->shape_first_vertex[shape], vertices, (size_t) n_vertices * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(h2d((float *) s->dev.vertices + 8 * (size_t) s->shape_first_vertex[shape], vertices, (size_t) n_vertices * 8 * sizeof(float)));
     launch_refit(s->dev, s->bvh_tight, s->bvh_level_start.data(), (uint32_t) s->bvh_level_start.size() - 1, (int) s->n_sm * 4, s->stream);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(s->stream));
@@ -441,22 +451,22 @@ b200pt_status b200pt_scene_update_texture(b200pt_scene *s, uint32_t tex, const f
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(cudaStreamSynchronize(s->stream));
     if (s->tex[tex].kind == B200PT_TEX_BITMAP) {
-        CU_TRY(cudaMemcpy(s->tex[tex].dev_data, host_data, n * sizeof(float), cudaMemcpyHostToDevice));
+        CU_TRY(h2d(s->tex[tex].dev_data, host_data, n * sizeof(float)));
         if ((int32_t) tex == s->env_tex) {
             // EnvironmentMapEmitter::parameters_changed (envmap.cpp:207-258): refresh the halo texture and
             // rebuild the sampling distribution (same sizes: the device buffers are reused)
             EnvHost eh;
             if (!build_envmap(host_data, s->env_w, s->env_h, s->env_mis_compensation, eh)) return fail(B200PT_ERR_INVALID, "envmap rebuild failed");
-            CU_TRY(cudaMemcpy(s->env_dev_tex, eh.tex.data(), eh.tex.size() * sizeof(float), cudaMemcpyHostToDevice));
-            CU_TRY(cudaMemcpy(s->env_dev_warp, eh.warp.data(), eh.warp.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CU_TRY(h2d(s->env_dev_tex, eh.tex.data(), eh.tex.size() * sizeof(float)));
+            CU_TRY(h2d(s->env_dev_warp, eh.warp.data(), eh.warp.size() * sizeof(float)));
         }
     }
     else {
         const DevTexture *dt = s->dev.textures + tex;
         int ch = s->tex[tex].channels;
-        CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value), host_data, ch * sizeof(float), cudaMemcpyHostToDevice));
+        CU_TRY(h2d((char *) dt + offsetof(DevTexture, value), host_data, ch * sizeof(float)));
         if (s->tex[tex].kind == B200PT_TEX_CHECKERBOARD)   // color0 then color1
-            CU_TRY(cudaMemcpy((char *) dt + offsetof(DevTexture, value1), host_data + ch, ch * sizeof(float), cudaMemcpyHostToDevice));
+            CU_TRY(h2d((char *) dt + offsetof(DevTexture, value1), host_data + ch, ch * sizeof(float)));
     }
     return B200PT_OK;
 }
@@ -519,7 +529,7 @@ static b200pt_status ensure_pix_ids(b200pt_scene *s, const b200pt_render_params 
             std::vector<uint32_t> ids((size_t) W * H);
             for (uint32_t i = 0; i < W * H; ++i) ids[i] = i;
             CU_TRY(cudaMalloc(&s->all_pix_ids, std::max<size_t>(ids.size(), 1) * 4));
-            CU_TRY(cudaMemcpy(s->all_pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+            CU_TRY(h2d(s->all_pix_ids, ids.data(), ids.size() * 4));
         }
         s->cur_pix_ids = s->all_pix_ids; s->n_pix_ids = W * H;
         return B200PT_OK;
@@ -537,7 +547,7 @@ static b200pt_status ensure_pix_ids(b200pt_scene *s, const b200pt_render_params 
         }
         if (s->pix_ids) { cudaFree(s->pix_ids); s->pix_ids = nullptr; }
         CU_TRY(cudaMalloc(&s->pix_ids, std::max<size_t>(ids.size(), 1) * 4));
-        CU_TRY(cudaMemcpy(s->pix_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+        CU_TRY(h2d(s->pix_ids, ids.data(), ids.size() * 4));
         s->n_shard_pix = (uint32_t) ids.size();
         s->pix_key[0] = rank; s->pix_key[1] = count; s->pix_key[2] = ts;
     }
@@ -866,7 +876,7 @@ b200pt_status b200pt_tangent_write(b200pt_scene *s, uint32_t tex, const float *h
     b200pt_status e = b200pt_grad_offset(s, tex, &off, &cnt); if (e) return e;
     if (n != cnt || !host_in) return fail(B200PT_ERR_INVALID, "tangent size mismatch");
     CU_TRY(cudaSetDevice(s->device));
-    CU_TRY(cudaMemcpy((void *) (s->dev.tangent + off), host_in, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(h2d((void *) (s->dev.tangent + off), host_in, n * sizeof(float)));
     return B200PT_OK;
 }
 

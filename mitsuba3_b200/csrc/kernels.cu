@@ -135,11 +135,25 @@ PT_DEV float4 ld_tri(const TraceCtx &c, uint32_t tri, int k) {
 
 PT_DEV float safe_inv(float d) { return fabsf(d) > 1e-30f ? __frcp_rn(d) : copysignf(1e30f, d); }
 
-// Slab test in fused form: t = lo * inv - (o * inv), one FFMA per plane instead of a subtraction and a multiplication.
-// The product o * inv is rounded once per ray, so a plane distance is off by up to 2^-24 |o * inv| against the exact
-// (lo - o) * inv; `slack` = 2^-22 max |o * inv| (RaySlabs::slack) widens the interval test by more than twice that. The
-// boxes only cull -- a hit is only ever decided by the reference's Moeller-Trumbore arithmetic -- so a wider test costs
-// node visits (rays almost parallel to an axis stop culling on it), never a result.
+// Slab test of the tree walk, subtraction first (no cancellation against o * inv); the ray origin is live for the triangle
+// test anyway, so this form costs the walk three registers (inv) where the fused one below costs seven.
+PT_DEV bool box_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, float3 o, float3 inv, float tmax, float &tnear) {
+    float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+    float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+    float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+    float tmx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+    tnear = tmin;
+    return tmin <= tmx * 1.0000004f;
+}
+
+// Slab test in fused form (flat traversal: 18+ boxes per ray, registers to spare): t = lo * inv - (o * inv), one FFMA per
+// plane instead of a subtraction and a multiplication. The product o * inv is rounded once per ray, so a plane distance is off
+// by up to 2^-24 |o * inv| against the exact (lo - o) * inv; `slack` = 2^-22 max |o * inv| widens the interval test by more
+// than twice that. The boxes only cull -- a hit is only ever decided by the reference's Moeller-Trumbore arithmetic -- so a
+// wider test costs candidates (rays almost parallel to an axis stop culling on it), never a result.
+// (In k_trace_dyn the four extra live registers of this form spill at its 48-register budget: Cornell 3.45 -> 3.34 ms per
+//  launch, but the 205k-triangle scene 7.3 -> 8.2 ms; the walk keeps the form above. profiles/r02_summary.md)
 struct RaySlabs { float3 inv, oi; float slack; };
 PT_DEV RaySlabs make_slabs(float3 o, float3 d) {
     RaySlabs r;
@@ -168,7 +182,7 @@ constexpr int32_t TRAV_SENTINEL = 0x76543210;
 template <bool ANY, bool SMEM_ALL>
 PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit) {
     hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
-    const RaySlabs rs = make_slabs(o, d);
+    float3 inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     int32_t stack[64]; stack[0] = TRAV_SENTINEL; int sp = 0;
     int32_t node = 0, leaf = 0;     // leaf >= 0: none postponed
     bool any = false;
@@ -180,8 +194,8 @@ PT_DEV bool traverse(const TraceCtx &c, float3 o, float3 d, float maxt, Hit &hit
             float tl, tr;
             // both slab tests are evaluated unconditionally (no short-circuit branches); the
             // "no child" marker only exists in the synthetic root of a <= 2-triangle scene
-            bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rs, maxt, tl) & (cl != 0x7fffffff);
-            bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rs, maxt, tr) & (cr != 0x7fffffff);
+            bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
+            bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
             if (!hl && !hr) node = stack[sp--];
             else {
                 node = hl ? cl : cr;
@@ -314,8 +328,8 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
 //      into the queue of the BSDF model it hit; a miss ends the path
 //   3. finished lanes write their radiance to lane_result (consumed by k_splat)
 // ---------------------------------------------------------------------------
-template <bool FIRST, bool SMEM_ALL, bool FLAT>
-__global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
+template <bool FIRST, bool SMEM_ALL>
+__global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
                                                  Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
                                                  unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -328,11 +342,6 @@ __global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_cons
     stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
     stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
     TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
-    __shared__ float4 s_leaf[FLAT ? 2 * FLAT_MAX_LEAVES : 1];
-    __shared__ uint32_t s_nleaf;
-    if (FLAT) build_leaf_list(s_nodes, n_smem_nodes, s_leaf, &s_nleaf);
-    const uint32_t n_leaves = FLAT ? min(s_nleaf, FLAT_MAX_LEAVES) : 0u;
-    auto closest = [&](float3 o, float3 d, float maxt, Hit &h) { return FLAT ? traverse_flat<false>(s_leaf, n_leaves, s_tris, o, d, maxt, h) : traverse<false, SMEM_ALL>(ctx, o, d, maxt, h); };
 
     const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
     const uint32_t lane_id = threadIdx.x & 31u;
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_cons
             if (!FIRST && (flags & PF_HAS_SHADOW)) {
                 float4 so = cur.sh_o[i], sd = cur.sh_d[i];
                 Hit h; n_shadow++;
-                bool occluded = FLAT ? traverse_flat<true>(s_leaf, n_leaves, s_tris, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h) : traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
+                bool occluded = traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
                 if (!occluded) {
                     if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[i].w] |= 1u << bit; }
                     float2 c = cur.sh_c[i];
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_cons
                 float3 o = V(ro.x, ro.y, ro.z), d = V(rd.x, rd.y, rd.z);
                 float maxt = ro.w;
                 Hit h; n_closest++;
-                bool found = closest(o, d, maxt, h);
+                bool found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
                 if (FIRST && cfg.hide_emitters) {
                     // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
                     while (found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0) {
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_cons
                         Ray r = spawn_ray(si.p, si.n, d);
                         o = r.o; maxt = r.maxt;
                         cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
-                        found = closest(o, d, maxt, h);
+                        found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
                     }
                 }
                 if (found) {
@@ -401,6 +410,192 @@ __global__ void __launch_bounds__(BLOCK, FLAT ? 4 : 1) k_trace(const __grid_cons
         }
     }
     // statistics: one atomic per warp
+    for (int o = 16; o; o >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, o); }
+    if (lane_id == 0) {
+        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_trace_flat -- the traversal kernel of scenes with at most FLAT_MAX_LEAVES leaves (see traverse_flat). Same work per
+// slot as k_trace, organised in warp-wide phases so that the exact triangle tests are shared by the whole warp:
+//   box pass    every lane tests its own ray against all leaf boxes (32 of 32 threads, registers only) -> candidate mask
+//   pair list   the (ray, leaf) candidates of the 32 rays are written to one list in shared memory (warp prefix sum)
+//   test rounds lane j tests pairs j, j + 32, ...: the reference's Moeller-Trumbore on another lane's ray (the rays sit in
+//               shared memory); closest hit = 64-bit atomicMin on (t bits, primitive id) per ray -- the same minimum and
+//               the same tie-break as a serial scan, in any order; any-hit = a flag
+//   winner      every lane repeats the test on its winning triangle to get (t, u, v): same inputs, same bits
+// A serial per-lane candidate loop (ncu, profiles/r02_summary.md) ran the triangle tests at 4-9 of 32 threads and took 56 %
+// of the kernel's instructions; the rounds run them at ~30 of 32.
+// ---------------------------------------------------------------------------
+constexpr uint32_t FLAT_PAIR_CAP = 32 * FLAT_MAX_LEAVES;      // candidate (ray, leaf) pairs of one warp and phase: every pair fits
+constexpr uint32_t FLAT_MAX_TRIS = 256;
+
+struct FlatWarp {          // per-warp scratch in shared memory
+    float4 ray[64];                        // (o, maxt), (d, -) of the 32 rays of the phase
+    unsigned long long key[32];            // closest hit so far: (t bits << 32) | primitive id
+    uint32_t occ[32];                      // any-hit flag
+    uint16_t pairs[FLAT_PAIR_CAP];         // (ray << 8) | leaf
+};
+
+// One phase for the 32 rays of a warp; called by all 32 lanes at a converged point. ANY: returns "occluded"; otherwise the
+// closest hit in `hit`.
+template <bool ANY>
+PT_DEV bool flat_phase(FlatWarp &w, const float4 *s_leaf, uint32_t n_leaves, const float4 *s_tris, const uint8_t *s_primmap,
+                       bool active, float3 o, float3 d, float maxt, Hit &hit) {
+    const uint32_t lane_id = threadIdx.x & 31u;
+    hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
+    uint32_t mask = 0;
+    if (active) {
+        const RaySlabs rs = make_slabs(o, d);
+#pragma unroll 3
+        for (uint32_t l = 0; l < n_leaves; ++l) {
+            float4 a = s_leaf[2 * l], b = s_leaf[2 * l + 1];
+            float tn;
+            if (box_hit(a.x, a.y, a.z, a.w, b.x, b.y, rs, maxt, tn)) mask |= 1u << l;
+        }
+        w.ray[2 * lane_id] = make_float4(o.x, o.y, o.z, maxt); w.ray[2 * lane_id + 1] = make_float4(d.x, d.y, d.z, 0.f);
+    }
+    if (ANY) w.occ[lane_id] = 0u; else w.key[lane_id] = ~0ull;
+    // exclusive prefix sum of the candidate counts
+    const uint32_t cnt = (uint32_t) __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int of = 1; of < 32; of <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, of); if ((int) lane_id >= of) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return false;
+    {   // pair list: (ray << 8) | leaf
+        uint32_t k = incl - cnt, m = mask;
+        while (m) { uint32_t l = (uint32_t) __ffs((int) m) - 1u; m &= m - 1u; w.pairs[k++] = (uint16_t) ((lane_id << 8) | l); }
+    }
+    __syncwarp();
+    for (uint32_t p = lane_id; p < total; p += 32u) {
+        const uint32_t e = w.pairs[p], r = e >> 8, l = e & 255u;
+        const float4 ro = w.ray[2 * r], rd = w.ray[2 * r + 1];
+        const uint32_t enc = __float_as_uint(s_leaf[2 * l + 1].z), t0 = enc >> 3, count = (enc & 7u) + 1u;
+        for (uint32_t ti = t0; ti < t0 + count; ++ti) {
+            const float4 ta = s_tris[3 * ti], tb = s_tris[3 * ti + 1], te = s_tris[3 * ti + 2];
+            float t, u, v;
+            if (moeller_trumbore(V(ro.x, ro.y, ro.z), V(rd.x, rd.y, rd.z), ro.w, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v)) {
+                if (ANY) w.occ[r] = 1u;
+                else atomicMin(&w.key[r], ((unsigned long long) __float_as_uint(t + 0.f) << 32) | __float_as_uint(ta.w));   // t >= 0: its bits order like its value; -0 -> +0
+            }
+        }
+    }
+    __syncwarp();
+    if (ANY) return active && w.occ[lane_id] != 0u;
+    const unsigned long long key = w.key[lane_id];
+    if (!active || key == ~0ull) return false;
+    const uint32_t ti = s_primmap[(uint32_t) key];
+    const float4 ta = s_tris[3 * ti], tb = s_tris[3 * ti + 1], te = s_tris[3 * ti + 2];
+    float t, u, v;
+    moeller_trumbore(o, d, maxt, V(ta.x, ta.y, ta.z), V(tb.x, tb.y, tb.z), V(te.x, te.y, te.z), t, u, v);     // the winner's (t, u, v): same inputs, same bits
+    hit.t = t; hit.u = u; hit.v = v; hit.prim = (uint32_t) key;
+    return true;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(BLOCK, 4) k_trace_flat(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
+                                                         Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
+                                                         unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ float4 s_leaf[2 * FLAT_MAX_LEAVES];
+    __shared__ uint32_t s_nleaf;
+    __shared__ uint8_t s_primmap[FLAT_MAX_TRIS];
+    __shared__ FlatWarp s_warp[BLOCK / 32];
+    DevScene sc = sc_in;
+    float4 *s_nodes = (float4 *) smem_raw;
+    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
+    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
+    build_leaf_list(s_nodes, n_smem_nodes, s_leaf, &s_nleaf);
+    for (uint32_t i = threadIdx.x; i < n_smem_tris; i += blockDim.x) s_primmap[__float_as_uint(s_tris[3 * i].w) & (FLAT_MAX_TRIS - 1u)] = (uint8_t) i;
+    __syncthreads();
+    const uint32_t n_leaves = min(s_nleaf, FLAT_MAX_LEAVES);
+    FlatWarp &w = s_warp[threadIdx.x >> 5];
+
+    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
+    const uint32_t lane_id = threadIdx.x & 31u;
+    const uint32_t warp_stride = gridDim.x * blockDim.x;
+    uint32_t n_shadow = 0, n_closest = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
+        const uint32_t i = base + lane_id;
+        const bool valid = i < n;
+        const uint32_t flags = valid ? (FIRST ? PF_ALIVE : __float_as_uint(cur.prev[i].w)) : 0u;
+        // ---- 1. pending NEE shadow rays (Scene::ray_test) ------------------------------------------------------------------
+        const bool has_shadow = !FIRST && (flags & PF_HAS_SHADOW);
+        float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool res_loaded = false;
+        if (!FIRST && __any_sync(0xffffffffu, has_shadow)) {
+            float4 so = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(0.f, 0.f, 1.f, 0.f);
+            if (has_shadow) { so = cur.sh_o[i]; sd = cur.sh_d[i]; n_shadow++; }
+            Hit hs;
+            const bool occluded = flat_phase<true>(w, s_leaf, n_leaves, s_tris, s_primmap, has_shadow, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, hs);
+            if (has_shadow && !occluded) {
+                if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[i].w] |= 1u << bit; }
+                float2 c = cur.sh_c[i];
+                res = cur.result[i]; res_loaded = true;
+                res.x += sd.w; res.y += c.x; res.z += c.y;
+                cur.result[i] = res;
+            }
+            __syncwarp();
+        }
+        // ---- 2. closest hit of the path rays (Scene::ray_intersect_preliminary) --------------------------------------------------
+        bool alive = valid && (flags & PF_ALIVE);
+        bool finished = valid && !alive;
+        int mytype = -1;
+        if (__any_sync(0xffffffffu, alive)) {
+            float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f); float maxt = 0.f;
+            if (alive) { float4 ro = cur.ray_o[i], rd = cur.ray_d[i]; o = V(ro.x, ro.y, ro.z); d = V(rd.x, rd.y, rd.z); maxt = ro.w; n_closest++; }
+            Hit h;
+            bool found = flat_phase<false>(w, s_leaf, n_leaves, s_tris, s_primmap, alive, o, d, maxt, h);
+            if (FIRST && cfg.hide_emitters) {
+                // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
+                bool again = alive && found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0;
+                while (__any_sync(0xffffffffu, again)) {
+                    if (again) {
+                        SurfaceInteraction si = compute_si(sc, h.t, h.u, h.v, h.prim, d);
+                        Ray r = spawn_ray(si.p, si.n, d);
+                        o = r.o; maxt = r.maxt;
+                        cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
+                    }
+                    __syncwarp();
+                    Hit h2;
+                    bool f2 = flat_phase<false>(w, s_leaf, n_leaves, s_tris, s_primmap, again, o, d, maxt, h2);
+                    if (again) { found = f2; h = h2; again = found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0; }
+                    __syncwarp();
+                }
+            }
+            if (alive) {
+                if (found) {
+                    hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                    const DevShape &sh = sc.shapes[sc.prim_verts[h.prim].w];
+                    mytype = sc.bsdfs[sh.bsdf].type;
+                } else if (sc.env_type >= 0) mytype = Q_ENV;   // the ray left the scene: environment emitter (k_shade_env)
+                else finished = true;      // path.cpp:225: si invalid, no environment emitter
+            }
+        }
+        if (finished) {
+            if (!res_loaded) res = cur.result[i];
+            lane_result[cur.rng[i].w] = res;
+        }
+        __syncwarp();
+        // bucket pass: bin the slot by material id (one atomic per warp and material)
+#pragma unroll
+        for (int t = 0; t < N_QUEUES; ++t) {
+            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
+            if (m) {
+                uint32_t leader = __ffs(m) - 1, off = 0;
+                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = i;
+            }
+        }
+    }
     for (int o = 16; o; o >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, o); }
     if (lane_id == 0) {
         if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
@@ -451,8 +646,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
     // job state of this lane
     int kind = 0;                     // 0 idle, 1 shadow ray, 2 path ray
     uint32_t slot = 0, flags = 0;
-    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f);
-    RaySlabs rs; rs.inv = rs.oi = V(0.f, 0.f, 0.f); rs.slack = 0.f;
+    float3 o = V(0.f, 0.f, 0.f), d = V(0.f, 0.f, 1.f), inv = V(0.f, 0.f, 0.f);
     float maxt = 0.f;
     Hit hit; hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
     int32_t stack[64]; int sp = 0; int32_t node = TRAV_SENTINEL, leaf = 0;
@@ -464,7 +658,7 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
 
     auto start_ray = [&](float3 ro, float3 rd, float rmaxt) {
         o = ro; d = rd; maxt = rmaxt;
-        rs = make_slabs(o, d);
+        inv = V(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
         hit.t = PT_INF; hit.u = hit.v = 0.f; hit.prim = 0xffffffffu;
         stack[0] = TRAV_SENTINEL; sp = 0; node = 0; leaf = 0; occluded = false;
 #ifdef B200PT_WATCHDOG
@@ -516,8 +710,8 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
                     float4 n0 = ld_node<SMEM_ALL>(c, node, 0), n1 = ld_node<SMEM_ALL>(c, node, 1), n2 = ld_node<SMEM_ALL>(c, node, 2), n3 = ld_node<SMEM_ALL>(c, node, 3);
                     int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
                     float tl, tr;
-                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, rs, maxt, tl) & (cl != 0x7fffffff);
-                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, rs, maxt, tr) & (cr != 0x7fffffff);
+                    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, maxt, tl) & (cl != 0x7fffffff);
+                    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, maxt, tr) & (cr != 0x7fffffff);
                     if (!hl && !hr) node = stack[sp--];
                     else {
                         node = hl ? cl : cr;
@@ -1244,8 +1438,8 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
     bool all = L.n_smem_nodes == sc.n_nodes && L.n_smem_tris == sc.n_tris;
     if (L.flat) {       // <= FLAT_MAX_LEAVES leaves: every lane tests every leaf box, no tree walk (see traverse_flat)
         int grid = L.grid_flat;
-        if (first) k_trace<true, true, true><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
-        else k_trace<false, true, true><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+        if (first) k_trace_flat<true><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
+        else k_trace_flat<false><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
         return;
     }
     if (L.dynamic_fetch) {
@@ -1255,7 +1449,7 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
 #undef LAUNCH_DYN
         return;
     }
-#define LAUNCH_TRACE(F, A) k_trace<F, A, false><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
+#define LAUNCH_TRACE(F, A) k_trace<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
     if (first) { if (all) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
     else { if (all) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
 #undef LAUNCH_TRACE
@@ -1425,12 +1619,12 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    cudaFuncSetAttribute(k_trace_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_shade<B200PT_BSDF_DIFFUSE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
