@@ -139,8 +139,8 @@ enum { B200PT_LAYOUT_NORMALS = 1, B200PT_LAYOUT_TANGENTS = 2, B200PT_LAYOUT_TEXC
 
 typedef struct b200pt_shape {
     uint32_t n_vertices, n_faces;
-    const float    *vertices; /* n_vertices*8: pos3, normal3, uv2            */
-    const uint32_t *faces;    /* n_faces*4: v0, v1, v2, flags                */
+    const float    *vertices; /* n_vertices*8: pos3, normal3 (or, with B200PT_LAYOUT_TANGENTS, the three floats of frame_encode(normal, tangent), mesh_utils.h:74-118), uv2 */
+    const uint32_t *faces;    /* n_faces*4: v0, v1, v2, flags (bit 31 = FaceUVFlipped, mesh_utils.h:32; read with B200PT_LAYOUT_TANGENTS) */
     uint32_t layout;          /* B200PT_LAYOUT_*                             */
     int32_t  bsdf;            /* index into b200pt_scene_desc::bsdfs         */
     int32_t  emitter;         /* index into ::emitters, -1 = not emissive    */

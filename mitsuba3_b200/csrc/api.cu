@@ -310,10 +310,13 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     if (n_prims >= (1u << 28)) S_FAIL(B200PT_ERR_UNSUPPORTED, "too many triangles");
     std::vector<float> verts(n_verts * 8); std::vector<uint32_t> pv(n_prims * 4); std::vector<float> tri9(n_prims * 9);
     std::vector<DevShape> hs(desc->n_shapes);
+    std::vector<uint32_t> uv_flipped((n_prims + 31) / 32 + 1, 0u); bool any_tangents = false;     // FaceUVFlipped bits (mesh_utils.h:32)
     size_t vo = 0, po = 0;
     for (uint32_t i = 0; i < desc->n_shapes; ++i) {
         const b200pt_shape &sh = desc->shapes[i];
-        if (sh.layout & B200PT_LAYOUT_TANGENTS) S_FAIL(B200PT_ERR_UNSUPPORTED, "packed tangent frames are outside the hot-path scope");
+        if ((sh.layout & B200PT_LAYOUT_TANGENTS) && (sh.layout & (B200PT_LAYOUT_NORMALS | B200PT_LAYOUT_TEXCOORDS)) != (B200PT_LAYOUT_NORMALS | B200PT_LAYOUT_TEXCOORDS))
+            S_FAIL(B200PT_ERR_INVALID, "packed tangent frames need normals and texture coordinates (mesh.cpp:523)");
+        any_tangents |= (sh.layout & B200PT_LAYOUT_TANGENTS) != 0;
         if (sh.bsdf < 0 || sh.bsdf >= (int32_t) desc->n_bsdfs) S_FAIL(B200PT_ERR_INVALID, "shape references a missing BSDF");
         if (sh.emitter >= (int32_t) desc->n_emitters) S_FAIL(B200PT_ERR_INVALID, "shape references a missing emitter");
         DevShape &o = hs[i]; memset(&o, 0, sizeof(o));
@@ -333,6 +336,7 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
                 memcpy(&tri9[(po + f) * 9 + 3 * k], sh.vertices + 8 * (size_t) fr[k], 3 * sizeof(float));
             }
             pv[(po + f) * 4 + 3] = i;
+            if ((sh.layout & B200PT_LAYOUT_TANGENTS) && (fr[3] & 0x80000000u)) uv_flipped[(po + f) >> 5] |= 1u << ((po + f) & 31u);
             if (sh.sampling == B200PT_SAMPLING_MESH) {
                 // Mesh::build_pmf: face areas, cdf accumulated in double (core/distr_1d.h)
                 const float *p0 = &tri9[(po + f) * 9], *p1 = p0 + 3, *p2 = p0 + 6;
@@ -355,6 +359,8 @@ b200pt_status b200pt_scene_create(const b200pt_scene_desc *desc, int device, b20
     }
     { float *p; S_TRY(dev_upload(s, verts.data(), verts.size(), &p)); d.vertices = (const float4 *) p; }
     { uint32_t *p; S_TRY(dev_upload(s, pv.data(), pv.size(), &p)); d.prim_verts = (const uint4 *) p; }
+    d.uv_flipped = nullptr;
+    if (any_tangents) { uint32_t *p; S_TRY(dev_upload(s, uv_flipped.data(), uv_flipped.size(), &p)); d.uv_flipped = p; }
     d.n_shapes = desc->n_shapes;
     {
         // one contiguous blob: shapes | bsdfs | emitters | textures, every section 16-byte aligned

@@ -153,6 +153,7 @@ struct DevScene {
     const float4 *tris;        // 3 float4 per triangle in leaf order
     // shading data in (shape, prim) order
     const uint4  *prim_verts;  // v0, v1, v2 (global vertex index), shape
+    const uint32_t *uv_flipped; // one bit per primitive: FaceUVFlipped of its face record (mesh.cpp:634-644); nullptr when no mesh packs tangents
     const float4 *vertices;    // 2 float4 per vertex: (p.xyz, n.x) (n.y, n.z, u, v)
     const DevShape *shapes; const DevBsdf *bsdfs; const DevEmitter *emitters; const DevTexture *textures;
     uint32_t n_shapes, n_bsdfs, n_emitters, n_textures;
@@ -206,6 +207,15 @@ PT_DEV bool moeller_trumbore(float3 o, float3 d, float maxt, float3 p0, float3 e
     return active && t >= 0.f && t <= maxt;
 }
 
+// mesh_utils.h:89-118 frame_decode: the three floats of a packed tangent frame (modified Rodrigues parameters of the frame's
+// quaternion) -> unit normal (third column of the rotation) and tangent (first column)
+PT_DEV void frame_decode(float3 p, float3 &n, float3 &s) {
+    float a = rcp_(1.f + vsqnorm(p)), A = 8.f * sqr(a), B = __fmaf_rn(-4.f, a, A);
+    float X = A * p.x, Y = A * p.y, Z = A * p.z, yy = p.y * Y, xy = p.x * Y, xz = p.x * Z, yz = p.y * Z, u = 1.f - yy;
+    n = V(__fmaf_rn(B, p.y, xz), __fmaf_rn(-B, p.x, yz), __fmaf_rn(-p.x, X, u));
+    s = V(__fmaf_rn(-p.z, Z, u), __fmaf_rn(B, p.z, xy), __fmaf_rn(-B, p.y, xz));
+}
+
 // interaction.h:804-830 + mesh.cpp:2254-2437 + interaction.h:558-603
 PT_DEV SurfaceInteraction compute_si(const DevScene &sc, float t, float b1, float b2, uint32_t prim, float3 ray_d) {
     SurfaceInteraction si;
@@ -220,9 +230,17 @@ PT_DEV SurfaceInteraction compute_si(const DevScene &sc, float t, float b1, floa
     si.p = vfmas(p0, b0, vfmas(p1, b1, p2 * b2));   // mesh.cpp:2300
     si.n = vnormalize(vcross(e1, e2));
     si.t = t;
+    const bool tangents = (sh.layout & B200PT_LAYOUT_TANGENTS) != 0;     // mesh.cpp:2274 need_tangents (Shading is always requested)
+    float3 sh_s = V(0.f, 0.f, 0.f);
     if (sh.layout & B200PT_LAYOUT_NORMALS) {
-        float3 n0 = V(a0.w, a1.x, a1.y);
-        float3 dn1 = V(c0.w, c1.x, c1.y) - n0, dn2 = V(g0.w, g1.x, g1.y) - n0;
+        float3 n0 = V(a0.w, a1.x, a1.y), n1 = V(c0.w, c1.x, c1.y), n2 = V(g0.w, g1.x, g1.y);
+        if (tangents) {
+            // packed tangent frame (mesh.cpp:2339-2351, 2417-2424): one decode per vertex yields the normal and the tangent
+            float3 t0, t1, t2;
+            frame_decode(n0, n0, t0); frame_decode(n1, n1, t1); frame_decode(n2, n2, t2);
+            sh_s = vfmas(t1 - t0, b1, vfmas(t2 - t0, b2, t0));
+        }
+        float3 dn1 = n1 - n0, dn2 = n2 - n0;
         float3 n = vfmas(dn1, b1, vfmas(dn2, b2, n0));
         si.sh_n = n * rsqrt_(vsqnorm(n));
     } else {
@@ -235,7 +253,18 @@ PT_DEV SurfaceInteraction compute_si(const DevScene &sc, float t, float b1, floa
     } else {
         si.uv = make_float2(b1, b2);
     }
-    coordinate_system(si.sh_n, si.sh_s, si.sh_t);
+    // finalize_surface_interaction (interaction.h:571-597): orthogonalise the shape's tangent against the shading normal; a zero
+    // tangent (no packed frames) falls back to coordinate_system; the bitangent follows the orientation of the parameterisation
+    float3 s_o = vfmas(si.sh_n, -vdot(si.sh_n, sh_s), sh_s);
+    float sqr_norm = vsqnorm(s_o);
+    if (tangents && sqr_norm > 0.f) {
+        si.sh_s = s_o * rsqrt_(sqr_norm);
+        float3 t2 = vcross(si.sh_n, si.sh_s);
+        const bool flipped = (sc.uv_flipped[prim >> 5] >> (prim & 31u)) & 1u;
+        si.sh_t = flipped ? V(-t2.x, -t2.y, -t2.z) : t2;
+    } else {
+        coordinate_system(si.sh_n, si.sh_s, si.sh_t);
+    }
     si.wi = si.to_local(-ray_d);
     si.shape = pv.w;
     return si;

@@ -271,8 +271,7 @@ class _Extractor:
         if au >= 0:
             d.tex[slot_u] = d.tex[slot_v] = au
         else:
-            d.tex[slot_u], d.tex[slot_v] = T("alpha_u", 1), T("alpha_v", 1)
-            raise NotImplementedError("anisotropic BSDFs need packed tangent frames, which are outside the hot-path scope")
+            d.tex[slot_u], d.tex[slot_v] = T("alpha_u", 1), T("alpha_v", 1)      # anisotropic: its meshes pack tangent frames (shapes())
 
     # ---- shapes / emitters ---------------------------------------------------------------
     def shapes(self):
@@ -280,13 +279,21 @@ class _Extractor:
         for i, s in enumerate(self.scene_mi.shapes()):
             if not s.is_mesh():
                 raise NotImplementedError("only triangle meshes are on the hot path (SURVEY.md 2, row 9b)")
-            if getattr(s, "packs_tangent", lambda: False)():
-                raise NotImplementedError("packed tangent frames (anisotropic / normal-mapped BSDFs) are outside the hot-path scope")
             sid = s.id() or f"shape_{i}"
             verts = _np(s.packed_vertices()).reshape(-1, 8)
             faces3 = _np(s.faces(), np.uint32).reshape(-1, 3)
             faces = np.concatenate([faces3, np.zeros((faces3.shape[0], 1), np.uint32)], axis=1)
             layout = (abi.LAYOUT_NORMALS if s.has_normals() else 0) | (abi.LAYOUT_TEXCOORDS if s.has_texcoords() else 0)
+            if getattr(s, "packs_tangent", lambda: False)():
+                # the frame slot of the packed records holds frame_encode(normal, tangent) (mesh_utils.h:74-118); the per-face
+                # FaceUVFlipped bit is not exposed by the bindings: it is the sign of the face's uv determinant, with the
+                # reference's own arithmetic (mesh.cpp:634-644: fmsub(duv0.x, duv1.y, duv0.y * duv1.x) < 0)
+                layout |= abi.LAYOUT_TANGENTS
+                uv = verts[:, 6:8]
+                duv0, duv1 = uv[faces3[:, 1]] - uv[faces3[:, 0]], uv[faces3[:, 2]] - uv[faces3[:, 0]]
+                c = (duv0[:, 1] * duv1[:, 0]).astype(f32)                              # rounded product
+                det = duv0[:, 0].astype(np.float64) * duv1[:, 1].astype(np.float64) - c.astype(np.float64)   # exact product, one subtraction: the sign of the fused result
+                faces[:, 3] = np.where(det < 0, np.uint32(0x80000000), np.uint32(0))
             sh = ShapeData(id=sid, vertices=verts, faces=faces, layout=layout, bsdf=self.bsdf(s.bsdf(), f"{sid}.bsdf"))
             if s.is_emitter():
                 ep = mi.traverse(s.emitter())
@@ -419,12 +426,34 @@ def register(mi):
             # by another scene while the entry lives
             key = (id(scene), sensor if isinstance(sensor, int) else id(sensor))
             ent = self._cache.get(key)
+            if ent is not None and ent[1] is scene and ent[3] != self._fingerprint(ent[0], ent[2]):
+                ent = None                                   # a non-texture parameter changed (vertex positions, to_world, eta, fov ...): extract again
             if ent is None or ent[1] is not scene:
                 host = extract_scene(mi, scene, sensor)
-                ent = (host, scene, mi.traverse(scene))     # the parameter map is built once per scene
+                params = mi.traverse(scene)                  # the parameter map is built once per scene
+                ent = (host, scene, params, self._fingerprint(host, params))
                 self._cache[key] = ent
             self._params_of = ent[2]
             return ent[0]
+
+        @staticmethod
+        def _fingerprint(host, params):
+            """Checksums of every traversed parameter that is NOT one of the textures `_sync_params` uploads: what they feed
+            (meshes, transforms, indices of refraction, the sensor) is baked into the extracted scene, so a change means a new
+            extraction (the reference rebuilds through parameters_changed, scene.cpp:517-540)."""
+            tex = set(host.parameters().keys())
+            out = []
+            for k in params.keys():
+                if k in tex:
+                    continue
+                try:
+                    v = params[k]
+                    v = getattr(v, "matrix", v)
+                    a = np.asarray(v, dtype=np.float64).reshape(-1)
+                    out.append((k, a.size, float(a.sum()), float(np.dot(a, a))))
+                except Exception:
+                    out.append((k, str(params[k])[:64]))
+            return tuple(out)
 
         def _sync_params(self, host, scene):
             """Push the parameter values that CHANGED since the last call (optimiser steps) to the device scene."""

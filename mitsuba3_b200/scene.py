@@ -462,10 +462,6 @@ class _Parser:
         aniso = (bd.type == abi.BSDF_PRINCIPLED and bd.flags & abi.P_HAS_ANISOTROPIC) or \
                 (bd.type == abi.BSDF_CONDUCTOR and bd.flags & abi.M_ROUGH and bd.tex[abi.SLOT_ALPHA_U] != bd.tex[abi.SLOT_ALPHA_V]) or \
                 (bd.type == abi.BSDF_DIELECTRIC and bd.flags & abi.M_ROUGH and bd.tex[abi.SLOT_D_ALPHA_U] != bd.tex[abi.SLOT_D_ALPHA_V])
-        if aniso:
-            # BSDFFlags::Anisotropic makes the reference's meshes pack per-vertex tangent frames
-            # (mesh.cpp:2417-2429, interaction.h:570-598); those are outside the hot-path scope
-            raise NotImplementedError("anisotropic BSDFs need packed tangent frames, which are outside the hot-path scope")
         to_world = _as_transform(d.get("to_world"))
         flip = bool(d.get("flip_normals", False))
         if ty == "rectangle":
@@ -477,6 +473,12 @@ class _Parser:
         else:
             raise NotImplementedError(f"shape {ty!r}: only triangle meshes are on the hot path; "
                                       "load it with the host Mitsuba and pass the packed records as type 'mesh'")
+        if aniso and not (sh.layout & abi.LAYOUT_TANGENTS):
+            # BSDFFlags::Anisotropic makes the reference's meshes pack per-vertex tangent frames (mesh.cpp:355,2417-2429,
+            # interaction.h:570-598). Generating them is the host loaders' job (mesh.cpp:600-700); this mirror takes them
+            # ready-made: `packed_vertices` whose frame slot holds frame_encode(n, s), `faces` (F, 4) with the FaceUVFlipped
+            # bit and `layout` including LAYOUT_TANGENTS -- what mitsuba_plugin.extract_scene reads off a live mesh.
+            raise NotImplementedError("anisotropic BSDFs need a mesh with packed tangent frames (packed_vertices + layout with LAYOUT_TANGENTS)")
         em = d.get("emitter")
         if em is not None:
             if em["type"] != "area":

@@ -132,9 +132,31 @@ def main(mode):
           plug.extract_scene(mi, mi.load_dict(d8)); raise AssertionError("extracted a stratified sampler")
       except NotImplementedError as e:
           assert "sampler" in str(e)
+      # anisotropic BSDF on a loaded mesh: the reference packs tangent frames into the vertex records; the extractor hands them on
+      # (LAYOUT_TANGENTS + FaceUVFlipped bits) and the oracle reproduces the live render (Embree may differ on a silhouette pixel)
+      import os
+      sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+      import gen_golden_tangent as gt
+      for mirror in (False, True):
+          sm10 = mi.load_dict(gt.scene_dict(gt.sphere_ply(mirror), "aniso_roughconductor", 8, 4))
+          host10 = plug.extract_scene(mi, sm10)
+          ball = [s for s in host10.shapes if s.id == "ball"][0]
+          assert ball.layout & mb.abi.LAYOUT_TANGENTS and int((ball.faces[:, 3] >> 31).sum()) == (ball.faces.shape[0] if mirror else 0)
+          ref10 = np.array(mi.render(sm10, seed=2, spp=8))
+          img10 = oracle.OracleScene(host10).render(spp=8, seed=2, mode=1, max_depth=4)
+          rel = np.abs(img10 - ref10) / np.maximum(np.abs(ref10), 1e-2)
+          assert (rel.max(axis=2) > 1e-3).mean() < 0.01, (mirror, rel.max())
       plug.register(mi)
       integ = mi.load_dict({"type": "b200_path", "max_depth": 8})
       assert "max_depth = 8" in str(integ)
+      # the plugin's extracted scene is cached per mi.Scene; an edit of a non-texture parameter (here the field of view)
+      # invalidates it instead of rendering the old geometry / sensor
+      d9 = cbox(32, {"type": "b200_path", "max_depth": 4}); sm9 = mi.load_dict(d9); it9 = sm9.integrator()
+      h9 = it9._host_scene(sm9, 0)
+      assert it9._host_scene(sm9, 0) is h9
+      p9 = mi.traverse(sm9); p9["sensor.x_fov"] = 30.0; p9.update()
+      h9b = it9._host_scene(sm9, 0)
+      assert h9b is not h9 and abs(h9b.sensor.x_fov - 30.0) < 1e-5
       print("LIVE_CPU_OK")
   elif mode == "gpu":
       plug.register(mi)

@@ -203,6 +203,36 @@ def smooth_mesh_scene(res=32, spp=16, max_depth=5):
     return d
 
 
+TANGENT_MATERIALS = {
+    "aniso_principled": {"type": "principled", "base_color": {"type": "rgb", "value": [0.9, 0.6, 0.2]}, "roughness": 0.35,
+                         "anisotropic": 0.8, "metallic": 0.9, "specular": 0.5},
+    "aniso_roughconductor": {"type": "roughconductor", "distribution": "ggx", "alpha_u": 0.05, "alpha_v": 0.3,
+                             "eta": {"type": "rgb", "value": [0.2, 0.9, 1.1]}, "k": {"type": "rgb", "value": [3.9, 2.4, 2.2]}},
+}
+
+
+def tangent_mesh_scene(mat="aniso_principled", tag="", res=32, spp=16, max_depth=5):
+    """env_scene floor + envmap + area light with the UV sphere of tests/golden/tangent_mesh.npz: packed vertex records whose
+    frame slot holds frame_encode(normal, tangent) and faces with the FaceUVFlipped bit, as the reference's loader packs them
+    for an anisotropic BSDF (gen_golden_tangent.py); `tag` "_m" = the u-mirrored copy (every face uv-flipped)."""
+    import mitsuba3_b200 as mb
+    g = golden("tangent_mesh.npz")
+    d = env_scene(res=res, spp=spp, max_depth=max_depth, area_light=True)
+    del d["cube-a"], d["cube-b"]
+    d["ball-mat"] = TANGENT_MATERIALS[mat]
+    d["ball"] = {"type": "mesh", "packed_vertices": g["packed_vertices" + tag], "faces": g["faces" + tag], "layout": int(g["layout"]),
+                 "bsdf": {"type": "ref", "id": "ball-mat"}}
+    assert int(g["layout"]) & mb.abi.LAYOUT_TANGENTS
+    # Scene::emitters() of the reference build that wrote this fixture lists the environment map BEFORE the area light (the
+    # order decides which emitter a sample picks, scene.cpp:248-271; the live extractor reads it off the scene, the host mirror
+    # follows the order of the dictionary): the fixture records it
+    order = [str(x) for x in g["emitter_order"]]
+    if order.index("envmap") < order.index("area"):
+        sky = d.pop("sky")
+        d = {k: v for kk, vv in d.items() for k, v in (([("sky", sky)] if kk == "lamp" else []) + [(kk, vv)])}
+    return d
+
+
 def principled_glass_cbox(res=32, rfilter="box", spp=16, max_depth=8):
     """Cornell box with a transmissive principled box and a sheen / flatness wall (gen_golden.py:principled_glass)."""
     import mitsuba3_b200 as mb

@@ -126,3 +126,14 @@ def test_smooth_mesh_scene_matches_oracle(oracle_mod):
     sc = mb.load_dict(smooth_mesh_scene(res=48, spp=16, max_depth=5))
     img = mb.render(sc, spp=16, seed=2)
     compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=2, mode=0), max_bad_frac=0.01)
+
+
+@pytest.mark.parametrize("mat,tag", [("aniso_principled", ""), ("aniso_principled", "_m"), ("aniso_roughconductor", "_m"), ("aniso_roughconductor", "")])
+def test_anisotropic_mesh_with_packed_tangent_frames_matches_oracle(oracle_mod, mat, tag):
+    """Packed tangent frames (mesh.cpp:2339-2351,2417-2429, interaction.h:571-597): anisotropic principled / rough conductor on
+    the UV sphere of tests/golden/tangent_mesh.npz (frames and FaceUVFlipped bits as the reference's loader packs them; the
+    oracle reproduces the reference's frames to 2e-6 and its renders per pixel, tests/test_oracle_golden.py)."""
+    from conftest import tangent_mesh_scene
+    sc = mb.load_dict(tangent_mesh_scene(mat, tag, res=48, spp=16, max_depth=5))
+    img = mb.render(sc, spp=16, seed=3)
+    compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=3, mode=0), max_bad_frac=0.01)

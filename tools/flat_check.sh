@@ -18,5 +18,5 @@ PY
 }
 C=cornell_box_512x512_256spp_8bounce
 run c_flat4 $C B200PT_FLAT_BLOCKS_PER_SM=4
-run c_flat8 $C B200PT_FLAT_BLOCKS_PER_SM=8
-run h_bvh heightfield205k_1024x1024_64spp_8bounce B200PT_X=0
+
+
