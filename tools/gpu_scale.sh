@@ -28,8 +28,8 @@ for w in $WL; do
   for n in $NS; do
     case $w in
       cbox) run cbox $n cornell_box_512x512_256spp_8bounce --steps 10 --warmup 3 --no-cpu-baseline --no-mi-render;;
-      matpreview) run matpreview $n matpreview_1024x1024_128spp_8bounce --steps 5 --warmup 3 --no-cpu-baseline --no-mi-render --no-prb;;
-      heightfield_full) run heightfield_full $n heightfield205k_1920x1080_512spp_8bounce --steps 3 --warmup 3 --no-cpu-baseline --no-mi-render --no-prb;;
+      matpreview) run matpreview $n matpreview_1024x1024_128spp_8bounce --steps 4 --warmup 3 --no-cpu-baseline --no-mi-render --no-prb;;
+      heightfield_full) run heightfield_full $n heightfield205k_1920x1080_512spp_8bounce --steps 2 --warmup 3 --no-cpu-baseline --no-mi-render --no-prb;;
     esac
   done
 done
