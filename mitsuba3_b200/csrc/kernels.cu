@@ -3,8 +3,8 @@
 // One wavefront per bounce:
 //
 //   k_generate      lane -> pixel, TEA/PCG32 seeding, primary ray          (integrator.cpp:322-339,448-485)
-//   k_trace_dyn     persistent BVH traversal with dynamic work fetch (default; k_trace is the
-//                   static grid-stride variant): resolves the pending NEE shadow ray of
+//   k_trace_flat /  traversal (flat leaf-box kernel for scenes of <= 32 leaves, persistent BVH walk with dynamic
+//   k_trace_dyn     work fetch otherwise): resolves the pending NEE shadow ray of
 //                   every slot (Scene::ray_test), then the closest hit of its path ray
 //                   (Scene::ray_intersect_preliminary) and bins the slot into the
 //                   queue of the material it hit, or into the queue of the rays that
@@ -321,102 +321,13 @@ __global__ void __launch_bounds__(BLOCK) k_generate(DevScene sc, RenderCfg cfg, 
 }
 
 // ---------------------------------------------------------------------------
-// k_trace -- persistent traversal kernel. Per slot of the current buffer:
+// Traversal kernels. Per slot of the current buffer:
 //   1. pending NEE shadow ray (Scene::ray_test, scene.cpp:232/344): unoccluded ->
 //      result += contribution (path.cpp:279-280)
 //   2. if the lane is alive: closest hit (scene.cpp:216) -> hit record, bin the slot
 //      into the queue of the BSDF model it hit; a miss ends the path
 //   3. finished lanes write their radiance to lane_result (consumed by k_splat)
 // ---------------------------------------------------------------------------
-template <bool FIRST, bool SMEM_ALL>
-__global__ void __launch_bounds__(BLOCK) k_trace(const __grid_constant__ DevScene sc_in, RenderCfg cfg, PathBuf cur, float4 *__restrict__ hit_out, const uint32_t *__restrict__ n_in,
-                                                 Queues q, uint32_t *__restrict__ qcounts, float4 *__restrict__ lane_result,
-                                                 unsigned long long *__restrict__ stats, uint32_t n_smem_nodes, uint32_t n_smem_tris) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    DevScene sc = sc_in;
-    float4 *s_nodes = (float4 *) smem_raw;
-    float4 *s_tris = s_nodes + 4 * (size_t) n_smem_nodes;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    stage_bvh(sc, s_nodes, s_tris, n_smem_nodes, n_smem_tris, &bar);
-    stage_tables(sc, smem_raw + ((n_smem_nodes * 64u + n_smem_tris * 48u + 127u) & ~127u), &bar, 1u);
-    TraceCtx ctx = { s_nodes, s_tris, sc.nodes, sc.tris, n_smem_nodes, n_smem_tris };
-
-    const uint32_t n = FIRST ? cfg.chunk_lanes : *n_in;
-    const uint32_t lane_id = threadIdx.x & 31u;
-    const uint32_t warp_stride = gridDim.x * blockDim.x;
-    uint32_t n_shadow = 0, n_closest = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += warp_stride) {
-        uint32_t i = base + lane_id;
-        bool valid = i < n;
-        int mytype = -1;
-        if (valid) {
-            uint32_t flags = __float_as_uint(cur.prev[i].w);
-            float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool res_loaded = false;
-            if (!FIRST && (flags & PF_HAS_SHADOW)) {
-                float4 so = cur.sh_o[i], sd = cur.sh_d[i];
-                Hit h; n_shadow++;
-                bool occluded = traverse<true, SMEM_ALL>(ctx, V(so.x, so.y, so.z), V(sd.x, sd.y, sd.z), so.w, h);
-                if (!occluded) {
-                    if (cur.vis) { uint32_t bit = (flags & PF_DEPTH_MASK) - 1u; if (bit < 32u) cur.vis[cur.rng[i].w] |= 1u << bit; }
-                    float2 c = cur.sh_c[i];
-                    res = cur.result[i]; res_loaded = true;
-                    res.x += sd.w; res.y += c.x; res.z += c.y;
-                    cur.result[i] = res;
-                }
-            }
-            bool finished = !(flags & PF_ALIVE);
-            if (!finished) {
-                float4 ro = cur.ray_o[i], rd = cur.ray_d[i];
-                float3 o = V(ro.x, ro.y, ro.z), d = V(rd.x, rd.y, rd.z);
-                float maxt = ro.w;
-                Hit h; n_closest++;
-                bool found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
-                if (FIRST && cfg.hide_emitters) {
-                    // skip_area_emitters (integrator.cpp:96-123): continue through directly visible emitters
-                    while (found && sc.shapes[sc.prim_verts[h.prim].w].emitter >= 0) {
-                        SurfaceInteraction si = compute_si(sc, h.t, h.u, h.v, h.prim, d);
-                        Ray r = spawn_ray(si.p, si.n, d);
-                        o = r.o; maxt = r.maxt;
-                        cur.ray_o[i] = make_float4(o.x, o.y, o.z, maxt);
-                        found = traverse<false, SMEM_ALL>(ctx, o, d, maxt, h);
-                    }
-                }
-                if (found) {
-                    hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-                    const DevShape &sh = sc.shapes[sc.prim_verts[h.prim].w];
-                    mytype = sc.bsdfs[sh.bsdf].type;
-                } else if (sc.env_type >= 0) mytype = Q_ENV;   // the ray left the scene: environment emitter (k_shade_env)
-                else finished = true;      // path.cpp:225: si invalid, no environment emitter
-            }
-            if (finished) {
-                if (!res_loaded) res = cur.result[i];
-                lane_result[cur.rng[i].w] = res;
-            }
-        }
-        __syncwarp();
-        // bucket pass: bin the slot by material id (one atomic per warp and material)
-#pragma unroll
-        for (int t = 0; t < N_QUEUES; ++t) {
-            uint32_t m = __ballot_sync(0xffffffffu, mytype == t);
-            if (m) {
-                uint32_t leader = __ffs(m) - 1, off = 0;
-                if (lane_id == leader) off = atomicAdd(&qcounts[t == Q_ENV ? QCOUNT_ENV : t], __popc(m));
-                off = __shfl_sync(0xffffffffu, off, leader);
-                if (mytype == t) q.slots[t][off + __popc(m & ((1u << lane_id) - 1u))] = i;
-            }
-        }
-    }
-    // statistics: one atomic per warp
-    for (int o = 16; o; o >>= 1) { n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o); n_closest += __shfl_xor_sync(0xffffffffu, n_closest, o); }
-    if (lane_id == 0) {
-        if (n_shadow) atomicAdd(&stats[ST_SHADOW], (unsigned long long) n_shadow);
-        if (n_closest) atomicAdd(&stats[ST_CLOSEST], (unsigned long long) n_closest);
-    }
-}
-
 // ---------------------------------------------------------------------------
 // k_trace_flat -- the traversal kernel of scenes with at most FLAT_MAX_LEAVES leaves (see traverse_flat). Same work per
 // slot as k_trace, organised in warp-wide phases so that the exact triangle tests are shared by the whole warp:
@@ -611,7 +522,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_trace_flat(const __grid_constant__
 // from a global counter (one atomicAdd per refill) instead of waiting for the slowest
 // ray of the batch. The traversal itself is the same speculative while-while walk,
 // resumable across refills (node / leaf / stack live in registers + local memory).
-// Semantics per slot are identical to k_trace.
+// Semantics per slot are those of k_trace_flat.
 // ---------------------------------------------------------------------------
 
 #ifndef TRACE_MIN_BLOCKS
@@ -1475,17 +1386,12 @@ void launch_trace(const DevScene &sc, const RenderCfg &cfg, PathBuf cur, float4 
         else k_trace_flat<false><<<grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris);
         return;
     }
-    if (L.dynamic_fetch) {
+    {
 #define LAUNCH_DYN(F, A) k_trace_dyn<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, qcounts + 5, lane_result, stats, L.n_smem_nodes, L.n_smem_tris, L.refill_idle)
         if (first) { if (all) LAUNCH_DYN(true, true); else LAUNCH_DYN(true, false); }
         else { if (all) LAUNCH_DYN(false, true); else LAUNCH_DYN(false, false); }
 #undef LAUNCH_DYN
-        return;
     }
-#define LAUNCH_TRACE(F, A) k_trace<F, A><<<L.grid, BLOCK, L.smem_trace + L.smem_tables, st>>>(sc, cfg, cur, hit, n_in, q, qcounts, lane_result, stats, L.n_smem_nodes, L.n_smem_tris)
-    if (first) { if (all) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
-    else { if (all) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
-#undef LAUNCH_TRACE
 }
 
 template <int TYPE>
@@ -1652,10 +1558,6 @@ void set_trace_smem_attr(size_t bytes_wanted) {
     cudaFuncSetAttribute(k_trace_dyn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_dyn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_trace_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
     cudaFuncSetAttribute(k_ray_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
