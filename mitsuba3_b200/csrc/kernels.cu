@@ -715,73 +715,44 @@ __global__ void __launch_bounds__(BLOCK, TRACE_MIN_BLOCKS) k_trace_dyn(const __g
 }
 
 // ---------------------------------------------------------------------------
-// Warp-cooperative fp32 gradient scatter (adjoint of tex_eval3). Called by all 32 lanes at a converged point; lanes
-// without a request pass tex = -1.
-//   * single-target textures (a constant, one of the two checkerboard colours): the lanes of a warp usually aim at a
-//     handful of targets (the light's radiance: all of them at one) -- one butterfly reduction and ONE atomicAdd per
-//     channel for every distinct target in the warp (the contention fix for few-float parameters);
-//   * bitmap taps: lanes that target the same texel are combined with __match_any_sync + shuffles first (the 32 lanes of a
-//     warp are samples of one pixel at the first bounce: same four texels; plain atomics measured slower, 39.7 -> 45.2 ms).
-// (Round 1 used the match/shuffle path for everything: 32 lanes on one target walk a 32-step peer loop, three shuffles a
-//  step -- the adjoint shading kernel took 3.8 x the primal one, profiles/r02_summary.md section 6.)
+// Warp-cooperative fp32 gradient scatter (adjoint of tex_eval3). Called by all 32
+// lanes at a converged point; lanes without a request pass tex = -1. Lanes that
+// target the same texel are combined with __match_any_sync + shuffles so that the
+// texture receives ONE atomicAdd per distinct (texel, channel) and warp -- the
+// contention fix for few-texel parameters (constant albedo = 3 floats).
+// (Measured in round 2 and NOT kept: a butterfly reduction per distinct single-target texture plus plain atomics for bitmap taps
+//  45.2 ms, the same with the match/shuffle path kept for bitmaps 44.2 ms, against 39.7 ms for this version on the configs[2]
+//  gradient step -- the adjoint kernel runs at its 128-register budget with spills, and the longer code costs more there than the
+//  32-step peer loop of the all-lanes-one-target case. profiles/r02_summary.md section 6.)
 // ---------------------------------------------------------------------------
 PT_DEV void warp_scatter3(const DevScene &sc, int32_t tex, float2 uv, float3 g) {
     const uint32_t lane_id = threadIdx.x & 31u;
-    const bool has = tex >= 0 && sc.textures[tex >= 0 ? tex : 0].differentiable && (g.x != 0.f || g.y != 0.f || g.z != 0.f);
+    bool has = tex >= 0 && sc.textures[tex >= 0 ? tex : 0].differentiable && (g.x != 0.f || g.y != 0.f || g.z != 0.f);
     if (!__any_sync(0xffffffffu, has)) return;
     TexTaps tp; tp.n = 0;
-    int C = 3; float *grad = nullptr;
-    bool single = false;
-    uint32_t key = 0xffffffffu;          // single-target requests: (texture, element)
+    int C = 3; float *grad = nullptr; bool is_const = false;
     if (has) {
         const DevTexture &t = sc.textures[tex];
         C = t.channels; grad = sc.grad + t.grad_offset;
-        if (t.kind == B200PT_TEX_CONST) { single = true; tp.idx[0] = 0; }
-        else if (t.kind == B200PT_TEX_CHECKERBOARD) { single = true; tp.idx[0] = checker_masks_equal(t, uv) ? 0 : 1; }
+        if (t.kind == B200PT_TEX_CONST) { tp.n = 1; tp.idx[0] = 0; tp.w[0] = 1.f; is_const = true; }
+        else if (t.kind == B200PT_TEX_CHECKERBOARD) { tp.n = 1; tp.idx[0] = checker_masks_equal(t, uv) ? 0 : 1; tp.w[0] = 1.f; }
         else tex_lookup(t, uv, tp);
-        if (single) key = ((uint32_t) tex << 1) | (uint32_t) tp.idx[0];
     }
-    // ---- single-target requests: one reduction per distinct target ------------------------------------------------------------
-    uint32_t pending = __ballot_sync(0xffffffffu, single);
-    while (pending) {
-        const int leader = __ffs((int) pending) - 1;
-        const uint32_t k0 = __shfl_sync(0xffffffffu, key, leader);
-        const bool mine = single && key == k0;
-        float v0 = mine ? g.x : 0.f, v1 = mine ? g.y : 0.f, v2 = mine ? g.z : 0.f;
-#pragma unroll
-        for (int of = 16; of; of >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, of); v1 += __shfl_xor_sync(0xffffffffu, v1, of); v2 += __shfl_xor_sync(0xffffffffu, v2, of); }
-        if ((int) lane_id == leader) {
-            if (C == 1) atomicAdd(grad + (sc.textures[tex].kind == B200PT_TEX_CONST ? 0 : tp.idx[0]), v0 + v1 + v2);
-            else { float *gp = grad + (size_t) tp.idx[0] * 3; atomicAdd(gp, v0); atomicAdd(gp + 1, v1); atomicAdd(gp + 2, v2); }
-        }
-        pending &= ~__ballot_sync(0xffffffffu, mine);
-    }
-    // ---- bitmap taps ---------------------------------------------------------------------------------------------------------------
-    const bool bm = has && !single;
-    if (!__any_sync(0xffffffffu, bm)) return;
     for (int k = 0; k < 4; ++k) {
-        bool hk = bm && k < tp.n;
+        bool hk = has && k < tp.n;
         if (!__any_sync(0xffffffffu, hk)) break;
-        unsigned long long mkey = hk ? (((unsigned long long) (uint32_t) tex << 32) | (uint32_t) tp.idx[k]) : ~0ull;
-        uint32_t peers = __match_any_sync(0xffffffffu, mkey);
+        unsigned long long key = hk ? (((unsigned long long) (uint32_t) tex << 32) | (uint32_t) tp.idx[k]) : ~0ull;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
         float w = hk ? tp.w[k] : 0.f;
         float v0 = g.x * w, v1 = g.y * w, v2 = g.z * w;
         uint32_t leader = __ffs(peers) - 1;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        const uint32_t hk_mask = __ballot_sync(0xffffffffu, hk);
-        if (__all_sync(0xffffffffu, !hk || peers == hk_mask)) {
-            // every requesting lane aims at the same texel (the samples of one pixel at the first bounce): one butterfly
-            s0 = v0; s1 = v1; s2 = v2;
-#pragma unroll
-            for (int of = 16; of; of >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, of); s1 += __shfl_xor_sync(0xffffffffu, s1, of); s2 += __shfl_xor_sync(0xffffffffu, s2, of); }
-        } else {
-            for (uint32_t m = peers; m; m &= m - 1) {
-                int src = __ffs(m) - 1;
-                s0 += __shfl_sync(peers, v0, src); s1 += __shfl_sync(peers, v1, src); s2 += __shfl_sync(peers, v2, src);
-            }
+        for (uint32_t m = peers; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            s0 += __shfl_sync(peers, v0, src); s1 += __shfl_sync(peers, v1, src); s2 += __shfl_sync(peers, v2, src);
         }
         if (hk && lane_id == leader) {
-            if (C == 1) atomicAdd(grad + tp.idx[k], s0 + s1 + s2);
+            if (C == 1) atomicAdd(grad + (is_const ? 0 : tp.idx[k]), s0 + s1 + s2);
             else { float *gp = grad + (size_t) tp.idx[k] * 3; atomicAdd(gp, s0); atomicAdd(gp + 1, s1); atomicAdd(gp + 2, s2); }
         }
     }

@@ -107,5 +107,13 @@ for name in ("trace", "shade"):
             if s[3] > 0.006 * tot:
                 out.append(f"| {s[1] & 0xffff:04x}-{s[2] & 0xffff:04x} | {s[5]} | {s[0]} | {s[3] / tot * 100:.1f} % | {s[4] / max(s[3], 1):.1f} |")
         out.append(f"\ntotal warp instructions {tot}\n")
+f = os.path.join(G, f"{tag}_shade.csv")
+if os.path.exists(f):
+    rows = [r for r in csv.reader(open(f)) if len(r) > 10]
+    h = rows[0]; mi, vi, ui, ki = h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit"), h.index("Kernel Name")
+    out.append(f"## Key metrics of one launch of the diffuse shading kernel: `{rows[1][ki][:80]}`\n\n| metric | value |\n|---|---|")
+    for r in rows[1:]:
+        out.append(f"| `{r[mi]}` | {r[vi]} {r[ui]} |")
+    out.append("")
 open(os.path.join(P, f"{tag}_ncu.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
