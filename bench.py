@@ -238,7 +238,9 @@ def e2e_mi_render(workload, steps, device):
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_mi_render.py"), str(w), str(h), str(spp), str(md), rf, str(steps), str(device)],
                            env=env, capture_output=True, text=True, timeout=900)
-        return json.loads(r.stdout.strip().splitlines()[-1])
+        # the JSON object sits on the last stdout line, possibly behind a log message of the host Mitsuba on the same line
+        line = r.stdout.strip().splitlines()[-1]
+        return json.loads(line[line.index('{"value"'):])
     except Exception as e:      # noqa: BLE001
         tail = ""
         try:
@@ -370,12 +372,13 @@ def main():
     names = scene.parameters()
     h2d = sum(scene.textures[i].size * 4 for i in names.values())
     img_bytes = w * h * 3 * 4
-    pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory() if world > 1 else None
+    pinned = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()          # the step's result lands in pinned host memory
+    pinned_np = pinned.numpy()
 
     def step_host(seed):
         update_params(scene, {k: scene.textures[i].array() for k, i in names.items()}, local)
         if world == 1:
-            return integ.render(scene, seed=seed, spp=spp, device=local)
+            return integ.render(scene, seed=seed, spp=spp, device=local, out=pinned_np)
         pinned.copy_(mbd.render_distributed(scene, integ, seed=seed, spp=spp, device=local), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pinned.numpy()

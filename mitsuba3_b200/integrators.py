@@ -160,12 +160,17 @@ class PathIntegrator:
 
     # -- SamplingIntegrator::render (integrator.cpp:151-396) -------------------------
     def render(self, scene: Scene, sensor=0, seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True,
-               device: int = 0) -> np.ndarray:
+               device: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """`out`: optional preallocated float32 (H, W, 3) host array for the image (e.g. the numpy view of a pinned buffer: the
+        device-to-host copy is then a plain asynchronous DMA instead of a staged copy into pageable memory)."""
         if not develop:
             raise NotImplementedError("develop=False: use render_accumulate() to obtain the raw film block")
         ds = device_scene(scene, device)
         p = self.params(scene, seed, spp)
-        out = np.empty(scene.film_shape, np.float32)
+        if out is None:
+            out = np.empty(scene.film_shape, np.float32)
+        elif out.dtype != np.float32 or tuple(out.shape) != tuple(scene.film_shape) or not out.flags.c_contiguous:
+            raise ValueError("`out` must be a C-contiguous float32 array of the film's shape")
         abi.check(ds.lib.b200pt_render(ds.h, C.byref(p), out.ctypes.data_as(C.POINTER(C.c_float))), ds.lib)
         return out
 

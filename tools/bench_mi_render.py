@@ -38,5 +38,5 @@ for i in range(steps):
     img = mi.render(scene, spp=spp, seed=i)
     a = np.array(img)
 dt = (time.perf_counter() - t0) / steps
-print(json.dumps({"value": w * h * spp / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3, "steps": steps, "checksum": float(a.mean()),
+print("\n" + json.dumps({"value": w * h * spp / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3, "steps": steps, "checksum": float(a.mean()),
                   "api": f"mi.render(scene, spp) of mitsuba {mi.__version__} ({variant}) with the registered b200_path integrator", "d2h_bytes_per_step": w * h * 12}))
