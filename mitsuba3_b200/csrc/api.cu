@@ -654,10 +654,14 @@ static size_t chunk_pixels(const b200pt_scene *s, const b200pt_render_params *p,
     if (!lanes) { const char *e = getenv("B200PT_CHUNK_LANES"); lanes = e ? (size_t) atoll(e) : ((size_t) 1 << 26); }
     // never ask for more state than the device can hold next to what other users of the GPU (torch, NCCL) have taken:
     // the wavefront already allocated counts as available, 10 % of the free memory stays untouched
+    // (only when the wavefront has to grow: the state already allocated for an earlier call of this size needs no new
+    //  question to the driver -- cudaMemGetInfo is a host-side cost of every frame otherwise)
+    const bool have_adj = s->wf.cap && s->wf.buf[0].adj_L != nullptr;
+    const size_t want = std::min<size_t>(lanes, (size_t) n_pix * std::max(1u, p->spp));
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    if ((s->wf.cap < want || (adjoint && !have_adj)) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         size_t per = wavefront_bytes_per_lane(s, adjoint);
-        size_t held = s->wf.cap * wavefront_bytes_per_lane(s, s->wf.cap && s->wf.buf[0].adj_L != nullptr);
+        size_t held = s->wf.cap * wavefront_bytes_per_lane(s, have_adj);
         size_t fit = (size_t) ((double) (free_b + held) * 0.9) / per;
         if (lanes > fit) lanes = std::max<size_t>(fit, 1024);
     }
