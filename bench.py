@@ -382,15 +382,20 @@ def main():
         pinned.copy_(mbd.render_distributed(scene, integ, seed=seed, spp=spp, device=local), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pinned.numpy()
-    step_host(77)
+    for i in range(3):
+        step_host(77 + i)
     sync_all()
+    host_ms = []
     t1 = time.perf_counter()
     for i in range(args.steps):
+        t_s = time.perf_counter()
         img = step_host(i)
+        host_ms.append((time.perf_counter() - t_s) * 1e3)
     sync_all()
     e2e_s = max_over_ranks((time.perf_counter() - t1) / args.steps)
     e2e = {"value": samples_per_step / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": img_bytes, "checksum": float(np.asarray(img).mean()),
+           "per_step_ms": [round(x, 3) for x in host_ms],      # rank 0: wall time of every timed host step (an outlier shows here)
            "api": "mitsuba3_b200.render -> b200pt_render (C ABI), host buffers in and out, wall clock, max over ranks"}
 
     # ---- PRB gradient step (BASELINE.json: "ms/grad-step (PRB)"): primal + adjoint, device-timed -------
