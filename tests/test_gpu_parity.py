@@ -430,3 +430,30 @@ def test_principled_transmission_scene_matches_oracle(oracle_mod):
     sc = mb.load_dict(principled_glass_cbox(res=48, spp=16, max_depth=8))
     img = mb.render(sc, spp=16, seed=3)
     compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=3, mode=0), max_bad_frac=0.01)
+
+
+def test_reference_shape_known_answers_through_the_abi(oracle_mod):
+    """The reference's own hit tests (src/shapes/tests/test_rectangle.py:80-109, test_cube.py:26-69) through
+    b200pt_ray_test / b200pt_ray_intersect: a 2-triangle and three 12-triangle scenes (the flat traversal), hits exactly where the
+    reference asserts them, records bit-identical to the oracle."""
+    d = mb.cornell_box()
+    rays_of = lambda o, dirv: np.concatenate([np.asarray(o, np.float32), np.broadcast_to(np.asarray(dirv, np.float32), (len(o), 3)),
+                                              np.full((len(o), 1), 3.4e38, np.float32)], axis=1)
+    cases = []
+    coords = np.linspace(-1, 1, 15, dtype=np.float32)
+    cases.append(({"type": "rectangle", "to_world": mb.Transform4f().scale([2.0, 0.5, 1.0])},
+                  rays_of(np.stack([coords, coords, np.full_like(coords, 5.0)], 1), [0, 0, -1]), np.abs(coords) <= 0.5))
+    pts = [-1.5, -0.9, -0.5, 0, 0.5, 0.9, 1.5]
+    xy = np.array([(x, y) for x in pts for y in pts], np.float32)
+    for scale in ([1.0, 1.0, 1.0], [2.0, 1.0, 1.0], [1.0, 2.0, 1.0]):
+        cases.append(({"type": "cube", "to_world": mb.Transform4f().scale(scale)},
+                      rays_of(np.concatenate([xy, np.full((len(xy), 1), -8.0, np.float32)], 1), [0, 0, 1]),
+                      (np.abs(xy[:, 0]) <= scale[0]) & (np.abs(xy[:, 1]) <= scale[1])))
+    for shape, rays, expect in cases:
+        sc = mb.load_dict({"type": "scene", "sensor": d["sensor"], "foo": shape})
+        ds, orc = device_scene(sc), oracle_mod.OracleScene(sc)
+        assert np.array_equal(ds.ray_test(rays), expect)
+        t, uv, prim, sh = ds.ray_intersect(rays)
+        to, uvo, primo, sho = orc.ray_intersect(rays)
+        assert np.array_equal(sh >= 0, expect) and np.array_equal(sh, sho) and np.array_equal(prim, primo)
+        assert np.array_equal(t[expect].view(np.uint32), to[expect].view(np.uint32)) and np.array_equal(uv[expect], uvo[expect])
