@@ -436,6 +436,7 @@ def test_reference_shape_known_answers_through_the_abi(oracle_mod):
     """The reference's own hit tests (src/shapes/tests/test_rectangle.py:80-109, test_cube.py:26-69) through
     b200pt_ray_test / b200pt_ray_intersect: a 2-triangle and three 12-triangle scenes (the flat traversal), hits exactly where the
     reference asserts them, records bit-identical to the oracle."""
+    from mitsuba3_b200.integrators import device_scene
     d = mb.cornell_box()
     rays_of = lambda o, dirv: np.concatenate([np.asarray(o, np.float32), np.broadcast_to(np.asarray(dirv, np.float32), (len(o), 3)),
                                               np.full((len(o), 1), 3.4e38, np.float32)], axis=1)
