@@ -137,3 +137,35 @@ def test_anisotropic_mesh_with_packed_tangent_frames_matches_oracle(oracle_mod, 
     sc = mb.load_dict(tangent_mesh_scene(mat, tag, res=48, spp=16, max_depth=5))
     img = mb.render(sc, spp=16, seed=3)
     compare_images(img, oracle_mod.OracleScene(sc).render(spp=16, seed=3, mode=0), max_bad_frac=0.01)
+
+
+def test_reference_envmap_lookup_known_answers_through_the_abi():
+    """src/emitters/tests/test_envmap.py:201-263 through b200pt_env_query: exact texel-centre / align-corners read-back of a ramp,
+    continuity across the phi seam, clamping poles (the oracle passes the same checks in tests/test_oracle_golden.py)."""
+    from mitsuba3_b200.integrators import device_scene
+
+    def env_eval(img, u, v):
+        d = env_scene(img=np.asarray(img, np.float32))
+        d["sky"] = {"type": "envmap", "bitmap": np.asarray(img, np.float32)}
+        sc = mb.load_dict(d)
+        u, v = np.atleast_1d(np.asarray(u, np.float64)), np.atleast_1d(np.asarray(v, np.float64))
+        phi, theta = u * 2 * np.pi, v * np.pi
+        dirs = np.stack([np.sin(phi) * np.sin(theta), np.cos(theta), -np.cos(phi) * np.sin(theta)], 1).astype(np.float32)
+        q = np.concatenate([np.zeros((len(u), 3), np.float32), np.full((len(u), 2), 0.5, np.float32), dirs], 1)
+        return device_scene(sc).env_query(q)[:, 14:17]
+
+    W, H = 16, 8
+    img = np.broadcast_to(np.arange(W, dtype=np.float32)[None, :, None], (H, W, 3)).copy()
+    t = np.linspace(1.0 / W, 1.0 - 1.0 / W, 50)
+    assert np.abs(env_eval(img, t, np.full_like(t, 0.5))[:, 0] - (t * W - 0.5)).max() < 1e-4
+    W, H = 8, 16
+    img = np.broadcast_to(np.arange(H, dtype=np.float32)[:, None, None], (H, W, 3)).copy()
+    t = np.linspace(1.0 / H, 1.0 - 1.0 / H, 50)
+    assert np.abs(env_eval(img, np.zeros_like(t), t)[:, 0] - t * (H - 1)).max() < 1e-4
+    W, H = 64, 8
+    img = np.broadcast_to(np.cos(2 * np.pi * np.arange(W) / W).astype(np.float32)[None, :, None], (H, W, 3)).copy()
+    u = np.linspace(-0.1, 0.1, 201)
+    assert np.abs(env_eval(img, u, np.full_like(u, 0.5))[:, 0] - np.cos(2 * np.pi * ((u - np.floor(u)) * W - 0.5) / W)).max() < 5e-3
+    W, H = 8, 16
+    img = np.zeros((H, W, 3), np.float32); img[0] = 10.0; img[H - 1] = 20.0
+    assert abs(env_eval(img, 0.0, 0.0)[0, 0] - 10.0) < 1e-3 and abs(env_eval(img, 0.0, 1.0)[0, 0] - 20.0) < 1e-3
