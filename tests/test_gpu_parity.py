@@ -458,3 +458,14 @@ def test_reference_shape_known_answers_through_the_abi(oracle_mod):
         to, uvo, primo, sho = orc.ray_intersect(rays)
         assert np.array_equal(sh >= 0, expect) and np.array_equal(sh, sho) and np.array_equal(prim, primo)
         assert np.array_equal(t[expect].view(np.uint32), to[expect].view(np.uint32)) and np.array_equal(uv[expect], uvo[expect])
+
+
+def test_reference_diffuse_and_twosided_known_answers_through_the_abi():
+    """src/bsdfs/tests/test_diffuse.py:14-36, test_twosided.py:29-45 through b200pt_bsdf_eval_pdf_sample."""
+    from mitsuba3_b200.integrators import device_scene
+    from test_oracle_golden import _bsdf_known_answers
+
+    def query(spec, q):
+        sc, idx = _bsdf_scene(spec)
+        return device_scene(sc).bsdf_eval_pdf_sample(idx, q)
+    _bsdf_known_answers(query)
