@@ -146,6 +146,24 @@ def main(mode):
           img10 = oracle.OracleScene(host10).render(spp=8, seed=2, mode=1, max_depth=4)
           rel = np.abs(img10 - ref10) / np.maximum(np.abs(ref10), 1e-2)
           assert (rel.max(axis=2) > 1e-3).mean() < 0.01, (mirror, rel.max())
+      # src/render/tests/test_mesh_shading.py:398-420 (test10_uv_flip_bits): two triangles whose uv determinants have opposite
+      # signs -- the extractor's recomputed FaceUVFlipped bits and the oracle's bitangents against the live surface interactions
+      m = mi.Mesh("mirrored")
+      m.from_fields(faces=np.arange(6, dtype=np.uint32).reshape(2, 3),
+                    positions=np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0], [2, 0, 0], [3, 0, 0], [2, 1, 0]]),
+                    texcoords=np.float32([[0, 0], [1, 0], [0, 1], [0, 0], [0, 1], [1, 0]]),
+                    normals=np.tile(np.float32([0, 0, 1]), (6, 1)))
+      m.set_bsdf(mi.load_dict({"type": "roughconductor", "alpha_u": 0.05, "alpha_v": 0.3}))
+      assert m.packs_tangent()
+      d11 = cbox(32, {"type": "path", "max_depth": 4}); sm11 = mi.load_dict({"type": "scene", "sensor": d11["sensor"], "m": m})
+      host11 = plug.extract_scene(mi, sm11)
+      assert [int(f) >> 31 for f in host11.shapes[0].faces[:, 3]] == [0, 1]
+      o11 = oracle.OracleScene(host11)
+      for x, flipped in ((0.25, False), (2.25, True)):
+          si = sm11.ray_intersect(mi.Ray3f(mi.Point3f(x, 0.25, 1), mi.Vector3f(0, 0, -1)))
+          assert bool(si.frame_flipped) == flipped
+          rec = o11.surface_interaction(np.array([[x, 0.25, 1, 0, 0, -1, np.inf]], np.float32))[0]
+          assert np.abs(rec[10:13] - np.array(si.sh_frame.s)).max() < 2e-6 and np.abs(rec[13:16] - np.array(si.sh_frame.t)).max() < 2e-6
       plug.register(mi)
       integ = mi.load_dict({"type": "b200_path", "max_depth": 8})
       assert "max_depth = 8" in str(integ)
