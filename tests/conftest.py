@@ -245,3 +245,17 @@ def principled_glass_cbox(res=32, rfilter="box", spp=16, max_depth=8):
     d["small-box"]["to_world"] = mb.Transform4f().translate([0.335, -0.65, 0.38]).rotate([0, 1, 0], -17).scale(0.3)
     d["green-wall"]["bsdf"] = {"type": "ref", "id": "cloth"}
     return d
+
+
+def bsdf_known_answers(query):
+    """src/bsdfs/tests/test_diffuse.py:14-36 (test02_eval_pdf) and test_twosided.py:29-45 (test02_pdf): `query(spec, q)` evaluates
+    BSDF `spec` on rows q = wi (3), wo (3), uv (2), sample1, sample2 (2) and returns value (3), pdf, ..."""
+    theta = np.arange(20) / 19.0 * (np.pi / 2)
+    wo = np.stack([np.sin(theta), np.zeros(20), np.cos(theta)], 1)
+    q = np.concatenate([np.tile([0, 0, 1], (20, 1)), wo, np.zeros((20, 5))], 1).astype(np.float32)
+    out = query({"type": "diffuse"}, q)
+    assert np.allclose(out[:, 3], wo[:, 2] / np.pi, rtol=1e-5, atol=1e-7)                  # pdf = cos / pi
+    assert np.allclose(out[:, 0], 0.5 * wo[:, 2] / np.pi, rtol=1e-5, atol=1e-7)            # eval = 0.5 cos / pi (default reflectance)
+    q2 = np.array([[0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0], [0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0]], np.float32)
+    out = query({"type": "twosided", "bsdf": {"type": "diffuse"}}, q2)
+    assert np.isclose(out[0, 3], 1 / np.pi, rtol=1e-6) and out[1, 3] == 0.0

@@ -463,7 +463,7 @@ def test_reference_shape_known_answers_through_the_abi(oracle_mod):
 def test_reference_diffuse_and_twosided_known_answers_through_the_abi():
     """src/bsdfs/tests/test_diffuse.py:14-36, test_twosided.py:29-45 through b200pt_bsdf_eval_pdf_sample."""
     from mitsuba3_b200.integrators import device_scene
-    from test_oracle_golden import _bsdf_known_answers
+    from conftest import bsdf_known_answers as _bsdf_known_answers
 
     def query(spec, q):
         sc, idx = _bsdf_scene(spec)
