@@ -309,7 +309,7 @@ class _Extractor:
                 sp = mi.traverse(s)
                 if "to_world" in sp and verts.shape[0] == 4 and faces.shape[0] == 2:
                     # Rectangle: sampled by its parameterisation (rectangle.cpp:159-172)
-                    tw = Transform4f(_np(sp["to_world"].matrix))
+                    tw = Transform4f(_np(sp["to_world"].matrix).reshape(4, 4))
                     sh.sampling, sh.to_world = abi.SAMPLING_RECTANGLE, tw.matrix.copy()
                     sh.frame_n = _normalize(tw.normal([0, 0, 1])).astype(f32)
                     area = np.sqrt(_sqnorm(_cross(tw.vector([2, 0, 0]), tw.vector([0, 2, 0]))), dtype=f32)
@@ -342,7 +342,7 @@ class _Extractor:
         if not m:
             raise NotImplementedError("independent sampler: cannot read base_seed from its string form")
         self.out.sensor = SensorData(
-            sample_to_camera=_np(proj.inverse().matrix), to_world=_np(p["to_world"].matrix),
+            sample_to_camera=_np(proj.inverse().matrix).reshape(4, 4), to_world=_np(p["to_world"].matrix).reshape(4, 4),   # (JIT variants: width-1 arrays)
             near_clip=_f(p["near_clip"]), far_clip=_f(p["far_clip"]), film_size=tuple(size), crop_size=tuple(crop),
             crop_offset=tuple(off), rfilter=rfilter, rfilter_stddev=stddev, base_seed=int(m.group(1)) & 0xffffffff,
             sample_count=int(se.sampler().sample_count()), x_fov=_f(p["x_fov"]))
@@ -368,7 +368,7 @@ class _Extractor:
                 data = _np(ep["data"]).reshape(tuple(int(v) for v in ep["data"].shape))
                 if data.shape[2] != 3:
                     raise NotImplementedError("spectral environment maps are outside the hot-path scope")
-                tw = Transform4f(_np(ep["to_world"].matrix), _np(ep["to_world"].inverse_transpose))
+                tw = Transform4f(_np(ep["to_world"].matrix).reshape(4, 4), _np(ep["to_world"].inverse_transpose).reshape(4, 4))
                 t = TextureData(name=f"{eid}.data", channels=3)
                 t.kind, t.data = abi.TEX_BITMAP, np.ascontiguousarray(data[:, 1:-1, :], f32)
                 t.wrap, t.filter = abi.WRAP_CLAMP, abi.FILTER_BILINEAR

@@ -36,3 +36,5 @@ echo "$EMBREE" > "$BUILD/EMBREE_SETTING"
 # LLVM for llvm_ad_rgb: the image has no libLLVM.so; oracle/llvm_shim builds one over the
 # LLVM that llvmlite carries (see oracle/llvm_shim/README.md).
 if [ -f "$HERE/llvm_shim/Makefile" ]; then make -C "$HERE/llvm_shim" || echo "llvm shim not built (llvm_ad_rgb unavailable)"; fi
+# the compiled native integrator plugin (native/b200_path_native.cpp) goes next to the reference's own plugins
+if [ -x "$HERE/../native/build_shim.sh" ]; then "$HERE/../native/build_shim.sh" "$BUILD" || echo "native shim not built"; fi
